@@ -1,0 +1,163 @@
+/*
+ * wfacuda.h -- C ABI of libwfacuda.so, the B200 (sm_100a) wavefront-alignment
+ * hot path behind the shenwei356/wfa Go API.
+ *
+ * The reference has no FFI seam; the seam is its exported Go API and the cut
+ * goes through (*Aligner).AlignPointers (reference wfa.go:201-268): everything
+ * that function calls -- initComponents (:143-184), extend (:381-458), reduce
+ * (:461-540), next (:549-700), backtraceStartPosistion (:270-375), backTrace
+ * (:703-983) and AlignmentResult.AddN/process (wfa_cigar.go:118-214) -- runs on
+ * the GPU behind the entry points below.  INTEGRATION.md shows the cgo shim a
+ * maintainer adds to the Go package; wfa_b200/host/wfa.hpp and wfa_b200/api.py
+ * are the C++ and ctypes mirrors used here (no Go toolchain in this image).
+ *
+ * Plain C, plain pointers and sizes.  There is no CPU fallback: every entry
+ * point fails loudly (negative return + wfacuda_last_error) without a GPU.
+ *
+ * Threading: one ctx per (host thread, device).  A ctx is not re-entrant;
+ * different ctxs are independent (the reference's "one Aligner per goroutine",
+ * wfa.go:73-78).  Memory: the caller owns every buffer it passes; the library
+ * copies and keeps no caller pointer after a call returns (cgo pointer rule).
+ */
+#ifndef WFACUDA_H
+#define WFACUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WFACUDA_VERSION 1
+
+/* Per-pair status (wfacuda_result.status). */
+#define WFACUDA_OK               0
+#define WFACUDA_ERR_EMPTY_SEQ    1   /* ErrEmptySeq,   wfa.go:187, :204-206 */
+#define WFACUDA_ERR_SEQ_TOO_LONG 2   /* ErrSeqTooLong, wfa.go:193, :207-209 */
+#define WFACUDA_ERR_RESOURCES    3   /* pair needs more device memory than the ctx may use */
+
+/* Call-level return codes (0 = success). */
+#define WFACUDA_E_INVALID      (-1)  /* bad argument / config */
+#define WFACUDA_E_CUDA         (-2)  /* CUDA runtime error, no device, wrong arch */
+#define WFACUDA_E_NOMEM        (-3)  /* host or device allocation failed */
+#define WFACUDA_E_OPS_CAPACITY (-4)  /* caller's ops buffer too small; see wfacuda_batch_ops_total */
+
+/* MaxSeqLen, wfa.go:190: offsets carry 3 type bits in a uint32. */
+#define WFACUDA_MAX_SEQ_LEN ((1u << 29) - 1u)
+
+/* Penalties (wfa.go:32-36), Options (wfa.go:64-66) and the optional
+ * AdaptiveReductionOption (wfa.go:46-50) of one Aligner.  `adaptive` = 0 is the
+ * reference's algn.ad == nil.  Unlike the reference's pooled Aligner (wfa.go:
+ * 120-131, which keeps a stale `ad`), the setting is explicit per ctx. */
+typedef struct wfacuda_config {
+    uint32_t mismatch, gap_open, gap_ext;       /* DefaultPenalties = 4, 6, 2 (wfa.go:39-43) */
+    uint8_t  global_alignment;                  /* Options.GlobalAlignment */
+    uint8_t  adaptive;                          /* 1 after AdaptiveReduction() */
+    uint8_t  reserved_[2];
+    uint32_t min_wf_len, max_dist_diff;         /* 10, 50 by default (wfa.go:56-60) */
+    uint32_t cutoff_step;                       /* carried, unused -- as in the reference */
+    /* Tuning, 0 = automatic. */
+    uint32_t flags;                             /* WFACUDA_FLAG_* */
+    uint64_t arena_budget_bytes;                /* cap on the HBM backtrace arena */
+} wfacuda_config;
+
+/* Semi-global only: run to the global corner and search the start cell over
+ * all retained scores exactly like wfa.go:270-375, instead of stopping at the
+ * first score whose M wavefront touches the last row/column (same result). */
+#define WFACUDA_FLAG_SEMIGLOBAL_LITERAL 1u
+/* Force every pair through the CTA-per-pair kernel (testing). */
+#define WFACUDA_FLAG_FORCE_CTA          2u
+/* Force every pair through the 8-bit symbol path (testing). */
+#define WFACUDA_FLAG_FORCE_8BIT         4u
+
+/* AlignmentResult (wfa_cigar.go:29-46) after process() (wfa_cigar.go:136-214).
+ * tend/qend are 0 when the alignment has no match run (the reference leaves
+ * stale pool values there, wfa_cigar.go:77-89). */
+typedef struct wfacuda_result {
+    uint32_t score;
+    int32_t  tbegin, tend, qbegin, qend;
+    uint32_t align_len, matches, gaps, gap_regions;
+    uint32_t n_ops;
+    uint8_t  status;
+    uint8_t  reserved_[3];
+} wfacuda_result;
+
+/* Counters of the last batch (device-side work counts are the roofline
+ * numerators of SURVEY.md section 8d). */
+typedef struct wfacuda_stats {
+    uint64_t pairs;              /* pairs aligned on the GPU */
+    uint64_t cells;              /* C: sum over scores of the M wavefront width (Hi-Lo+1) before reduce */
+    uint64_t cells_written;      /* wavefront cells stored in the arena (x3 components x4 bytes) */
+    uint64_t score_steps;        /* existing scores processed */
+    uint64_t ops;                /* R: merged ops emitted */
+    uint64_t seq_bases;          /* sum n+m */
+    uint64_t arena_bytes;        /* arena allocated */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t kernel_launches;    /* launches of our kernels */
+    uint32_t align_launches;     /* of which wavefront kernels */
+    uint32_t retries;            /* pairs re-queued with a bigger arena / wider kernel */
+    uint32_t pairs_warp, pairs_cta, pairs_8bit;
+    float    ms_pack, ms_align, ms_total_device;   /* CUDA-event times on the ctx stream */
+} wfacuda_stats;
+
+typedef struct wfacuda_ctx   wfacuda_ctx;
+typedef struct wfacuda_batch wfacuda_batch;
+
+/* Number of usable sm_100 devices (0 if none; negative on CUDA error). */
+int wfacuda_device_count(void);
+
+/* wfa.New(p, opt) (+ AdaptiveReduction) -- wfa.go:120-140.  NULL on failure;
+ * wfacuda_last_error(NULL) then describes why. */
+wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg);
+/* RecycleAligner, wfa.go:102-116. */
+void wfacuda_destroy(wfacuda_ctx *ctx);
+/* Re-point an existing ctx at new penalties/options (wfa.New on a pooled Aligner). */
+int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg);
+
+/* (*Aligner).Align for many pairs (wfa.go:196-268), blocking, host buffers.
+ *   seq_bytes            byte pool holding all sequences (arbitrary bytes, case-sensitive)
+ *   q_off/q_len, t_off/t_len   per pair, offsets into seq_bytes
+ *   results[n_pairs]     filled for every pair (status says which are valid)
+ *   ops / ops_capacity   receives the concatenated AlignmentResult.Ops words
+ *                        (op<<32|n, already reversed + merged, wfa_cigar.go:32,123,136-169);
+ *                        may be NULL with capacity 0 to skip CIGARs
+ *   ops_off[n_pairs]     start of pair i's words in ops (pairs in index order)
+ * Returns 0, or a WFACUDA_E_* code.  On WFACUDA_E_OPS_CAPACITY results are
+ * valid and wfacuda_last_ops_total() tells the capacity needed. */
+int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                        const uint64_t *q_off, const uint32_t *q_len,
+                        const uint64_t *t_off, const uint32_t *t_len,
+                        wfacuda_result *results,
+                        uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off);
+uint64_t wfacuda_last_ops_total(const wfacuda_ctx *ctx);
+
+/* The same call split in three, so that a caller (or bench.py) can keep a
+ * batch resident in HBM: upload = H2D + planning, run = kernels only (inputs
+ * and outputs stay in HBM), download = D2H. */
+wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                                    const uint64_t *q_off, const uint32_t *q_len,
+                                    const uint64_t *t_off, const uint32_t *t_len);
+int  wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b);
+int  wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *results,
+                            uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off);
+uint64_t wfacuda_batch_ops_total(const wfacuda_batch *b);
+void wfacuda_batch_free(wfacuda_ctx *ctx, wfacuda_batch *b);
+
+/* One host thread per device, work-balanced static sharding, no collective
+ * (pairs are independent): the C side of AlignBatch over several GPUs. */
+int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs,
+                              const uint8_t *seq_bytes,
+                              const uint64_t *q_off, const uint32_t *q_len,
+                              const uint64_t *t_off, const uint32_t *t_len,
+                              wfacuda_result *results,
+                              uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off);
+
+int wfacuda_get_stats(const wfacuda_ctx *ctx, wfacuda_stats *out);
+/* Last error text of the ctx (or of the calling thread when ctx is NULL). */
+const char *wfacuda_last_error(const wfacuda_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WFACUDA_H */

@@ -1,0 +1,59 @@
+"""Shared helpers: run a batch through the GPU C ABI and through the oracle, compare bit-exactly."""
+import numpy as np
+
+import oracle_lib
+from wfa_b200 import api
+
+FIELDS = ["status", "score", "tbegin", "tend", "qbegin", "qend", "align_len", "matches", "gaps", "gap_regions", "n_ops"]
+
+
+def make_aligner(mismatch=4, gap_open=6, gap_ext=2, global_alignment=True, adaptive=None, **kw):
+    a = api.New(api.Penalties(mismatch, gap_open, gap_ext), api.Options(global_alignment), **kw)
+    if adaptive is not None:
+        a.AdaptiveReduction(api.AdaptiveReductionOption(adaptive[0], adaptive[1], 1))
+    return a
+
+
+def oracle_batch(batch, threads=8, **cfgkw):
+    cfg = oracle_lib.make_config(**cfgkw)
+    return oracle_lib.align_batch(cfg, batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len, threads=threads)
+
+
+def assert_same(batch, gpu, ref, what=""):
+    """gpu/ref = (results, ops, ops_off[, counters]).  TEnd/QEnd are only defined
+    when the alignment has a match run (reference leaves stale values otherwise)."""
+    gr, gops, goff = gpu[0], gpu[1], gpu[2]
+    rr, rops, roff = ref[0], ref[1], ref[2]
+    assert len(gr) == len(rr)
+    for f in FIELDS:
+        bad = np.nonzero(gr[f] != rr[f])[0]
+        if len(bad):
+            i = int(bad[0])
+            q, t = batch.pair(i)
+            gc = oracle_lib.ops_to_cigar(gops[int(goff[i]):int(goff[i]) + int(gr["n_ops"][i])]) if gr["status"][i] == 0 else "-"
+            rc = oracle_lib.ops_to_cigar(rops[int(roff[i]):int(roff[i]) + int(rr["n_ops"][i])])
+            raise AssertionError("%s: %d/%d pairs differ in %s; first pair %d (n=%d m=%d)\n gpu %s %s\n ref %s %s\n q=%r\n t=%r" % (
+                what, len(bad), len(gr), f, i, len(q), len(t), {k: int(gr[k][i]) for k in FIELDS}, gc,
+                {k: int(rr[k][i]) for k in FIELDS}, rc, q[:200], t[:200]))
+    ok = gr["status"] == 0
+    # ops: both laid out in index order
+    assert np.array_equal(goff[ok], roff[ok]), what + ": ops offsets differ"
+    assert len(gops) == len(rops), what + ": total op count differs"
+    if not np.array_equal(gops, rops):
+        d = int(np.nonzero(gops != rops)[0][0])
+        i = int(np.searchsorted(roff, d, side="right") - 1)
+        raise AssertionError("%s: ops differ first at word %d (pair %d)\n gpu %s\n ref %s" % (
+            what, d, i, oracle_lib.ops_to_cigar(gops[int(goff[i]):int(goff[i]) + int(gr['n_ops'][i])]),
+            oracle_lib.ops_to_cigar(rops[int(roff[i]):int(roff[i]) + int(rr['n_ops'][i])])))
+
+
+def check(batch, what="", threads=8, gpu_kw=None, **cfgkw):
+    a = make_aligner(**cfgkw, **(gpu_kw or {}))
+    try:
+        gpu = a.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)
+        stats = a.stats()
+    finally:
+        a.close()
+    ref = oracle_batch(batch, threads=threads, **cfgkw)
+    assert_same(batch, gpu, ref, what)
+    return gpu, ref, stats

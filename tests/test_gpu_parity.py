@@ -1,0 +1,133 @@
+"""GPU parity: libwfacuda.so (through the C ABI) vs the CPU oracle, bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+import parity
+from wfa_b200 import api, datagen
+
+pytestmark = pytest.mark.gpu
+
+README = [  # (kwargs, q, t, cigar, score) -- reference README.md:18-27, 101-124, 231-240, 245-254
+    (dict(global_alignment=False, adaptive=(10, 50)), b"Bioinformatics helps Biology", b"We learn bioinformatics to help biologists", "9I1X14M3I4M1D1M1X5M1X3I", 32),
+    (dict(adaptive=(10, 50)), b"ACCATACTCG", b"AGGATGCTCG", "1M2X2M1X4M", 12),
+    (dict(adaptive=(10, 50)), b"AGCTAGTGTCAATGGCTACTTTTCAGGTCCT", b"AACTAAGTGTCGGTGGCTACTATATATCAGGTCCT", "1M1X3M1I5M2X8M3I1M1X9M", 36),
+    (dict(adaptive=(10, 50)), b"ATTGGAAAATAGGATTGGGGTTTGTTTATATTTGGGTTGAGGGATGTCCCACCTTCGTCGTCCTTACGTTTCCGGAAGGGAGTGGTTAGCTCGAAGCCCA",
+     b"GATTGGAAAATAGGATGGGGTTTGTTTATATTTGGGTTGAGGGATGTCCCACCTTGTCGTCCTTACGTTTCCGGAAGGGAGTGGTTGCTCGAAGCCCA", "1X1I14M1D39M1D31M1D12M", 36),
+]
+
+
+def test_readme_goldens(built_lib):
+    for kw, q, t, cigar, score in README:
+        a = parity.make_aligner(**kw)
+        r = a.Align(q, t)
+        assert (r.CIGAR(False), r.Score) == (cigar, score)
+        api.RecycleAligner(a)
+
+
+def _mutate(rng, s, rate, alpha):
+    out = bytearray()
+    for c in s:
+        r = rng.random()
+        if r < rate / 3:
+            out.append(rng.choice(alpha))
+        elif r < 2 * rate / 3:
+            pass
+        elif r < rate:
+            out.append(c); out.append(rng.choice(alpha))
+        else:
+            out.append(c)
+    return bytes(out) or b"A"
+
+
+def _random_pairs(seed, count, alpha=b"ACGT", maxlen=120):
+    rng = random.Random(seed)
+    pairs = []
+    for it in range(count):
+        al = alpha if it % 3 else alpha[:2]
+        L = rng.choice([1, 2, 3, 5, 8, 13, 20, 40, 70, maxlen])
+        q = bytes(rng.choice(al) for _ in range(L))
+        mode = it % 4
+        if mode == 0:
+            t = _mutate(rng, q, 0.2, al)
+        elif mode == 1:
+            t = bytes(rng.choice(al) for _ in range(rng.randint(1, L + 10)))
+        elif mode == 2:
+            t = _mutate(rng, q, 0.05, al) + bytes(rng.choice(al) for _ in range(rng.randint(0, 20)))
+        else:
+            t = bytes(rng.choice(al) for _ in range(rng.randint(0, 15))) + _mutate(rng, q, 0.3, al)
+        pairs.append((q, t))
+    return pairs
+
+
+CONFIGS = [(glob, ad, pen) for glob in (True, False) for ad in (None, (10, 50), (3, 5), (1, 2), (5, 0))
+           for pen in ((4, 6, 2), (1, 0, 1), (3, 1, 2), (2, 3, 1), (5, 2, 3), (4, 4, 4), (7, 11, 3))]
+
+
+@pytest.mark.parametrize("cta", [False, True])
+def test_random_small_all_configs(built_lib, cta):
+    pairs = _random_pairs(7, 300)
+    batch = datagen.Batch.from_pairs(pairs)
+    for glob, ad, pen in CONFIGS:
+        parity.check(batch, what="glob=%s ad=%s pen=%s cta=%s" % (glob, ad, pen, cta), mismatch=pen[0], gap_open=pen[1],
+                     gap_ext=pen[2], global_alignment=glob, adaptive=ad,
+                     gpu_kw=dict(flags=api.FLAG_FORCE_CTA if cta else 0))
+
+
+def test_text_and_8bit_path(built_lib):
+    pairs = _random_pairs(11, 200, alpha=b"abcdefgh -N") + [(b"Bioinformatics helps Biology", b"We learn bioinformatics to help biologists"),
+                                                            (b"acgt", b"ACGT"), (b"ACGTN", b"ACGTN")]
+    batch = datagen.Batch.from_pairs(pairs)
+    for glob in (True, False):
+        for ad in (None, (3, 5)):
+            parity.check(batch, what="text glob=%s ad=%s" % (glob, ad), global_alignment=glob, adaptive=ad)
+    # forcing the 8-bit path on ACGT input must not change anything
+    batch = datagen.Batch.from_pairs(_random_pairs(12, 200))
+    parity.check(batch, what="force8", gpu_kw=dict(flags=api.FLAG_FORCE_8BIT))
+
+
+def test_semiglobal_literal_equals_early_stop(built_lib):
+    batch = datagen.Batch.from_pairs(_random_pairs(13, 300))
+    for ad in (None, (10, 50), (3, 5)):
+        parity.check(batch, what="semi literal ad=%s" % (ad,), global_alignment=False, adaptive=ad,
+                     gpu_kw=dict(flags=api.FLAG_SEMIGLOBAL_LITERAL))
+
+
+def test_errors_and_empty(built_lib):
+    a = parity.make_aligner()
+    res, errs = a.AlignBatch([b"", b"ACGT", b"A"], [b"ACGT", b"", b"A"])
+    assert errs[0] is api.ErrEmptySeq and errs[1] is api.ErrEmptySeq and errs[2] is None
+    assert res[2].CIGAR() == "1M"
+    with pytest.raises(api.WfaError):
+        a.Align(b"", b"A")
+    r, o, off = a.align_arrays(np.zeros(16, np.uint8), [], [], [], [])
+    assert len(r) == 0
+    api.RecycleAligner(a)
+    with pytest.raises(api.WfaError):
+        parity.make_aligner().AdaptiveReduction(api.AdaptiveReductionOption(0, 50, 1))
+
+
+@pytest.mark.parametrize("name,count", [("cfg2_150bp_e5_global", 20000), ("cfg3_1kbp_e10_global_adaptive", 2000),
+                                        ("cfg4_10kbp_in_12kbp_e5_semiglobal", 3), ("cfg5_100kbp_e15_global_adaptive", 2)])
+def test_synthetic_configs(built_lib, name, count):
+    c = datagen.CONFIGS[name]
+    batch = datagen.generate_config(name, count)
+    gpu, ref, stats = parity.check(batch, what=name, global_alignment=c["global_alignment"], adaptive=c["adaptive"])
+    # device work counter C must equal the oracle's (roofline numerator)
+    if c["global_alignment"]:
+        assert stats["cells"] == ref[3]["cells"], (stats, ref[3])
+
+
+def test_seqs_txt_config1(built_lib):
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "readme_vectors.json")))
+    pairs = [(p["q"].encode(), p["t"].encode()) for p in G["seqs_txt"]]
+    assert len(pairs) == 2
+    batch = datagen.Batch.from_pairs(pairs)
+    parity.check(batch, what="seqs.txt", adaptive=(10, 50))      # CLI defaults (wfa-go.go:96-106)
+    a = parity.make_aligner(adaptive=(10, 50))
+    r = a.Align(*pairs[0])
+    assert r.CIGAR() == "1X1I14M1D39M1D31M1D12M" and r.Score == 36
+    assert (r.QBegin, r.QEnd, r.TBegin, r.TEnd, r.AlignLen, r.Matches, r.Gaps, r.GapRegions) == (2, 100, 3, 98, 99, 96, 3, 3)

@@ -1,0 +1,343 @@
+"""Host-side mirror of the reference's Go API on top of the C ABI (ctypes).
+
+Names, argument meaning and error behaviour follow the reference package
+(/root/reference/wfa.go, wfa_cigar.go) so that tests read like the
+reference's own usage (README.md:153-216):
+
+    algn = wfa.New(wfa.Penalties(4, 6, 2), wfa.Options(GlobalAlignment=True))
+    algn.AdaptiveReduction(wfa.AdaptiveReductionOption(10, 50, 1))
+    result = algn.Align(q, t)          # -> AlignmentResult, raises ErrEmptySeq/ErrSeqTooLong
+    result.CIGAR(False); result.AlignmentText(q, t, False)
+    results, errors = algn.AlignBatch(qs, ts)      # new: many pairs per call
+    wfa.RecycleAlignmentResult(result); wfa.RecycleAligner(algn)
+
+This is the ctypes twin of the cgo shim shown in INTEGRATION.md (no Go
+toolchain exists in this image).  Every call goes to libwfacuda.so; there is
+no CPU fallback: without the built library or without a GPU it raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwfacuda.so")
+
+MaxSeqLen = (1 << 29) - 1                      # wfa.go:190
+
+
+class WfaError(Exception):
+    pass
+
+
+class _ErrEmptySeq(WfaError):
+    pass
+
+
+class _ErrSeqTooLong(WfaError):
+    pass
+
+
+ErrEmptySeq = _ErrEmptySeq("wfa: invalid empty sequence")                                     # wfa.go:187
+ErrSeqTooLong = _ErrSeqTooLong("wfa: sequences longer than %d are not supported" % MaxSeqLen)  # wfa.go:193
+ErrResources = WfaError("wfacuda: pair needs more device memory than available")
+
+
+class Penalties:                                # wfa.go:32-36
+    def __init__(self, Mismatch=4, GapOpen=6, GapExt=2):
+        self.Mismatch, self.GapOpen, self.GapExt = Mismatch, GapOpen, GapExt
+
+
+class AdaptiveReductionOption:                  # wfa.go:46-50
+    def __init__(self, MinWFLen=10, MaxDistDiff=50, CutoffStep=1):
+        self.MinWFLen, self.MaxDistDiff, self.CutoffStep = MinWFLen, MaxDistDiff, CutoffStep
+
+
+class Options:                                  # wfa.go:64-66
+    def __init__(self, GlobalAlignment=True):
+        self.GlobalAlignment = GlobalAlignment
+
+
+DefaultPenalties = Penalties(4, 6, 2)           # wfa.go:39-43
+DefaultAdaptiveOption = AdaptiveReductionOption(10, 50, 1)   # wfa.go:56-60
+DefaultOptions = Options(True)                  # wfa.go:69-71
+
+OpM, OpD, OpI, OpX, OpH = (ord(c) for c in "MDIXH")   # wfa_cigar.go:60-64
+MaskLower32 = 4294967295
+
+FLAG_SEMIGLOBAL_LITERAL = 1
+FLAG_FORCE_CTA = 2
+FLAG_FORCE_8BIT = 4
+
+
+class _Config(C.Structure):
+    _fields_ = [("mismatch", C.c_uint32), ("gap_open", C.c_uint32), ("gap_ext", C.c_uint32),
+                ("global_alignment", C.c_uint8), ("adaptive", C.c_uint8), ("reserved_", C.c_uint8 * 2),
+                ("min_wf_len", C.c_uint32), ("max_dist_diff", C.c_uint32), ("cutoff_step", C.c_uint32),
+                ("flags", C.c_uint32), ("arena_budget_bytes", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("pairs", C.c_uint64), ("cells", C.c_uint64), ("cells_written", C.c_uint64),
+                ("score_steps", C.c_uint64), ("ops", C.c_uint64), ("seq_bases", C.c_uint64),
+                ("arena_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("kernel_launches", C.c_uint32), ("align_launches", C.c_uint32), ("retries", C.c_uint32),
+                ("pairs_warp", C.c_uint32), ("pairs_cta", C.c_uint32), ("pairs_8bit", C.c_uint32),
+                ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_total_device", C.c_float)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+RESULT_DTYPE = np.dtype([("score", "<u4"), ("tbegin", "<i4"), ("tend", "<i4"), ("qbegin", "<i4"),
+                         ("qend", "<i4"), ("align_len", "<u4"), ("matches", "<u4"), ("gaps", "<u4"),
+                         ("gap_regions", "<u4"), ("n_ops", "<u4"), ("status", "u1"), ("reserved_", "u1", 3)])
+
+EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda_set_config",
+           "wfacuda_align_batch", "wfacuda_last_ops_total", "wfacuda_batch_upload", "wfacuda_batch_run",
+           "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
+           "wfacuda_align_batch_multi", "wfacuda_get_stats", "wfacuda_last_error"]
+
+_LIB = None
+
+
+def load_library():
+    """dlopen libwfacuda.so (never a fallback: a missing library is an error)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise WfaError("libwfacuda.so is not built (run `python -m wfa_b200.build`); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32p = C.c_void_p, C.c_uint64, C.c_void_p
+    L.wfacuda_device_count.restype = C.c_int
+    L.wfacuda_create.restype = vp
+    L.wfacuda_create.argtypes = [C.c_int, C.POINTER(_Config)]
+    L.wfacuda_destroy.argtypes = [vp]
+    L.wfacuda_set_config.restype = C.c_int
+    L.wfacuda_set_config.argtypes = [vp, C.POINTER(_Config)]
+    L.wfacuda_align_batch.restype = C.c_int
+    L.wfacuda_align_batch.argtypes = [vp, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
+    L.wfacuda_last_ops_total.restype = u64
+    L.wfacuda_last_ops_total.argtypes = [vp]
+    L.wfacuda_batch_upload.restype = vp
+    L.wfacuda_batch_upload.argtypes = [vp, u64, vp, vp, u32p, vp, u32p]
+    L.wfacuda_batch_run.restype = C.c_int
+    L.wfacuda_batch_run.argtypes = [vp, vp]
+    L.wfacuda_batch_download.restype = C.c_int
+    L.wfacuda_batch_download.argtypes = [vp, vp, vp, vp, u64, vp]
+    L.wfacuda_batch_ops_total.restype = u64
+    L.wfacuda_batch_ops_total.argtypes = [vp]
+    L.wfacuda_batch_free.argtypes = [vp, vp]
+    L.wfacuda_align_batch_multi.restype = C.c_int
+    L.wfacuda_align_batch_multi.argtypes = [C.POINTER(vp), C.c_int, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
+    L.wfacuda_get_stats.restype = C.c_int
+    L.wfacuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.wfacuda_last_error.restype = C.c_char_p
+    L.wfacuda_last_error.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def device_count():
+    return load_library().wfacuda_device_count()
+
+
+class AlignmentResult:
+    """wfa_cigar.go:29-46 (after process(), :136-214)."""
+    __slots__ = ("Ops", "Score", "TBegin", "TEnd", "QBegin", "QEnd", "AlignLen", "Matches", "Gaps", "GapRegions")
+
+    def __init__(self, rec, ops):
+        self.Ops = ops                          # numpy uint64 view: op<<32 | n
+        self.Score = int(rec["score"])
+        self.TBegin, self.TEnd = int(rec["tbegin"]), int(rec["tend"])
+        self.QBegin, self.QEnd = int(rec["qbegin"]), int(rec["qend"])
+        self.AlignLen, self.Matches = int(rec["align_len"]), int(rec["matches"])
+        self.Gaps, self.GapRegions = int(rec["gaps"]), int(rec["gap_regions"])
+
+    def CIGAR(self, onlyAignedRegion=False):    # wfa_cigar.go:236-255
+        ops = trimOps(self.Ops) if onlyAignedRegion else self.Ops
+        return "".join("%d%s" % (int(op) & MaskLower32, chr(int(op) >> 32)) for op in ops)
+
+    def AlignmentText(self, q, t, onlyAignedRegion=False):      # wfa_cigar.go:259-333
+        ops = self.Ops
+        if onlyAignedRegion:
+            q = q[self.QBegin - 1:self.QEnd]
+            t = t[self.TBegin - 1:self.TEnd]
+            ops = trimOps(ops)
+        Q, A, T = bytearray(), bytearray(), bytearray()
+        v = h = 0
+        for op in ops:
+            n, o = int(op) & MaskLower32, int(op) >> 32
+            if o == OpM or o == OpX:
+                Q += q[v:v + n]; A += (b"|" if o == OpM else b" ") * n; T += t[h:h + n]; v += n; h += n
+            elif o == OpI:
+                Q += b"-" * n; A += b" " * n; T += t[h:h + n]; h += n
+            elif o == OpD or o == OpH:
+                Q += q[v:v + n]; A += b" " * n; T += b"-" * n; v += n
+        return bytes(Q), bytes(A), bytes(T)
+
+
+def Op(op):                                     # wfa_cigar.go:56-58
+    return chr(int(op) >> 32), int(op) & MaskLower32
+
+
+def trimOps(ops):                               # wfa_cigar.go:217-233
+    start = end = -1
+    for i in range(len(ops)):
+        if int(ops[i]) >> 32 == OpM:
+            start = i
+            break
+    for i in range(len(ops) - 1, -1, -1):
+        if int(ops[i]) >> 32 == OpM:
+            end = i
+            break
+    return ops[start:end + 1]
+
+
+class Aligner:
+    """wfa.go:79-268 backed by one wfacuda ctx (one Aligner per thread, wfa.go:73-78)."""
+
+    def __init__(self, p, opt, device=0, flags=0, arena_budget_bytes=0):
+        self.p, self.opt, self.ad = p, opt, None
+        self._flags, self._budget, self._device = flags, arena_budget_bytes, device
+        self._L = load_library()
+        cfg = self._config()
+        self._ctx = self._L.wfacuda_create(device, C.byref(cfg))
+        if not self._ctx:
+            raise WfaError((self._L.wfacuda_last_error(None) or b"wfacuda_create failed").decode())
+
+    def _config(self):
+        c = _Config()
+        c.mismatch, c.gap_open, c.gap_ext = self.p.Mismatch, self.p.GapOpen, self.p.GapExt
+        c.global_alignment = 1 if self.opt.GlobalAlignment else 0
+        c.adaptive = 0 if self.ad is None else 1
+        if self.ad is not None:
+            c.min_wf_len, c.max_dist_diff, c.cutoff_step = self.ad.MinWFLen, self.ad.MaxDistDiff, self.ad.CutoffStep
+        c.flags, c.arena_budget_bytes = self._flags, self._budget
+        return c
+
+    def _err(self):
+        return (self._L.wfacuda_last_error(self._ctx) or b"").decode()
+
+    def AdaptiveReduction(self, ad):            # wfa.go:134-140
+        if ad.MinWFLen == 0:
+            raise WfaError("cutoff step should not be 0")
+        self.ad = ad
+        cfg = self._config()
+        if self._L.wfacuda_set_config(self._ctx, C.byref(cfg)) != 0:
+            raise WfaError(self._err())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.wfacuda_destroy(self._ctx)
+            self._ctx = None
+
+    __del__ = close
+
+    # ---- batched entry point (new API) -------------------------------------
+    def align_arrays(self, seq_bytes, q_off, q_len, t_off, t_len, want_ops=True):
+        """Raw C-ABI call on numpy arrays -> (results, ops, ops_off)."""
+        n = len(q_len)
+        seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
+        q_off = np.ascontiguousarray(q_off, np.uint64); t_off = np.ascontiguousarray(t_off, np.uint64)
+        q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
+        results = np.zeros(n, RESULT_DTYPE)
+        ops_off = np.zeros(n, np.uint64)
+        cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64 if want_ops else 0
+        while True:
+            ops = np.empty(max(cap, 1), np.uint64)
+            rc = self._L.wfacuda_align_batch(self._ctx, n, seq_bytes.ctypes.data, q_off.ctypes.data, q_len.ctypes.data,
+                                             t_off.ctypes.data, t_len.ctypes.data, results.ctypes.data,
+                                             ops.ctypes.data if want_ops else None, cap, ops_off.ctypes.data)
+            if rc == -4:                        # WFACUDA_E_OPS_CAPACITY
+                cap = int(self._L.wfacuda_last_ops_total(self._ctx))
+                continue
+            if rc != 0:
+                raise WfaError("wfacuda_align_batch failed (%d): %s" % (rc, self._err()))
+            total = int(self._L.wfacuda_last_ops_total(self._ctx)) if want_ops else 0
+            return results, ops[:total], ops_off
+
+    def AlignBatch(self, qs, ts):
+        """[]*AlignmentResult, []error for many pairs in one call."""
+        from .datagen import Batch
+        b = Batch.from_pairs(zip(qs, ts))
+        results, ops, ops_off = self.align_arrays(b.seq_bytes, b.q_off, b.q_len, b.t_off, b.t_len)
+        out, errs = [], []
+        for i in range(len(results)):
+            st = int(results["status"][i])
+            if st == 0:
+                a = int(ops_off[i])
+                out.append(AlignmentResult(results[i], ops[a:a + int(results["n_ops"][i])]))
+                errs.append(None)
+            else:
+                out.append(None)
+                errs.append({1: ErrEmptySeq, 2: ErrSeqTooLong}.get(st, ErrResources))
+        return out, errs
+
+    def Align(self, q, t):                      # wfa.go:196-198
+        res, errs = self.AlignBatch([q], [t])
+        if errs[0] is not None:
+            raise errs[0]
+        return res[0]
+
+    def stats(self):
+        st = Stats()
+        self._L.wfacuda_get_stats(self._ctx, C.byref(st))
+        return st.as_dict()
+
+
+def New(p=DefaultPenalties, opt=DefaultOptions, **kw):          # wfa.go:120-131
+    return Aligner(p, opt, **kw)
+
+
+def RecycleAligner(algn):                       # wfa.go:102-116
+    if algn is not None:
+        algn.close()
+
+
+def RecycleAlignmentResult(cigar):              # wfa_cigar.go:92-96 (nothing to pool here)
+    return None
+
+
+def RecycleAlignmentText(Q, A, T):              # wfa_cigar.go:346-360
+    return None
+
+
+class ResidentBatch:
+    """upload / run / download split (wfacuda_batch_*): keeps a batch in HBM."""
+
+    def __init__(self, algn, seq_bytes, q_off, q_len, t_off, t_len):
+        self.algn, self.n = algn, len(q_len)
+        self._keep = [np.ascontiguousarray(seq_bytes, np.uint8), np.ascontiguousarray(q_off, np.uint64),
+                      np.ascontiguousarray(q_len, np.uint32), np.ascontiguousarray(t_off, np.uint64),
+                      np.ascontiguousarray(t_len, np.uint32)]
+        s, qo, ql, to, tl = self._keep
+        self._b = algn._L.wfacuda_batch_upload(algn._ctx, self.n, s.ctypes.data, qo.ctypes.data, ql.ctypes.data,
+                                               to.ctypes.data, tl.ctypes.data)
+        if not self._b:
+            raise WfaError("wfacuda_batch_upload failed: " + algn._err())
+
+    def run(self):
+        rc = self.algn._L.wfacuda_batch_run(self.algn._ctx, self._b)
+        if rc != 0:
+            raise WfaError("wfacuda_batch_run failed (%d): %s" % (rc, self.algn._err()))
+
+    def download(self, want_ops=True):
+        L = self.algn._L
+        results = np.zeros(self.n, RESULT_DTYPE)
+        ops_off = np.zeros(self.n, np.uint64)
+        total = int(L.wfacuda_batch_ops_total(self._b)) if want_ops else 0
+        ops = np.empty(max(total, 1), np.uint64)
+        rc = L.wfacuda_batch_download(self.algn._ctx, self._b, results.ctypes.data,
+                                      ops.ctypes.data if want_ops else None, total, ops_off.ctypes.data)
+        if rc != 0:
+            raise WfaError("wfacuda_batch_download failed (%d): %s" % (rc, self.algn._err()))
+        return results, ops[:total], ops_off
+
+    def free(self):
+        if self._b:
+            self.algn._L.wfacuda_batch_free(self.algn._ctx, self._b)
+            self._b = None
+
+    __del__ = free

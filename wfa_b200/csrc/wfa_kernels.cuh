@@ -1,0 +1,782 @@
+/*
+ * wfa_kernels.cuh -- device code of libwfacuda.so (sm_100a).
+ *
+ * One "worker" aligns one pair at a time: a warp (WARP kernel: diagonals are
+ * strided over the 32 lanes, the last max(x,o+e)/g+1 score rows of M and the
+ * last e/g+1 rows of I/D live in a per-warp shared-memory ring, no block
+ * barrier anywhere) or a whole CTA (CTA kernel: diagonals strided over the
+ * block, source rows re-read from the HBM arena through L1/L2).  Workers are
+ * persistent and pull pairs from an atomic queue sorted by decreasing cost.
+ *
+ * Every (score, diagonal) cell of M, I and D is written exactly once, as the
+ * reference's raw word offset<<3|code, to the worker's slot of the HBM
+ * backtrace arena; `next` and `extend` are fused per cell (the value stored
+ * for M is the extended one, as after the reference's Increase).  Backtrace
+ * and CIGAR emission follow the reference's control flow literally and run on
+ * the same worker right after the forward pass.
+ *
+ * Semantics follow the reference at /root/reference (cited per function as
+ * wfa.go:LINE etc.); equivalences used instead of a literal translation are
+ * argued in DESIGN.md section 4.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wfak {
+
+/* wfa_backtrace_types.go:23-37 */
+constexpr uint32_t T_BITS = 3, T_MASK = 7;
+enum : uint32_t { T_INS_OPEN = 1, T_INS_EXT = 2, T_DEL_OPEN = 3, T_DEL_EXT = 4, T_MISMATCH = 5, T_MATCH = 6 };
+
+/* internal per-pair states (>= 100 never leave the library) */
+enum : uint8_t { ST_OK = 0, ST_EMPTY = 1, ST_TOO_LONG = 2, ST_RESOURCES = 3,
+                 ST_ARENA = 100, ST_RING = 101, ST_OPS = 102, ST_PENDING = 255 };
+
+struct PairDesc {
+    uint64_t q_byte, t_byte;   /* byte offsets into the raw sequence pool */
+    uint64_t q_word, t_word;   /* word offsets into the 2-bit packed pool */
+    uint32_t n, m;             /* len(q), len(t) */
+};
+
+/* One score's wavefront row in a worker's arena slot.  Cells of M, I, D for
+ * diagonals [alo, alo+aw) sit at word offsets off, off+aw, off+2*aw.  [lo,hi]
+ * is the reference's M WaveFront.Lo/Hi *after* reduce: a cell outside it reads
+ * as absent (that is what reduce's Delete calls achieve, wfa.go:526-537).
+ * lo > hi means the score does not exist (HasScore false). */
+struct RowHdr {
+    int32_t  alo, aw, lo, hi;
+    uint64_t off;
+};
+
+struct Result {                /* == wfacuda_result */
+    uint32_t score;
+    int32_t  tbegin, tend, qbegin, qend;
+    uint32_t align_len, matches, gaps, gap_regions;
+    uint32_t n_ops;
+    uint8_t  status;
+    uint8_t  pad_[3];
+};
+
+struct Counters {              /* device-side work counters, one set per launch */
+    unsigned long long cells, cells_written, steps, ops, retry_n, ops_cursor, work_next, arena_used_max;
+};
+
+struct KParams {
+    const PairDesc *pairs;
+    const uint32_t *work;      /* pair indices, decreasing cost */
+    uint32_t        n_work;
+    const uint32_t *packed;    /* 2-bit pool */
+    const uint32_t *raw;       /* byte pool viewed as words (base is 16-byte aligned) */
+    const uint8_t  *pflags;    /* bit0: pair has a non-ACGT byte -> 8-bit path */
+    uint8_t        *arena;
+    uint64_t        slot_bytes;
+    Result         *results;
+    uint64_t       *ops_pool;  /* completion-order pool */
+    uint64_t        ops_cap;
+    uint64_t       *ops_where; /* per pair: start in ops_pool */
+    uint64_t       *retry;     /* status<<32 | pair for pairs that ran out of arena / ring / pool */
+    Counters       *ctr;
+    /* penalties: raw and divided by g = gcd(x, o+e, e) */
+    uint32_t x, oe, e, g;
+    int32_t  xg, oeg, eg;
+    int32_t  dM, dE;           /* ring depths: max(xg,oeg)+1, eg+1 */
+    int32_t  ring_cap;         /* diagonals per ring row (WARP kernel) */
+    uint8_t  global_aln, adaptive, semi_literal, force8;
+    int32_t  min_wf_len, max_dist_diff;
+};
+
+/* ------------------------------------------------------------------ sequences
+ * 2-bit mode: 16 bases per 32-bit word, base i in bits 2(i%16)..; code =
+ * (byte>>1)&3 (A=0 C=1 T=2 G=3), only used when every byte of the pair is one
+ * of "ACGT" so that code equality == byte equality (wfa.go:408-454 compares
+ * raw bytes).  8-bit mode reads the caller's bytes unchanged. */
+template <int BITS> struct SeqView {
+    const uint32_t *w;   /* word holding symbol 0 (aligned down) */
+    uint32_t        mis; /* symbols before symbol 0 inside that word (8-bit mode only) */
+    static constexpr int PER_WORD = 32 / BITS;
+    __device__ __forceinline__ uint32_t sym(int i) const {
+        uint32_t j = (uint32_t)i + mis;
+        return (__ldg(w + j / PER_WORD) >> ((j % PER_WORD) * BITS)) & ((1u << BITS) - 1u);
+    }
+    /* PER_WORD symbols starting at symbol i, symbol i in the low bits */
+    __device__ __forceinline__ uint32_t chunk(int i) const {
+        uint32_t j = (uint32_t)i + mis, wi = j / PER_WORD;
+        return __funnelshift_r(__ldg(w + wi), __ldg(w + wi + 1), (j % PER_WORD) * BITS);
+    }
+};
+
+/* Longest common prefix of q[v:] and t[h:], at most maxl symbols: exactly what
+ * the reference's 8-byte block loop + byte loop compute (wfa.go:411-454),
+ * here 16 bases (or 4 bytes) per XOR + find-first-set step. */
+template <int BITS>
+__device__ __forceinline__ int lcp(const SeqView<BITS> &Q, const SeqView<BITS> &T, int v, int h, int maxl)
+{
+    constexpr int PW = 32 / BITS;
+    int l = 0;
+    while (l < maxl) {
+        uint32_t x = Q.chunk(v + l) ^ T.chunk(h + l);
+        if (x) { l += (__ffs((int)x) - 1) / BITS; break; }
+        l += PW;
+    }
+    return l < maxl ? l : maxl;
+}
+
+/* ------------------------------------------------------------------ next
+ * One diagonal of wfa.go:572-699.  Inputs are raw source words (0 = absent):
+ *   mo_l = M[s-o-e][k-1]  ie_l = I[s-e][k-1]
+ *   mo_r = M[s-o-e][k+1]  de_r = D[s-e][k+1]   mx = M[s-x][k]
+ * Validity uses '>' exactly like the reference (:581,:585,:616,:620,:651), so
+ * the one-past-the-end phantom cells are produced identically. */
+struct Cell3 { uint32_t M, I, D; };
+
+__device__ __forceinline__ Cell3 next_cell(uint32_t mo_l, uint32_t ie_l, uint32_t mo_r, uint32_t de_r,
+                                           uint32_t mx, int k, int n, int m)
+{
+    Cell3 r;
+    /* insertion (:579-609) */
+    uint32_t a = mo_l >> T_BITS, b = ie_l >> T_BITS;
+    bool fa = mo_l != 0 && (int)a <= m, fb = ie_l != 0 && (int)b <= m;
+    a = fa ? a : 0; b = fb ? b : 0;
+    const bool updI = fa || fb;
+    const uint32_t Isk = updI ? max(a, b) + 1 : 0;
+    const uint32_t tI = (fa && (!fb || a >= b)) ? T_INS_OPEN : T_INS_EXT;
+    r.I = updI ? (Isk << T_BITS | tI) : 0;
+    /* deletion (:614-645) */
+    a = mo_r >> T_BITS; b = de_r >> T_BITS;
+    fa = mo_r != 0 && (int)a - k <= n; fb = de_r != 0 && (int)b - k <= n;
+    a = fa ? a : 0; b = fb ? b : 0;
+    const bool updD = fa || fb;
+    const uint32_t Dsk = updD ? max(a, b) : 0;
+    const uint32_t tD = (fa && (!fb || a >= b)) ? T_DEL_OPEN : T_DEL_EXT;
+    r.D = updD ? (Dsk << T_BITS | tD) : 0;
+    /* mismatch + provenance priority Mismatch > I > D on ties (:650-698) */
+    uint32_t c = mx >> T_BITS;
+    const bool fx = mx != 0 && (int)c <= m && (int)c - k <= n;
+    c = fx ? c : 0;
+    const uint32_t Msk = max(max(Isk, Dsk), c + 1);
+    uint32_t tM;
+    if (fx && Msk == c + 1) tM = T_MISMATCH;
+    else if (updI && (Msk == Isk || !updD)) tM = tI;
+    else tM = tD;
+    r.M = (updI || updD || fx) ? (Msk << T_BITS | tM) : 0;
+    return r;
+}
+
+/* distance-to-end of one M cell for reduce, -1 = not counted (wfa.go:474-494) */
+__device__ __forceinline__ int dist_of(uint32_t raw, int k, int n, int m)
+{
+    if (raw == 0) return -1;
+    const int h = (int)(raw >> T_BITS), v = h - k;
+    if (v < 0 || v >= n || h >= m) return -1;
+    return max(m - h, n - v);
+}
+
+/* start-cell classification for semi-global (wfa.go:306-323 / :341-358):
+ * 0 = keep scanning, 1 = scan stops without a hit, 2 = hit */
+__device__ __forceinline__ int hit_class(uint32_t raw, int k, int n, int m)
+{
+    if (raw == 0) return 0;
+    const int h = (int)(raw >> T_BITS), v = h - k;
+    if (v <= 0 || v > n || h > m) return 1;
+    if ((v == n && h >= n) || (h == m && v >= m)) return 2;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ groups
+ * A worker is a warp (CTA=false) or a block (CTA=true). */
+template <bool CTA> struct Grp {
+    __device__ static __forceinline__ int tid()  { return CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31); }
+    __device__ static __forceinline__ int size() { return CTA ? (int)blockDim.x : 32; }
+    __device__ static __forceinline__ void sync() { if (CTA) __syncthreads(); else __syncwarp(); }
+    /* all-reduce of (min a, max b, or c) over the group; red = 3*32 ints of block scratch */
+    __device__ static __forceinline__ void reduce3(int &a, int &b, int &c, int *red)
+    {
+        a = __reduce_min_sync(0xffffffffu, a);
+        b = __reduce_max_sync(0xffffffffu, b);
+        c = (int)__reduce_or_sync(0xffffffffu, (unsigned)c);
+        if (CTA) {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+            __syncthreads();                     /* scratch free again */
+            if (lane == 0) { red[wid] = a; red[32 + wid] = b; red[64 + wid] = c; }
+            __syncthreads();
+            a = lane < nw ? red[lane] : INT_MAX;
+            b = lane < nw ? red[32 + lane] : INT_MIN;
+            c = lane < nw ? red[64 + lane] : 0;
+            a = __reduce_min_sync(0xffffffffu, a);
+            b = __reduce_max_sync(0xffffffffu, b);
+            c = (int)__reduce_or_sync(0xffffffffu, (unsigned)c);
+        }
+    }
+    template <typename T> __device__ static __forceinline__ T bcast0(T v, T *slot)
+    {
+        if (CTA) {
+            __syncthreads();
+            if (threadIdx.x == 0) *slot = v;
+            __syncthreads();
+            return *slot;
+        } else {
+            return __shfl_sync(0xffffffffu, v, 0);
+        }
+    }
+};
+
+/* ------------------------------------------------------------------ arena reads for backtrace
+ * Component.Get / GetRaw (wfa_component.go:142-155) on the arena.  `s` is the
+ * reference's uint32 score arithmetic carried in 64 bits: a wrapped value
+ * (s - diff with diff > s) is >= len(WaveFronts) there, i.e. absent. */
+struct ArenaView {
+    const RowHdr   *hdr;
+    const uint32_t *cells;
+    int64_t         s_last;    /* highest score with a header */
+    uint32_t        g;
+    __device__ __forceinline__ uint32_t get(int comp, int64_t s, int k) const
+    {
+        if (s < 0 || s > s_last || (s % g) != 0) return 0;
+        const RowHdr h = hdr[s / g];
+        if (k < h.lo || k > h.hi) return 0;
+        return cells[h.off + (uint64_t)comp * (uint32_t)h.aw + (uint32_t)(k - h.alo)];
+    }
+};
+
+/* Reversed, run-merged op emitter: AddN (wfa_cigar.go:118-124) followed by
+ * process()'s merge of equal neighbours (:147-166); merging commutes with the
+ * reversal, so runs are merged as they are produced. */
+struct OpSink {
+    uint64_t *buf; uint32_t cap, n; uint32_t cur_op, cur_n; bool overflow;
+    __device__ __forceinline__ void add(uint32_t op, uint32_t cnt)
+    {
+        if (op == cur_op) { cur_n += cnt; return; }
+        flush();
+        cur_op = op; cur_n = cnt;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (cur_op == 0) return;
+        if (n < cap) buf[n] = (uint64_t)cur_op << 32 | cur_n; else overflow = true;
+        n++;
+        cur_op = 0;
+    }
+};
+
+__device__ __forceinline__ uint32_t op_of_type(uint32_t t)
+{
+    /* wfaOps = ". I I D D X M H" (wfa_backtrace_types.go:37) */
+    return (uint32_t)(".IIDDXMH"[t & 7]);
+}
+
+/* backTrace, wfa.go:703-983, executed by one thread.  Returns ops (reversed
+ * order, merged) in sink; fills score/begin/end of res. */
+__device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, int n, int m,
+                                        uint32_t s0, int Ak, Result &res, OpSink &sink)
+{
+    const bool semi = !P.global_aln;
+    const int64_t x = P.x, oe = P.oe, e = P.e;
+    int64_t s = s0;
+    res.score = s0;
+    res.tbegin = res.tend = res.qbegin = res.qend = 0;
+    int k = Ak, h, v, tBegin = 0, qBegin = 0;
+    bool firstMatch = true, previousFromM = true, fromItself = false;
+    uint32_t offset0 = 0, Isk = 0, Dsk = 0;
+    int M0 = 0;                                   /* component of the next cell: 0 M, 1 I, 2 D */
+
+    uint32_t raw = A.get(0, s, k);                /* :738 */
+    uint32_t type = raw & T_MASK;
+    h = (int)(raw >> T_BITS);
+    v = h - k;
+    if (h < m) sink.add('I', (uint32_t)m - (uint32_t)h);          /* :746-750 */
+    else if (v < n) sink.add('H', (uint32_t)n - (uint32_t)v);
+
+    while (v > 0 && h > 0) {                      /* :753 */
+        const int64_t sX = s - x, sO = s - oe, sE = s - e;
+        if (type == T_INS_EXT) {                  /* :767-777 */
+            const uint32_t r1 = A.get(0, sO, k - 1), r2 = A.get(1, sE, k - 1);
+            offset0 = (r1 | r2) ? max(r1 >> T_BITS, r2 >> T_BITS) + 1 : 0;
+            M0 = 1;
+        } else if (type == T_DEL_EXT) {           /* :778-788 */
+            const uint32_t r1 = A.get(0, sO, k + 1), r2 = A.get(2, sE, k + 1);
+            offset0 = (r1 | r2) ? max(r1 >> T_BITS, r2 >> T_BITS) : 0;
+            M0 = 2;
+        } else {                                  /* :789-817 */
+            const uint32_t r1 = A.get(0, sO, k - 1), r2 = A.get(1, sE, k - 1);
+            const uint32_t r3 = A.get(0, sO, k + 1), r4 = A.get(2, sE, k + 1);
+            const uint32_t r5 = A.get(0, sX, k);
+            Isk = (r1 | r2) ? max(r1 >> T_BITS, r2 >> T_BITS) + 1 : 0;
+            Dsk = (r3 | r4) ? max(r3 >> T_BITS, r4 >> T_BITS) : 0;
+            if (r1 | r2 | r3 | r4 | r5) { offset0 = max(max(Isk, Dsk), (r5 >> T_BITS) + 1); fromItself = false; }
+            else fromItself = true;
+            M0 = 0;
+        }
+        if (fromItself) break;                    /* :818-825 */
+        if (offset0 == 0) break;
+        const int h0 = (int)offset0;
+        if (previousFromM) {                      /* :833-869 */
+            const int nMatches = h - h0;
+            if (nMatches > 0) {
+                if (firstMatch) { firstMatch = false; res.tend = h; res.qend = v; }
+                sink.add('M', (uint32_t)nMatches);
+            }
+            h = h0; v = h - k;
+            if (type == T_MATCH) { tBegin = h; qBegin = v; }
+            else if (nMatches > 0) { tBegin = h + 1; qBegin = v + 1; }
+            if (h <= 0 || v <= 0) break;
+        }
+        sink.add(op_of_type(type), 1);            /* :872-873 */
+        if (semi && (h == 1 || v == 1)) break;    /* :876-879 */
+        previousFromM = true;                     /* :885-909 */
+        bool leave = false;
+        switch (type) {
+        case T_MISMATCH: s = sX; h--; break;
+        case T_INS_OPEN: s = sO; k--; h--; break;
+        case T_INS_EXT:  s = sE; k--; h--; previousFromM = false; break;
+        case T_DEL_OPEN: s = sO; k++; break;
+        case T_DEL_EXT:  s = sE; k++; previousFromM = false; break;
+        default: leave = true;
+        }
+        if (leave) break;
+        v = h - k;
+        raw = A.get(M0, s, k);                    /* :915-920 */
+        if (raw == 0) break;
+        type = raw & T_MASK;
+    }
+
+    if (h > 0 && v > 0) {                         /* :930-968 */
+        const int nMatches = min(h, v) - 1;
+        if (nMatches > 0) {
+            if (firstMatch) { firstMatch = false; res.tend = h; res.qend = v; }
+            sink.add('M', (uint32_t)nMatches);
+            h -= nMatches; v -= nMatches;
+            if (type == T_MATCH) { tBegin = h; qBegin = v; }
+            else { tBegin = h + 1; qBegin = v + 1; }
+        } else if (type == T_MATCH) {
+            tBegin = h; qBegin = v;
+            if (firstMatch) { firstMatch = false; res.tend = h; res.qend = v; }
+        }
+        sink.add(op_of_type(type), 1);
+    }
+    if (v > 1) sink.add('H', (uint32_t)(v - 1));  /* :970-976 */
+    if (h > 1) sink.add('I', (uint32_t)(h - 1));
+    res.tbegin = tBegin; res.qbegin = qBegin;     /* :979 */
+    sink.flush();
+}
+
+/* ------------------------------------------------------------------ one pair
+ * Shared-memory layout of a worker (32-bit words):
+ *   hdrs  RowHdr[dM]         ring of the most recent row headers
+ *   red   int[96]            block reduction scratch (CTA only)
+ *   rM    u32[dM][cap]       WARP only: ring of M rows
+ *   rI,rD u32[dE][cap]       WARP only: ring of I / D rows
+ */
+template <bool CTA> __host__ __device__ inline size_t worker_smem_bytes(int dM, int dE, int cap)
+{
+    size_t b = (size_t)dM * sizeof(RowHdr) + 96 * sizeof(int) + 16;
+    if (!CTA) b += (size_t)(dM + 2 * dE) * (size_t)cap * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+template <int BITS, bool CTA>
+__device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char *smem, uint8_t *slot)
+{
+    using G = Grp<CTA>;
+    const int tid = G::tid(), gsz = G::size();
+    const PairDesc pd = P.pairs[pair];
+    const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
+    const int dM = P.dM, dE = P.dE, cap = P.ring_cap;
+
+    SeqView<BITS> Q, T;
+    if (BITS == 2) { Q.w = P.packed + pd.q_word; Q.mis = 0; T.w = P.packed + pd.t_word; T.mis = 0; }
+    else { Q.w = P.raw + (pd.q_byte >> 2); Q.mis = (uint32_t)(pd.q_byte & 3); T.w = P.raw + (pd.t_byte >> 2); T.mis = (uint32_t)(pd.t_byte & 3); }
+
+    RowHdr   *hring = reinterpret_cast<RowHdr *>(smem);
+    int      *red   = reinterpret_cast<int *>(hring + dM);
+    uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 96);          /* 16 bytes of broadcast scratch */
+    uint32_t *rM = reinterpret_cast<uint32_t *>(bslot + 2);
+    uint32_t *rI = rM + (size_t)dM * cap;
+    uint32_t *rD = rI + (size_t)dE * cap;
+
+    RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);                /* grows up, index s/g */
+    uint32_t *cells = reinterpret_cast<uint32_t *>(slot);              /* rows grow down from the end */
+    const uint64_t slot_words = P.slot_bytes >> 2;
+    uint64_t top = slot_words;
+
+    for (int i = tid; i < dM; i += gsz) { RowHdr z; z.alo = 0; z.aw = 0; z.lo = 1; z.hi = 0; z.off = 0; hring[i] = z; }
+    G::sync();
+
+    const int x = (int)P.x;
+    const int ilo = P.global_aln ? 0 : -(n - 1), ihi = P.global_aln ? 0 : m - 1;   /* init cells, wfa.go:160-183 */
+    const int maxdiff = P.max_dist_diff;
+
+    int status = ST_OK;
+    uint32_t s = 0; int si = 0;
+    uint32_t minS = 0; int lastK = Ak;
+    unsigned long long c_cells = 0, c_written = 0, c_steps = 0;
+
+    /* ---------------- forward: wfa.go:228-251 with next+extend fused per cell */
+    for (;;) {
+        if (((uint64_t)(si + 2) * sizeof(RowHdr) + 3) / 4 + 8 > top) { status = ST_ARENA; break; }
+        /* loop range (wfa.go:557-563); a superset is harmless, the clamp is not */
+        int lo = INT_MAX, hi = INT_MIN;
+        RowHdr hX, hO, hE; hX.lo = hO.lo = hE.lo = 1; hX.hi = hO.hi = hE.hi = 0;
+        hX.alo = hO.alo = hE.alo = 0; hX.aw = hO.aw = hE.aw = 0; hX.off = hO.off = hE.off = 0;
+        int slX = 0, slO = 0, slE = 0, slEe = 0;
+        if (si - P.xg >= 0)  { slX = (si - P.xg) % dM;  hX = hring[slX]; }
+        if (si - P.oeg >= 0) { slO = (si - P.oeg) % dM; hO = hring[slO]; }
+        if (si - P.eg >= 0)  { slE = (si - P.eg) % dM;  hE = hring[slE]; slEe = (si - P.eg) % dE; }
+        if (hX.lo <= hX.hi) { lo = min(lo, hX.lo); hi = max(hi, hX.hi); }
+        if (hO.lo <= hO.hi) { lo = min(lo, hO.lo); hi = max(hi, hO.hi); }
+        if (hE.lo <= hE.hi) { lo = min(lo, hE.lo); hi = max(hi, hE.hi); }
+        if (lo <= hi) { lo = max(lo - 1, -(n - 1)); hi = min(hi + 1, m - 1); }
+        const bool has_init = (s == 0) || (s == (uint32_t)x);
+        if (has_init) { lo = min(lo, ilo); hi = max(hi, ihi); }
+        const int cur = si % dM, cure = si % dE;
+
+        bool exists = false;
+        int wlo = INT_MAX, whi = INT_MIN, endhit = 0;
+        int aw = 0; uint64_t off = 0;
+        if (lo <= hi) {
+            aw = hi - lo + 1;
+            if (!CTA && aw > cap) { status = ST_RING; break; }
+            const uint64_t need = 3ull * (uint32_t)aw;
+            if (((uint64_t)(si + 2) * sizeof(RowHdr) + 3) / 4 + 8 + need > top) { status = ST_ARENA; break; }
+            off = top - need;
+            const uint32_t *srcX, *srcO, *srcI, *srcD;
+            if (CTA) { srcX = cells + hX.off; srcO = cells + hO.off; srcI = cells + hE.off + (uint32_t)hE.aw; srcD = cells + hE.off + 2ull * (uint32_t)hE.aw; }
+            else { srcX = rM + (size_t)slX * cap; srcO = rM + (size_t)slO * cap; srcI = rI + (size_t)slEe * cap; srcD = rD + (size_t)slEe * cap; }
+            (void)slE;
+            for (int k = lo + tid; k <= hi; k += gsz) {
+                uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
+                if (k - 1 >= hO.lo && k - 1 <= hO.hi) mo_l = srcO[k - 1 - hO.alo];
+                if (k + 1 >= hO.lo && k + 1 <= hO.hi) mo_r = srcO[k + 1 - hO.alo];
+                if (k - 1 >= hE.lo && k - 1 <= hE.hi) ie_l = srcI[k - 1 - hE.alo];
+                if (k + 1 >= hE.lo && k + 1 <= hE.hi) de_r = srcD[k + 1 - hE.alo];
+                if (k >= hX.lo && k <= hX.hi) mx = srcX[k - hX.alo];
+                Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
+                if (has_init && c.M == 0 && k >= ilo && k <= ihi) {
+                    /* initComponents (wfa.go:155-183): cell (k) of the first row / column;
+                     * next's Set overwrites it when both write (wfa_wavefront.go:93) */
+                    const bool eq = Q.sym(k < 0 ? -k : 0) == T.sym(k > 0 ? k : 0);
+                    if (eq ? (s == 0) : (s == (uint32_t)x))
+                        c.M = (uint32_t)((k > 0 ? k : 0) + 1) << T_BITS | (eq ? T_MATCH : T_MISMATCH);
+                }
+                if (c.M) {
+                    /* extend (wfa.go:394-455) */
+                    int h = (int)(c.M >> T_BITS), v = h - k;
+                    if (v > 0 && v < n && h < m) {
+                        const int l = lcp<BITS>(Q, T, v, h, min(n - v, m - h));
+                        c.M += (uint32_t)l << T_BITS;
+                        h += l;
+                    }
+                    wlo = min(wlo, k); whi = max(whi, k);
+                    if (k == Ak && h >= m) endhit = 1;            /* wfa.go:235-239 */
+                }
+                const int idx = k - lo;
+                if (!CTA) { rM[(size_t)cur * cap + idx] = c.M; rI[(size_t)cure * cap + idx] = c.I; rD[(size_t)cure * cap + idx] = c.D; }
+                cells[off + idx] = c.M;
+                cells[off + (uint32_t)aw + idx] = c.I;
+                cells[off + 2ull * (uint32_t)aw + idx] = c.D;
+            }
+            G::reduce3(wlo, whi, endhit, red);
+            exists = wlo <= whi;
+        }
+
+        RowHdr hc; hc.alo = lo; hc.aw = aw; hc.lo = 1; hc.hi = 0; hc.off = off;
+        if (!exists) {
+            hc.alo = 0; hc.aw = 0; hc.off = 0;
+            G::sync();
+            if (tid == 0) { hring[cur] = hc; hdrs[si] = hc; }
+            G::sync();
+            s += P.g; si++;
+            continue;
+        }
+        top = off;
+        c_steps++; c_cells += (unsigned)(whi - wlo + 1); c_written += (unsigned)aw;
+        int elo = wlo, ehi = whi;
+        const uint32_t *rowM;
+        if (CTA) { G::sync(); rowM = cells + off; }                     /* arena row visible to the block */
+        else { __syncwarp(); rowM = rM + (size_t)cur * cap; }
+
+        bool finished = endhit != 0;
+        if (!finished && P.adaptive && whi - wlo + 1 >= P.min_wf_len) {
+            /* reduce (wfa.go:461-540) as three group reductions; see DESIGN.md 4.3 */
+            int mind = INT_MAX, dummy1 = INT_MIN, dummy2 = 0;
+            for (int k = wlo + tid; k <= whi; k += gsz) {
+                const int d = dist_of(rowM[k - lo], k, n, m);
+                if (d >= 0) mind = min(mind, d);
+            }
+            G::reduce3(mind, dummy1, dummy2, red);
+            int f = INT_MAX, L = INT_MIN, anyfar = 0;
+            for (int k = wlo + tid; k <= whi; k += gsz) {
+                const int d = dist_of(rowM[k - lo], k, n, m);
+                if (d >= 0) { if (d - mind > maxdiff) anyfar = 1; else { f = min(f, k); L = max(L, k); } }
+            }
+            G::reduce3(f, L, anyfar, red);
+            if (anyfar) {
+                int lf = INT_MIN, d0 = INT_MAX, d2 = 0;
+                for (int k = wlo + tid; k <= whi && k < f; k += gsz)
+                    if (dist_of(rowM[k - lo], k, n, m) >= 0) lf = max(lf, k);
+                G::reduce3(d0, lf, d2, red);
+                if (lf != INT_MIN) elo = lf + 1;
+                ehi = L;
+            }
+        }
+        bool hit = false; int hitK = Ak;
+        if (!P.global_aln && (finished || !P.semi_literal)) {
+            /* backtraceStartPosistion (wfa.go:270-375) for this one score, on the row as the
+             * reference leaves it (post-reduce, or un-reduced when it is the final score) */
+            int ka = INT_MIN, kb = INT_MAX, d2 = 0;
+            const int a_hi = min(Ak, ehi), b_lo = max(Ak + 1, elo);
+            for (int k = elo + tid; k <= ehi; k += gsz) {
+                const int c = hit_class(rowM[k - lo], k, n, m);
+                if (c) {
+                    const int key = (k + n) * 2 + (c == 2);
+                    if (k <= a_hi) ka = max(ka, key);
+                    if (k >= b_lo) kb = min(kb, key);
+                }
+            }
+            G::reduce3(kb, ka, d2, red);
+            if (ka != INT_MIN && (ka & 1)) { hit = true; hitK = (ka >> 1) - n; }
+            if (kb != INT_MAX && (kb & 1)) { hit = true; hitK = (kb >> 1) - n; }     /* scan (b) overrides (a) */
+        }
+        hc.lo = elo; hc.hi = ehi;
+        G::sync();
+        if (tid == 0) { hring[cur] = hc; hdrs[si] = hc; }
+        G::sync();
+        if (finished) { minS = s; lastK = Ak; if (hit) lastK = hitK; break; }
+        if (hit) { minS = s; lastK = hitK; break; }
+        s += P.g; si++;
+    }
+
+    /* ---------------- semi-global, literal mode: scan every retained score downwards (wfa.go:287-371) */
+    if (status == ST_OK && !P.global_aln && P.semi_literal) {
+        minS = s; lastK = Ak;
+        for (int sj = si; sj >= 0; sj--) {
+            const RowHdr h = hdrs[sj];
+            if (h.lo > h.hi) continue;
+            const uint32_t *rowM = cells + h.off;
+            int ka = INT_MIN, kb = INT_MAX, d2 = 0;
+            const int a_hi = min(Ak, h.hi), b_lo = max(Ak + 1, h.lo);
+            for (int k = h.lo + tid; k <= h.hi; k += gsz) {
+                const int c = hit_class(rowM[k - h.alo], k, n, m);
+                if (c) {
+                    const int key = (k + n) * 2 + (c == 2);
+                    if (k <= a_hi) ka = max(ka, key);
+                    if (k >= b_lo) kb = min(kb, key);
+                }
+            }
+            G::reduce3(kb, ka, d2, red);
+            if (ka != INT_MIN && (ka & 1)) { minS = (uint32_t)sj * P.g; lastK = (ka >> 1) - n; }
+            if (kb != INT_MAX && (kb & 1)) { minS = (uint32_t)sj * P.g; lastK = (kb >> 1) - n; }
+        }
+    }
+
+    /* ---------------- backtrace + result (one thread), then the group copies the ops out */
+    Result res;
+    res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
+    res.align_len = res.matches = res.gaps = res.gap_regions = 0; res.n_ops = 0;
+    res.status = (uint8_t)status; res.pad_[0] = res.pad_[1] = res.pad_[2] = 0;
+
+    const uint64_t scratch_w = (((uint64_t)(si + 1) * sizeof(RowHdr) + 7) / 8) * 2;   /* word index, 8-byte aligned */
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w);
+    uint32_t n_ops = 0;
+    if (status == ST_OK) {
+        G::sync();
+        if (tid == 0) {
+            ArenaView A; A.hdr = hdrs; A.cells = cells; A.s_last = (int64_t)s; A.g = P.g;
+            OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
+            sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
+            back_trace(A, P, n, m, minS, lastK, res, sink);
+            res.n_ops = sink.n;
+            if (sink.overflow) res.status = ST_ARENA;
+        }
+        n_ops = G::bcast0(res.n_ops, reinterpret_cast<uint32_t *>(bslot));
+        status = G::bcast0((int)res.status, reinterpret_cast<int *>(bslot) + 1);
+    }
+    if (status == ST_OK) {
+        /* process() (wfa_cigar.go:136-214): reverse (merge already done), stats between first and last M */
+        unsigned long long base = 0;
+        if (tid == 0) base = atomicAdd(&P.ctr->ops_cursor, (unsigned long long)n_ops);
+        base = G::bcast0(base, reinterpret_cast<unsigned long long *>(bslot));
+        if (P.ops_pool != nullptr && base + n_ops > P.ops_cap) status = ST_OPS;
+        else {
+            int begin = INT_MAX, end = INT_MIN, d2 = 0;
+            for (uint32_t i = tid; i < n_ops; i += gsz) {
+                const uint64_t op = scratch[n_ops - 1 - i];
+                if (P.ops_pool) P.ops_pool[base + i] = op;
+                if ((op >> 32) == 'M') { begin = min(begin, (int)i); end = max(end, (int)i); }
+            }
+            G::reduce3(begin, end, d2, red);
+            if (begin == INT_MAX) { begin = 0; end = 0; }          /* no M: begin = end = 0 (:170-186) */
+            unsigned alen = 0, matches = 0, gaps = 0, regions = 0;
+            for (int i = begin + tid; i <= end; i += gsz) {
+                const uint64_t op = scratch[n_ops - 1 - i];
+                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
+                alen += cnt;
+                if (o == 'M') matches += cnt;
+                else if (o == 'I' || o == 'D') { gaps += cnt; regions++; }
+            }
+            /* sums via the same all-reduce shape: use warp adds, then block */
+            for (int d = 16; d > 0; d >>= 1) {
+                alen += __shfl_xor_sync(0xffffffffu, alen, d); matches += __shfl_xor_sync(0xffffffffu, matches, d);
+                gaps += __shfl_xor_sync(0xffffffffu, gaps, d); regions += __shfl_xor_sync(0xffffffffu, regions, d);
+            }
+            if (CTA) {
+                const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+                unsigned *ured = reinterpret_cast<unsigned *>(red);
+                __syncthreads();
+                if (lane == 0 && wid < 24) { ured[wid] = alen; ured[24 + wid] = matches; ured[48 + wid] = gaps; ured[72 + wid] = regions; }
+                __syncthreads();
+                alen = matches = gaps = regions = 0;
+                for (int w = 0; w < nw && w < 24; w++) { alen += ured[w]; matches += ured[24 + w]; gaps += ured[48 + w]; regions += ured[72 + w]; }
+            }
+            res.align_len = alen; res.matches = matches; res.gaps = gaps; res.gap_regions = regions;
+            if (tid == 0) P.ops_where[pair] = base;
+        }
+    }
+    if (tid == 0) {
+        res.status = (uint8_t)status;
+        if (status != ST_OK) {
+            const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+            P.retry[r] = (uint64_t)status << 32 | pair;
+        } else {
+            atomicAdd(&P.ctr->cells, c_cells); atomicAdd(&P.ctr->cells_written, c_written);
+            atomicAdd(&P.ctr->steps, c_steps); atomicAdd(&P.ctr->ops, (unsigned long long)n_ops);
+            atomicMax(&P.ctr->arena_used_max, (unsigned long long)((slot_words - top + scratch_w) * 4 + 8ull * n_ops));
+        }
+        /* score/begin/end live in thread 0's res; stats were reduced to every thread */
+        P.results[pair] = res;
+    }
+    G::sync();
+}
+
+/* ------------------------------------------------------------------ kernels */
+template <bool CTA>
+__global__ void __launch_bounds__(CTA ? 512 : 128)
+align_kernel(const KParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using G = Grp<CTA>;
+    const int wpb = CTA ? 1 : (int)(blockDim.x >> 5);
+    const int wib = CTA ? 0 : (int)(threadIdx.x >> 5);
+    const size_t wbytes = worker_smem_bytes<CTA>(P.dM, P.dE, P.ring_cap);
+    unsigned char *smem = smem_raw + (size_t)wib * wbytes;
+    const uint64_t worker = (uint64_t)blockIdx.x * wpb + wib;
+    uint8_t *slot = P.arena + worker * P.slot_bytes;
+    __shared__ uint32_t next_item[4];
+
+    for (;;) {
+        uint32_t item = 0;
+        if (G::tid() == 0) item = (uint32_t)atomicAdd(&P.ctr->work_next, 1ull);
+        if (CTA) {
+            __syncthreads();
+            if (threadIdx.x == 0) next_item[0] = item;
+            __syncthreads();
+            item = next_item[0];
+        } else {
+            item = __shfl_sync(0xffffffffu, item, 0);
+        }
+        if (item >= P.n_work) break;
+        const uint32_t pair = P.work[item];
+        const bool eight = P.force8 || (P.pflags[pair] & 1);
+        if (eight) align_pair<8, CTA>(P, pair, smem, slot);
+        else       align_pair<2, CTA>(P, pair, smem, slot);
+    }
+}
+
+/* 2-bit packing of every sequence of the batch + detection of non-ACGT bytes.
+ * One warp per sequence (2*n_pairs sequences), lanes stride over 16-base
+ * words: 4 aligned 32-bit loads in, one 32-bit word out. */
+__global__ void __launch_bounds__(256)
+pack_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t *__restrict__ raw,
+            uint32_t *__restrict__ packed, uint8_t *__restrict__ pflags)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t sq = warp0; sq < 2ull * n_pairs; sq += nwarps) {
+        const PairDesc pd = pairs[sq >> 1];
+        const bool is_t = sq & 1;
+        const uint64_t boff = is_t ? pd.t_byte : pd.q_byte;
+        const uint32_t len = is_t ? pd.m : pd.n;
+        uint32_t *out = packed + (is_t ? pd.t_word : pd.q_word);
+        const uint32_t nwords = (len + 15) >> 4;
+        const uint32_t *src = raw + (boff >> 2);
+        const uint32_t sh = (uint32_t)(boff & 3) * 8;
+        bool bad = false;
+        for (uint32_t w = lane; w < nwords; w += 32) {
+            uint32_t in[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) in[j] = __ldg(src + 4 * w + j);
+            uint32_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t x = __funnelshift_r(in[j], in[j + 1], sh);       /* bases 16w+4j .. +3 */
+                const int rem = (int)len - (int)(16 * w + 4 * j);          /* valid bytes in x */
+                if (rem < 4) x = rem <= 0 ? 0x41414141u : ((x & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem)));
+                const uint32_t c = (x >> 1) & 0x03030303u;
+                /* valid iff every byte equals the letter its code maps back to (A,C,T,G) */
+                const uint32_t sel = (c & 3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
+                bad |= __byte_perm(0x47544341u, 0u, sel) != x;
+                const uint32_t p = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
+                o |= p << (8 * j);
+            }
+            out[w] = o;
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(pflags) + (sq >> 3), 1u << (((sq >> 1) & 3) * 8));
+    }
+}
+
+/* ops reorder: completion-order pool -> index-order buffer */
+__global__ void __launch_bounds__(256)
+gather_ops_kernel(const Result *__restrict__ results, const uint64_t *__restrict__ where,
+                  const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ pool,
+                  uint64_t *__restrict__ out, uint32_t n_pairs)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t p = warp0; p < n_pairs; p += nwarps) {
+        if (results[p].status != ST_OK) continue;
+        const uint32_t cnt = results[p].n_ops;
+        const uint64_t a = where[p], b = dst_off[p];
+        for (uint32_t i = lane; i < cnt; i += 32) out[b + i] = pool[a + i];
+    }
+}
+
+/* exclusive prefix sum of n_ops (index order) in three tiny kernels */
+__global__ void __launch_bounds__(1024)
+scan_block_kernel(const Result *__restrict__ results, uint32_t n, uint64_t *__restrict__ excl, uint64_t *__restrict__ block_sums)
+{
+    __shared__ uint64_t wsum[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint64_t v = (i < n && results[i].status == ST_OK) ? results[i].n_ops : 0;
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint64_t inc = v;
+    for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = wsum[lane], winc = w;
+        for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, winc, d); if ((int)lane >= d) winc += t; }
+        wsum[lane] = winc - w;
+        if (lane == 31) block_sums[blockIdx.x] = winc;
+    }
+    __syncthreads();
+    if (i < n) excl[i] = wsum[wid] + inc - v;
+}
+__global__ void scan_sums_kernel(uint64_t *block_sums, uint32_t nb, uint64_t *total)
+{
+    /* single thread: nb <= a few thousand */
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint64_t acc = 0;
+        for (uint32_t i = 0; i < nb; i++) { uint64_t t = block_sums[i]; block_sums[i] = acc; acc += t; }
+        *total = acc;
+    }
+}
+__global__ void __launch_bounds__(1024)
+scan_add_kernel(uint64_t *__restrict__ excl, const uint64_t *__restrict__ block_sums, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    if (i < n) excl[i] += block_sums[blockIdx.x];
+}
+
+} /* namespace wfak */

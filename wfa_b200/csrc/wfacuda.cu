@@ -1,0 +1,698 @@
+/*
+ * wfacuda.cu -- host driver + C ABI of libwfacuda.so (see include/wfacuda.h).
+ *
+ * Flow of one batch (wfacuda_align_batch = upload + run + download):
+ *   upload    validate lengths (wfa.go:202-209), stage the byte pool and the
+ *             pair descriptors into HBM through pinned double buffers, bin
+ *             pairs by cost (counting sort, longest first)
+ *   run       pack_kernel (bytes -> 2-bit, flags non-ACGT pairs), then the
+ *             persistent align kernels: WARP class (one warp per pair) and CTA
+ *             class (one block per pair); pairs that ran out of ring width,
+ *             arena or ops pool are re-queued with more of it -- still on the
+ *             GPU, there is no CPU path
+ *   download  prefix-sum n_ops, gather the ops into index order, D2H
+ */
+#include "../../include/wfacuda.h"
+#include "wfa_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace wfak;
+
+static_assert(sizeof(Result) == sizeof(wfacuda_result), "result layout");
+static_assert(sizeof(RowHdr) == 24, "row header layout");
+
+namespace {
+
+thread_local std::string g_tls_error;
+
+struct DevBuf { void *p = nullptr; size_t cap = 0; };
+
+} // namespace
+
+struct wfacuda_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    wfacuda_config cfg{};
+    uint32_t g = 1; int xg = 0, oeg = 0, eg = 0, dM = 0, dE = 0;
+    int sm_count = 0; size_t smem_optin = 0; size_t total_mem = 0;
+    /* grow-only device buffers shared by consecutive batches */
+    DevBuf arena, retry, work, ctr, ops_pool;
+    std::vector<std::pair<void *, size_t>> free_dev;     /* returned batch buffers */
+    void *pinned[2] = {nullptr, nullptr}; size_t pinned_cap = 0;
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    double arena_scale = 1.0;      /* learned: observed / estimated arena need */
+    wfacuda_stats stats{};
+    uint64_t last_ops_total = 0;
+    int last_rc = 0;
+    std::string err;
+};
+
+struct wfacuda_batch {
+    uint64_t n_pairs = 0;
+    std::vector<uint8_t> host_status;       /* EMPTY / TOO_LONG decided on the host */
+    std::vector<uint32_t> order_warp, order_cta;
+    std::vector<PairDesc> descs;
+    uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
+    void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
+    void *d_results = nullptr, *d_where = nullptr, *d_dst = nullptr, *d_ops_sorted = nullptr, *d_bsums = nullptr;
+    size_t sz_raw = 0, sz_packed = 0, sz_descs = 0, sz_flags = 0, sz_results = 0, sz_where = 0, sz_dst = 0, sz_ops_sorted = 0, sz_bsums = 0;
+    uint64_t ops_total = 0, n_invalid = 0;
+    bool ran = false;
+};
+
+namespace {
+
+int fail(wfacuda_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) { ctx->err = buf; ctx->last_rc = code; }
+    g_tls_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                            \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? WFACUDA_E_NOMEM : WFACUDA_E_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
+
+int apply_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
+{
+    if (!cfg) return fail(ctx, WFACUDA_E_INVALID, "config is NULL");
+    if (cfg->mismatch == 0 || cfg->gap_ext == 0)
+        return fail(ctx, WFACUDA_E_INVALID, "mismatch and gap_ext penalties must be > 0 (the reference's recurrences read the score being written otherwise)");
+    if (cfg->adaptive && cfg->min_wf_len == 0)      /* wfa.go:135-137 */
+        return fail(ctx, WFACUDA_E_INVALID, "cutoff step should not be 0");
+    const uint64_t oe = (uint64_t)cfg->gap_open + cfg->gap_ext;
+    if (cfg->mismatch > (1u << 20) || oe > (1u << 20))
+        return fail(ctx, WFACUDA_E_INVALID, "penalties above 2^20 are not supported");
+    const uint32_t g = gcd_u32(gcd_u32(cfg->mismatch, (uint32_t)oe), cfg->gap_ext);
+    const int xg = (int)(cfg->mismatch / g), oeg = (int)(oe / g), eg = (int)(cfg->gap_ext / g);
+    const int dM = std::max(xg, oeg) + 1;
+    if (dM > 1024) return fail(ctx, WFACUDA_E_INVALID, "max(mismatch, gap_open+gap_ext)/gcd must be <= 1023");
+    ctx->cfg = *cfg; ctx->g = g; ctx->xg = xg; ctx->oeg = oeg; ctx->eg = eg; ctx->dM = dM; ctx->dE = eg + 1;
+    return 0;
+}
+
+int ensure(wfacuda_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return 0;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    bytes = (bytes + 255) & ~(size_t)255;
+    CU(ctx, cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+/* batch buffers are recycled through the ctx so that steady-state batches do no cudaMalloc */
+int dev_take(wfacuda_ctx *ctx, void **p, size_t *sz, size_t bytes)
+{
+    bytes = (std::max<size_t>(bytes, 256) + 255) & ~(size_t)255;
+    int best = -1;
+    for (size_t i = 0; i < ctx->free_dev.size(); i++)
+        if (ctx->free_dev[i].second >= bytes && ctx->free_dev[i].second <= 2 * bytes + (1 << 20) &&
+            (best < 0 || ctx->free_dev[i].second < ctx->free_dev[best].second)) best = (int)i;
+    if (best >= 0) {
+        *p = ctx->free_dev[best].first; *sz = ctx->free_dev[best].second;
+        ctx->free_dev.erase(ctx->free_dev.begin() + best);
+        return 0;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        /* drop the cache and retry once */
+        for (auto &f : ctx->free_dev) cudaFree(f.first);
+        ctx->free_dev.clear();
+        cudaGetLastError();
+        CU(ctx, cudaMalloc(p, bytes));
+    }
+    *sz = bytes;
+    return 0;
+}
+void dev_give(wfacuda_ctx *ctx, void **p, size_t *sz)
+{
+    if (*p) ctx->free_dev.emplace_back(*p, *sz);
+    *p = nullptr; *sz = 0;
+}
+
+/* H2D of a host (pageable) region through two pinned buffers, copy overlapped with DMA */
+int staged_h2d(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    size_t done = 0; int which = 0;
+    while (done < bytes) {
+        const size_t chunk = std::min(ctx->pinned_cap, bytes - done);
+        CU(ctx, cudaEventSynchronize(ctx->pin_ev[which]));
+        memcpy(ctx->pinned[which], (const char *)src + done, chunk);
+        CU(ctx, cudaMemcpyAsync((char *)dst + done, ctx->pinned[which], chunk, cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaEventRecord(ctx->pin_ev[which], ctx->stream));
+        done += chunk; which ^= 1;
+    }
+    ctx->stats.h2d_bytes += bytes;
+    return 0;
+}
+
+/* ---- planning ------------------------------------------------------------ */
+
+struct Need { uint64_t arena; int width; };
+
+/* Rough per-pair need before anything is known about the error rate.  Pairs
+ * that overflow are re-queued with 4x, and ctx->arena_scale learns the ratio
+ * observed/estimated from every batch, so only the first batch pays. */
+Need estimate(const wfacuda_ctx *ctx, uint32_t n, uint32_t m)
+{
+    const wfacuda_config &c = ctx->cfg;
+    const double L = std::min(n, m), diag = (double)n + m - 1;
+    const double oe = (double)c.gap_open + c.gap_ext;
+    /* score guess: ~10 % edits at the mean edit cost, plus the end gap */
+    const double per_edit = (c.mismatch + 2.0 * oe) / 3.0;
+    const double score = 0.10 * L * per_edit + oe + std::abs((double)m - n) * c.gap_ext + 4.0 * c.mismatch;
+    const double rows = score / ctx->g + 2;
+    double width_final;
+    if (!c.global_alignment) width_final = diag;
+    else {
+        width_final = std::min(diag, 2.0 * score / c.gap_ext + 3);
+        if (c.adaptive) width_final = std::min(width_final, 1.5 * c.max_dist_diff + c.min_wf_len + 16.0);
+    }
+    const double avg_width = (!c.global_alignment || c.adaptive) ? width_final : 0.55 * width_final + 3;
+    double bytes = rows * (avg_width * 12.0 + sizeof(RowHdr)) + (n + m) * 0.5 + 4096;
+    bytes *= 1.3 * ctx->arena_scale;
+    Need nd; nd.arena = (uint64_t)bytes; nd.width = (int)std::min(diag, width_final);
+    return nd;
+}
+
+struct LaunchPlan {
+    bool cta; int threads; int blocks; int ring_cap; size_t smem; uint64_t slot_bytes; uint64_t workers; bool slot_at_max;
+};
+
+uint64_t arena_budget(wfacuda_ctx *ctx)
+{
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 1ull << 30; }
+    const uint64_t avail = (uint64_t)free_b + ctx->arena.cap;
+    uint64_t budget = (uint64_t)(avail * 0.85);
+    if (ctx->cfg.arena_budget_bytes) budget = std::min<uint64_t>(budget, ctx->cfg.arena_budget_bytes);
+    return std::max<uint64_t>(budget, 1u << 20);
+}
+
+/* choose worker count / slot size for one class launch */
+int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint32_t> &order, bool cta,
+                double boost, int min_ring_cap, LaunchPlan *lp)
+{
+    uint64_t need_max = 0; int width_max = 1;
+    /* the list is sorted longest first; a prefix sample bounds the estimate cheaply */
+    const size_t sample = std::min<size_t>(order.size(), 4096);
+    for (size_t i = 0; i < sample; i++) {
+        const PairDesc &d = b->descs[order[i]];
+        const Need nd = estimate(ctx, d.n, d.m);
+        need_max = std::max(need_max, nd.arena); width_max = std::max(width_max, nd.width);
+    }
+    need_max = (uint64_t)((double)need_max * boost);
+    lp->cta = cta; lp->slot_at_max = false;
+    const uint64_t budget = arena_budget(ctx);
+    uint64_t slot = (std::max<uint64_t>(need_max, 16384) + 255) & ~255ull;
+    int wpb, blocks_per_sm = 1;
+    if (cta) {
+        wpb = 1; lp->threads = 512; lp->ring_cap = 0;
+        lp->smem = worker_smem_bytes<true>(ctx->dM, ctx->dE, 0);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, align_kernel<true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
+        blocks_per_sm = std::max(1, std::min(blocks_per_sm, 4));
+    } else {
+        wpb = 4;
+        int cap = 64;
+        while (cap < (int)(width_max * 0.6) + 8 && cap < 512) cap *= 2;
+        cap = std::max(cap, min_ring_cap);
+        size_t per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap);
+        while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap); }
+        if (per_warp * wpb > ctx->smem_optin) return fail(ctx, WFACUDA_E_INVALID, "penalties need a deeper shared-memory ring than fits");
+        lp->ring_cap = cap; lp->threads = wpb * 32; lp->smem = per_warp * wpb;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, align_kernel<false>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
+        blocks_per_sm = std::max(1, blocks_per_sm);
+    }
+    uint64_t workers = (uint64_t)ctx->sm_count * blocks_per_sm * wpb;
+    workers = std::min<uint64_t>(workers, ((order.size() + wpb - 1) / wpb) * wpb);
+    if (slot * workers > budget) workers = std::max<uint64_t>(wpb, (budget / slot) / wpb * wpb);
+    if (slot * workers > budget) { slot = (budget / workers) & ~255ull; lp->slot_at_max = true; }
+    lp->blocks = (int)(workers / wpb); lp->workers = workers; lp->slot_bytes = slot;
+    return 0;
+}
+
+/* Runs one class of pairs to completion, re-queuing pairs that ran out of
+ * ring width (WARP kernel -> wider ring or the CTA kernel through *to_cta),
+ * arena (4x slot) or ops pool (pool doubled). */
+int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, bool cta, KParams base, std::vector<uint32_t> *to_cta)
+{
+    double boost = 1.0; int min_cap = 0;
+    for (int attempt = 0; !order.empty(); attempt++) {
+        if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
+        LaunchPlan lp;
+        int rc = plan_launch(ctx, b, order, cta, boost, min_cap, &lp);
+        if (rc) return rc;
+        if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.workers))) return rc;
+        if ((rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        /* reset queue + retry counters, keep the work counters and the ops cursor */
+        Counters *dc = (Counters *)ctx->ctr.p;
+        CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
+        KParams P = base;
+        P.work = (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
+        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes;
+        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
+        P.ring_cap = lp.ring_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+        if (cta) align_kernel<true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
+        else     align_kernel<false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++; ctx->stats.align_launches++;
+        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, lp.slot_bytes * lp.workers);
+        Counters hc;
+        CU(ctx, cudaMemcpyAsync(&hc, dc, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hc.retry_n == 0) {
+            /* learn: aim the next batch's slots at 1.5x the largest slot use seen */
+            if (attempt == 0 && !lp.slot_at_max && lp.slot_bytes > 16384 && hc.arena_used_max) {
+                const double r = 1.5 * (double)hc.arena_used_max / (double)lp.slot_bytes;
+                ctx->arena_scale = std::min(64.0, std::max(1.0 / 64, ctx->arena_scale * std::min(1.0, std::max(r, 0.25))));
+            }
+            break;
+        }
+        std::vector<uint64_t> rl(hc.retry_n);
+        CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
+        ctx->stats.retries += (uint32_t)rl.size();
+        std::vector<uint32_t> again, wide;
+        bool ops_full = false, arena_full = false;
+        for (uint64_t r : rl) {
+            const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
+            if (st == ST_RING) wide.push_back(pair);
+            else { again.push_back(pair); if (st == ST_OPS) ops_full = true; else arena_full = true; }
+        }
+        if (ops_full) {
+            /* grow the completion-order pool; what successful pairs wrote stays valid */
+            const uint64_t old_cap = ctx->ops_pool.cap / 8;
+            const uint64_t new_cap = std::max<uint64_t>(2 * old_cap, 2 * hc.ops_cursor + (1u << 20));
+            DevBuf nb;
+            if ((rc = ensure(ctx, nb, new_cap * 8))) return rc;
+            CU(ctx, cudaMemcpy(nb.p, ctx->ops_pool.p, std::min<uint64_t>(old_cap, hc.ops_cursor) * 8, cudaMemcpyDeviceToDevice));
+            cudaFree(ctx->ops_pool.p);
+            ctx->ops_pool = nb;
+        }
+        if (!wide.empty()) {
+            /* many pairs too wide for the ring: double it once if shared memory allows; else the CTA kernel */
+            const bool can_double = !cta && lp.ring_cap < 512 && worker_smem_bytes<false>(ctx->dM, ctx->dE, lp.ring_cap * 2) * 4 <= ctx->smem_optin;
+            if (can_double && wide.size() > 256) { min_cap = lp.ring_cap * 2; again.insert(again.end(), wide.begin(), wide.end()); }
+            else if (to_cta) to_cta->insert(to_cta->end(), wide.begin(), wide.end());
+        }
+        if (arena_full) {
+            if (lp.slot_at_max && lp.workers <= (uint64_t)(cta ? 1 : 4)) {
+                /* one worker already owns the whole budget: these pairs cannot be aligned on this device */
+                std::vector<uint32_t> keep;
+                for (uint64_t r : rl) {
+                    const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
+                    if (st != ST_ARENA) continue;
+                    Result res; memset(&res, 0, sizeof res); res.status = ST_RESOURCES;
+                    CU(ctx, cudaMemcpy((Result *)b->d_results + pair, &res, sizeof res, cudaMemcpyHostToDevice));
+                }
+                for (uint64_t r : rl) if ((uint32_t)(r >> 32) == ST_OPS) keep.push_back((uint32_t)r);
+                if (min_cap) keep.insert(keep.end(), wide.begin(), wide.end());
+                again.swap(keep);
+            } else boost *= 4.0;
+            ctx->arena_scale = std::min(64.0, ctx->arena_scale * 2.0);
+        }
+        order.swap(again);
+    }
+    return 0;
+}
+
+} // namespace
+
+/* ========================================================================== API */
+
+extern "C" {
+
+const char *wfacuda_last_error(const wfacuda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+
+int wfacuda_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return 0; fail(nullptr, 0, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); return WFACUDA_E_CUDA; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++; }
+    return ok;
+}
+
+wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
+{
+    wfacuda_ctx *ctx = new wfacuda_ctx();
+    auto bail = [&](void) -> wfacuda_ctx * { g_tls_error = ctx->err; wfacuda_destroy(ctx); return nullptr; };
+    if (apply_config(ctx, cfg) != 0) return bail();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        fail(ctx, WFACUDA_E_CUDA, "no CUDA device available (%s); libwfacuda has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+        return bail();
+    }
+    if (device < 0 || device >= n) { fail(ctx, WFACUDA_E_INVALID, "device %d out of range (have %d)", device, n); return bail(); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "cudaGetDeviceProperties failed"); return bail(); }
+    if (prop.major != 10) { fail(ctx, WFACUDA_E_CUDA, "device %d is sm_%d%d; libwfacuda is built for sm_100a only", device, prop.major, prop.minor); return bail(); }
+    ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin; ctx->total_mem = prop.totalGlobalMem;
+    if (cudaSetDevice(device) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "cudaSetDevice failed"); return bail(); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "stream creation failed"); return bail(); }
+    for (auto &ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "event creation failed"); return bail(); }
+    ctx->pinned_cap = 16u << 20;
+    for (int i = 0; i < 2; i++) {
+        if (cudaHostAlloc(&ctx->pinned[i], ctx->pinned_cap, cudaHostAllocDefault) != cudaSuccess) { fail(ctx, WFACUDA_E_NOMEM, "pinned staging allocation failed"); return bail(); }
+        if (cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "event creation failed"); return bail(); }
+    }
+    cudaFuncSetAttribute(align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    cudaFuncSetAttribute(align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    return ctx;
+}
+
+void wfacuda_destroy(wfacuda_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool}) if (b->p) cudaFree(b->p);
+    for (auto &f : ctx->free_dev) cudaFree(f.first);
+    for (int i = 0; i < 2; i++) { if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]); if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]); }
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
+{
+    if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
+    wfacuda_config old = ctx->cfg;
+    int rc = apply_config(ctx, cfg);
+    if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) ctx->arena_scale = 1.0;
+    return rc;
+}
+
+int wfacuda_get_stats(const wfacuda_ctx *ctx, wfacuda_stats *out)
+{
+    if (!ctx || !out) return WFACUDA_E_INVALID;
+    *out = ctx->stats;
+    return 0;
+}
+
+uint64_t wfacuda_last_ops_total(const wfacuda_ctx *ctx) { return ctx ? ctx->last_ops_total : 0; }
+uint64_t wfacuda_batch_ops_total(const wfacuda_batch *b) { return b ? b->ops_total : 0; }
+
+void wfacuda_batch_free(wfacuda_ctx *ctx, wfacuda_batch *b)
+{
+    if (!b) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        dev_give(ctx, &b->d_raw, &b->sz_raw); dev_give(ctx, &b->d_packed, &b->sz_packed);
+        dev_give(ctx, &b->d_descs, &b->sz_descs); dev_give(ctx, &b->d_flags, &b->sz_flags);
+        dev_give(ctx, &b->d_results, &b->sz_results); dev_give(ctx, &b->d_where, &b->sz_where);
+        dev_give(ctx, &b->d_dst, &b->sz_dst); dev_give(ctx, &b->d_ops_sorted, &b->sz_ops_sorted);
+        dev_give(ctx, &b->d_bsums, &b->sz_bsums);
+    }
+    delete b;
+}
+
+wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                                    const uint64_t *q_off, const uint32_t *q_len,
+                                    const uint64_t *t_off, const uint32_t *t_len)
+{
+    if (!ctx) { fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL"); return nullptr; }
+    if (n_pairs > 0xfffffff0ull) { fail(ctx, WFACUDA_E_INVALID, "at most 2^32-16 pairs per batch"); return nullptr; }
+    if (n_pairs && (!seq_bytes || !q_off || !q_len || !t_off || !t_len)) { fail(ctx, WFACUDA_E_INVALID, "NULL input array"); return nullptr; }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "cudaSetDevice failed"); return nullptr; }
+    wfacuda_batch *b = new wfacuda_batch();
+    b->n_pairs = n_pairs;
+    b->host_status.assign(n_pairs, ST_PENDING);
+    b->descs.resize(n_pairs);
+    auto body = [&]() -> int {
+        ctx->stats = wfacuda_stats{};
+        /* validation (wfa.go:202-209) + extent of the byte pool actually referenced */
+        uint64_t lo = UINT64_MAX, hi = 0, words = 0;
+        for (uint64_t i = 0; i < n_pairs; i++) {
+            PairDesc &d = b->descs[i];
+            d.n = q_len[i]; d.m = t_len[i]; d.q_byte = d.t_byte = d.q_word = d.t_word = 0;
+            if (d.n == 0 || d.m == 0) { b->host_status[i] = ST_EMPTY; d.n = d.m = 0; b->n_invalid++; continue; }
+            if (d.n > WFACUDA_MAX_SEQ_LEN || d.m > WFACUDA_MAX_SEQ_LEN) { b->host_status[i] = ST_TOO_LONG; d.n = d.m = 0; b->n_invalid++; continue; }
+            lo = std::min(lo, std::min(q_off[i], t_off[i]));
+            hi = std::max(hi, std::max(q_off[i] + d.n, t_off[i] + d.m));
+        }
+        if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+        const uint64_t base = lo & ~(uint64_t)15;            /* keep the caller's alignment mod 16 */
+        for (uint64_t i = 0; i < n_pairs; i++) {
+            if (b->host_status[i] != ST_PENDING) continue;
+            PairDesc &d = b->descs[i];
+            d.q_byte = q_off[i] - base; d.t_byte = t_off[i] - base;
+            d.q_word = words; words += ((uint64_t)((d.n + 15) >> 4) + 3) & ~3ull;
+            d.t_word = words; words += ((uint64_t)((d.m + 15) >> 4) + 3) & ~3ull;
+            b->seq_bases += (uint64_t)d.n + d.m;
+            b->max_nm = std::max<uint64_t>(b->max_nm, (uint64_t)d.n + d.m);
+        }
+        b->raw_bytes = hi - base; b->packed_words = words;
+        int rc;
+        if ((rc = dev_take(ctx, &b->d_raw, &b->sz_raw, b->raw_bytes + 64))) return rc;
+        if ((rc = dev_take(ctx, &b->d_packed, &b->sz_packed, (words + 16) * 4))) return rc;
+        if ((rc = dev_take(ctx, &b->d_descs, &b->sz_descs, n_pairs * sizeof(PairDesc)))) return rc;
+        if ((rc = dev_take(ctx, &b->d_flags, &b->sz_flags, n_pairs + 16))) return rc;
+        if ((rc = dev_take(ctx, &b->d_results, &b->sz_results, n_pairs * sizeof(Result)))) return rc;
+        if ((rc = dev_take(ctx, &b->d_where, &b->sz_where, n_pairs * 8))) return rc;
+        if (b->raw_bytes) {
+            if ((rc = staged_h2d(ctx, b->d_raw, seq_bytes + base, b->raw_bytes))) return rc;
+            CU(ctx, cudaMemsetAsync((char *)b->d_raw + b->raw_bytes, 0, 64, ctx->stream));
+        }
+        if (n_pairs) if ((rc = staged_h2d(ctx, b->d_descs, b->descs.data(), n_pairs * sizeof(PairDesc)))) return rc;
+        /* cost bins: longest first (counting sort on log2-ish buckets of n+m) */
+        const bool force_cta = ctx->cfg.flags & WFACUDA_FLAG_FORCE_CTA;
+        const int warp_cap_max = 512;
+        std::vector<uint32_t> bucket_of(n_pairs);
+        uint32_t counts[2][130] = {{0}};
+        std::vector<uint8_t> cls(n_pairs, 2);
+        for (uint64_t i = 0; i < n_pairs; i++) {
+            if (b->host_status[i] != ST_PENDING) continue;
+            const PairDesc &d = b->descs[i];
+            const uint64_t nm = (uint64_t)d.n + d.m;
+            int lg = 63 - __builtin_clzll(nm | 1);
+            int bk = 2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1);     /* half-octave buckets */
+            bucket_of[i] = 127 - bk;
+            const Need nd = estimate(ctx, d.n, d.m);
+            cls[i] = (force_cta || nd.width > warp_cap_max) ? 1 : 0;
+            counts[cls[i]][bucket_of[i] + 1]++;
+        }
+        for (int c = 0; c < 2; c++) for (int k = 1; k < 130; k++) counts[c][k] += counts[c][k - 1];
+        b->order_warp.resize(counts[0][129]); b->order_cta.resize(counts[1][129]);
+        for (uint64_t i = 0; i < n_pairs; i++) {
+            if (cls[i] == 2) continue;
+            (cls[i] ? b->order_cta : b->order_warp)[counts[cls[i]][bucket_of[i]]++] = (uint32_t)i;
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return 0;
+    };
+    if (body() != 0) { wfacuda_batch_free(ctx, b); return nullptr; }
+    return b;
+}
+
+} // extern "C"
+
+extern "C" {
+
+int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
+{
+    if (!ctx || !b) return fail(ctx, WFACUDA_E_INVALID, "NULL ctx or batch");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = b->n_pairs;
+    int rc;
+    if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    CU(ctx, cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
+    CU(ctx, cudaMemsetAsync(b->d_flags, 0, b->sz_flags, ctx->stream));
+    /* results start as PENDING, or as the host-side verdict (EMPTY / TOO_LONG) */
+    if (b->n_invalid) {
+        std::vector<Result> init(n);
+        memset(init.data(), 0, n * sizeof(Result));
+        for (uint64_t i = 0; i < n; i++) init[i].status = b->host_status[i];
+        if ((rc = staged_h2d(ctx, b->d_results, init.data(), n * sizeof(Result)))) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));     /* init goes out of scope */
+    } else if (n) CU(ctx, cudaMemsetAsync(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
+    const uint64_t n_valid = b->order_warp.size() + b->order_cta.size();
+    if (n_valid) {
+        const int pack_blocks = (int)std::min<uint64_t>((2 * n_valid + 7) / 8, (uint64_t)ctx->sm_count * 16);
+        pack_kernel<<<pack_blocks, 256, 0, ctx->stream>>>((const PairDesc *)b->d_descs, (uint32_t)n, (const uint32_t *)b->d_raw,
+                                                         (uint32_t *)b->d_packed, (uint8_t *)b->d_flags);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    /* ops pool: first guess 1/4 op per base, grown on demand */
+    uint64_t ops_cap = std::max<uint64_t>(b->seq_bases / 5 + 16 * n_valid + 1024, ctx->ops_pool.cap / 8);
+    if ((rc = ensure(ctx, ctx->ops_pool, ops_cap * 8))) return rc;
+    ops_cap = ctx->ops_pool.cap / 8;
+
+    KParams P{};
+    P.pairs = (const PairDesc *)b->d_descs; P.packed = (const uint32_t *)b->d_packed; P.raw = (const uint32_t *)b->d_raw;
+    P.pflags = (const uint8_t *)b->d_flags; P.results = (Result *)b->d_results; P.ops_where = (uint64_t *)b->d_where;
+    P.ops_cap = ops_cap;
+    P.x = ctx->cfg.mismatch; P.oe = ctx->cfg.gap_open + ctx->cfg.gap_ext; P.e = ctx->cfg.gap_ext; P.g = ctx->g;
+    P.xg = ctx->xg; P.oeg = ctx->oeg; P.eg = ctx->eg; P.dM = ctx->dM; P.dE = ctx->dE;
+    P.global_aln = ctx->cfg.global_alignment ? 1 : 0; P.adaptive = ctx->cfg.adaptive ? 1 : 0;
+    P.semi_literal = (ctx->cfg.flags & WFACUDA_FLAG_SEMIGLOBAL_LITERAL) ? 1 : 0;
+    P.force8 = (ctx->cfg.flags & WFACUDA_FLAG_FORCE_8BIT) ? 1 : 0;
+    P.min_wf_len = (int32_t)std::min<uint32_t>(ctx->cfg.min_wf_len, 0x7fffffffu);
+    P.max_dist_diff = (int32_t)std::min<uint32_t>(ctx->cfg.max_dist_diff, 0x7fffffffu);
+
+    std::vector<uint32_t> to_cta;
+    if ((rc = run_class(ctx, b, b->order_warp, false, P, &to_cta))) return rc;
+    std::vector<uint32_t> cta_order = b->order_cta;
+    cta_order.insert(cta_order.end(), to_cta.begin(), to_cta.end());
+    ctx->stats.pairs_warp = (uint32_t)(b->order_warp.size() - to_cta.size());
+    ctx->stats.pairs_cta = (uint32_t)cta_order.size();
+    if ((rc = run_class(ctx, b, cta_order, true, P, nullptr))) return rc;
+    CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+
+    /* index-order offsets of the ops + total */
+    if ((rc = dev_take(ctx, &b->d_dst, &b->sz_dst, n * 8 + 8))) return rc;
+    const uint32_t nb = (uint32_t)((n + 1023) / 1024);
+    if ((rc = dev_take(ctx, &b->d_bsums, &b->sz_bsums, (size_t)nb * 8 + 16))) return rc;
+    uint64_t *d_total = (uint64_t *)b->d_bsums + nb;
+    if (n) {
+        scan_block_kernel<<<nb, 1024, 0, ctx->stream>>>((const Result *)b->d_results, (uint32_t)n, (uint64_t *)b->d_dst, (uint64_t *)b->d_bsums);
+        scan_sums_kernel<<<1, 32, 0, ctx->stream>>>((uint64_t *)b->d_bsums, nb, d_total);
+        scan_add_kernel<<<nb, 1024, 0, ctx->stream>>>((uint64_t *)b->d_dst, (const uint64_t *)b->d_bsums, (uint32_t)n);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 3;
+        CU(ctx, cudaMemcpyAsync(&b->ops_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    } else b->ops_total = 0;
+    Counters hc{};
+    CU(ctx, cudaMemcpyAsync(&hc, ctx->ctr.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (b->ops_total) {
+        if ((rc = dev_take(ctx, &b->d_ops_sorted, &b->sz_ops_sorted, b->ops_total * 8))) return rc;
+        const int gb = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);
+        gather_ops_kernel<<<gb, 256, 0, ctx->stream>>>((const Result *)b->d_results, (const uint64_t *)b->d_where, (const uint64_t *)b->d_dst,
+                                                      (const uint64_t *)ctx->ops_pool.p, (uint64_t *)b->d_ops_sorted, (uint32_t)n);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->stats.ms_pack, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.ms_align, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.ms_total_device, ctx->ev[0], ctx->ev[3]);
+    ctx->stats.pairs = n_valid; ctx->stats.cells = hc.cells; ctx->stats.cells_written = hc.cells_written;
+    ctx->stats.score_steps = hc.steps; ctx->stats.ops = hc.ops; ctx->stats.seq_bases = b->seq_bases;
+    ctx->last_ops_total = b->ops_total;
+    b->ran = true;
+    return 0;
+}
+
+int wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *results,
+                           uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
+{
+    if (!ctx || !b) return fail(ctx, WFACUDA_E_INVALID, "NULL ctx or batch");
+    if (!b->ran) return fail(ctx, WFACUDA_E_INVALID, "batch has not been run");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n = b->n_pairs;
+    if (n && results) { CU(ctx, cudaMemcpy(results, b->d_results, n * sizeof(Result), cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += n * sizeof(Result); }
+    if (n && ops_off) { CU(ctx, cudaMemcpy(ops_off, b->d_dst, n * 8, cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += n * 8; }
+    if (ops) {
+        if (b->ops_total > ops_capacity)
+            return fail(ctx, WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)b->ops_total);
+        if (b->ops_total) { CU(ctx, cudaMemcpy(ops, b->d_ops_sorted, b->ops_total * 8, cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += b->ops_total * 8; }
+    }
+    return 0;
+}
+
+int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                        const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
+                        wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
+{
+    if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
+    if (n_pairs && !results) return fail(ctx, WFACUDA_E_INVALID, "results is NULL");
+    wfacuda_batch *b = wfacuda_batch_upload(ctx, n_pairs, seq_bytes, q_off, q_len, t_off, t_len);
+    if (!b) return ctx->last_rc ? ctx->last_rc : WFACUDA_E_CUDA;
+    int rc = wfacuda_batch_run(ctx, b);
+    if (rc == 0) rc = wfacuda_batch_download(ctx, b, results, ops, ops_capacity, ops_off);
+    wfacuda_batch_free(ctx, b);
+    return rc;
+}
+
+int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                              const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
+                              wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
+{
+    if (!ctxs || n_ctx < 1) return fail(nullptr, WFACUDA_E_INVALID, "need at least one ctx");
+    if (n_ctx == 1) return wfacuda_align_batch(ctxs[0], n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
+    /* contiguous index ranges of equal estimated cost: cost ~ (n+m) * band, band ~ (n+m) without
+     * heuristic (work grows with the square of the edit count), constant with wf-adaptive */
+    const bool quad = !ctxs[0]->cfg.adaptive;
+    std::vector<double> pre(n_pairs + 1, 0.0);
+    for (uint64_t i = 0; i < n_pairs; i++) {
+        const double nm = (double)q_len[i] + t_len[i];
+        pre[i + 1] = pre[i] + (quad ? nm * nm : nm) + 64.0;
+    }
+    std::vector<uint64_t> cut(n_ctx + 1, n_pairs);
+    cut[0] = 0;
+    for (int d = 1; d < n_ctx; d++)
+        cut[d] = (uint64_t)(std::lower_bound(pre.begin(), pre.end(), pre[n_pairs] * d / n_ctx) - pre.begin());
+    for (int d = 1; d <= n_ctx; d++) cut[d] = std::max(cut[d], cut[d - 1]);
+    std::vector<wfacuda_batch *> bs(n_ctx, nullptr);
+    std::vector<int> rcs(n_ctx, 0);
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n_ctx; d++)
+            th.emplace_back([&, d]() {
+                const uint64_t a = cut[d], cnt = cut[d + 1] - cut[d];
+                bs[d] = wfacuda_batch_upload(ctxs[d], cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
+                rcs[d] = bs[d] ? wfacuda_batch_run(ctxs[d], bs[d]) : WFACUDA_E_CUDA;
+            });
+        for (auto &t : th) t.join();
+    }
+    int rc = 0;
+    for (int d = 0; d < n_ctx; d++) if (rcs[d]) { rc = rcs[d]; g_tls_error = ctxs[d]->err; }
+    std::vector<uint64_t> obase(n_ctx + 1, 0);
+    for (int d = 0; d < n_ctx; d++) obase[d + 1] = obase[d] + (bs[d] ? bs[d]->ops_total : 0);
+    for (int d = 0; d < n_ctx; d++) ctxs[d]->last_ops_total = obase[n_ctx];
+    if (rc == 0 && ops && obase[n_ctx] > ops_capacity)
+        rc = fail(ctxs[0], WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)obase[n_ctx]);
+    const bool want_ops = rc == 0 && ops;
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < n_ctx; d++)
+            th.emplace_back([&, d]() {
+                if (!bs[d]) return;
+                const uint64_t a = cut[d], cnt = cut[d + 1] - cut[d];
+                if (rcs[d] == 0) {
+                    int r = wfacuda_batch_download(ctxs[d], bs[d], results + a, want_ops ? ops + obase[d] : nullptr,
+                                                   want_ops ? ops_capacity - obase[d] : 0, ops_off ? ops_off + a : nullptr);
+                    if (r) rcs[d] = r;
+                    if (ops_off) for (uint64_t i = 0; i < cnt; i++) ops_off[a + i] += obase[d];
+                }
+                wfacuda_batch_free(ctxs[d], bs[d]);
+            });
+        for (auto &t : th) t.join();
+    }
+    for (int d = 0; d < n_ctx; d++) if (rcs[d] && rc == 0) { rc = rcs[d]; g_tls_error = ctxs[d]->err; }
+    return rc;
+}
+
+} // extern "C"
