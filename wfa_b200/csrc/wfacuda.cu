@@ -382,8 +382,12 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
         if (cudaHostAlloc(&ctx->pinned[i], ctx->pinned_cap, cudaHostAllocDefault) != cudaSuccess) { fail(ctx, WFACUDA_E_NOMEM, "pinned staging allocation failed"); return bail(); }
         if (cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "event creation failed"); return bail(); }
     }
-    cudaFuncSetAttribute(align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
-    cudaFuncSetAttribute(align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin);
+    ctx->smem_optin -= 1024;       /* room for the kernels' static shared memory */
+    if (cudaFuncSetAttribute(align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
+        fail(ctx, WFACUDA_E_CUDA, "cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail();
+    }
     return ctx;
 }
 
