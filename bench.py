@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Benchmark of the wavefront hot path (BASELINE.json metric: alignments/s and
+cells-equivalent GCUPS) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--pairs P]
+    python bench.py --impl reference ...     # CPU arm: the oracle port on all host cores
+
+A step = one pass of the hot path over one batch of synthetic pairs of the
+workload.  `value` = pairs/s with the batch already resident in HBM
+(wfacuda_batch_run: pack + align + backtrace kernels, nothing crosses PCIe);
+`e2e` = the same metric through wfacuda_align_batch with host buffers, H2D and
+D2H inside the timed region.  Under torchrun every rank drives its own GPU
+with its own shard of the pair stream (weak scaling, no collective on the data
+path); the step time is the max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+from wfa_b200 import datagen  # noqa: E402
+
+DEFAULT_WORKLOAD = "cfg2_150bp_e5_global"
+WORKLOAD_TEXT = {
+    "cfg2_150bp_e5_global": "config 2: 1M synthetic pairs 150 bp, 5% error, global, no heuristic (warp-per-pair path)",
+    "cfg3_1kbp_e10_global_adaptive": "config 3: 1M synthetic pairs 1 kbp, 10% error, global, wf-adaptive 10/50",
+    "cfg4_10kbp_in_12kbp_e5_semiglobal": "config 4: 100k semi-global alignments, 10 kbp reads vs 12 kbp windows, 5% error",
+    "cfg5_100kbp_e15_global_adaptive": "config 5: 10k synthetic pairs 100 kbp, 15% error, global, wf-adaptive 10/50",
+}
+# bounded CPU samples (about 10-30 s of CPU work on a few dozen cores)
+CPU_SAMPLE = {"cfg2_150bp_e5_global": 400_000, "cfg3_1kbp_e10_global_adaptive": 40_000,
+              "cfg4_10kbp_in_12kbp_e5_semiglobal": 8, "cfg5_100kbp_e15_global_adaptive": 64}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes(stats, batch):
+    """B = 12*C + ceil((n+m)/4) + 8*R + 64 per pair (2-bit sequences)."""
+    return 12 * stats["cells"] + (stats["seq_bases"] + 3) // 4 + 8 * stats["ops"] + 64 * stats["pairs"]
+
+
+def run_cpu(args, workload, cfgc):
+    """CPU arm / baseline: the C restatement of the reference (oracle port; the Go
+    reference cannot be built here) on all host cores."""
+    import oracle_lib
+    cores = os.cpu_count() or 1
+    n = args.pairs or CPU_SAMPLE[workload]
+    batch = datagen.generate_config(workload, n)
+    cfg = oracle_lib.make_config(global_alignment=cfgc["global_alignment"], adaptive=cfgc["adaptive"])
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        oracle_lib.align_batch(cfg, batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len,
+                               want_ops=True, threads=cores)
+        if it >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n / sec, sec, cores, batch, "%d pairs of the workload per step, %d threads" % (n, cores)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="wfacuda", choices=["wfacuda", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=list(datagen.CONFIGS))
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (default: the config's full size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    workload = args.workload
+    cfgc = datagen.CONFIGS[workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ws = max(args.warmup, 1) if args.warmup else 0
+        args.warmup = min(ws, 1)
+        args.steps = min(args.steps, 3)
+        v, sec, cores, batch, sample = run_cpu(args, workload, cfgc)
+        line = {"impl": "reference", "metric": "alignments_per_sec", "value": v, "unit": "alignments/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "gcups_equiv": batch.cells_equiv() / sec / 1e9,
+                "config": {"workload": WORKLOAD_TEXT[workload], "pairs_per_step": len(batch)},
+                "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample,
+                                 "note": "C restatement of wfa-go (oracle/); no Go toolchain, reference not buildable"},
+                "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from wfa_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no GPU visible; the wfacuda arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_pairs = args.pairs or cfgc["pairs"]
+    batch = datagen.generate_config(workload, n_pairs, first=rank * n_pairs)      # weak scaling: own shard per rank
+    algn = api.New(api.Penalties(4, 6, 2), api.Options(cfgc["global_alignment"]), device=local_rank)
+    if cfgc["adaptive"]:
+        algn.AdaptiveReduction(api.AdaptiveReductionOption(cfgc["adaptive"][0], cfgc["adaptive"][1], 1))
+
+    # ---- device-resident throughput (value) ---------------------------------
+    rb = api.ResidentBatch(algn, batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)
+    for _ in range(args.warmup):
+        rb.run()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    ms_align = ms_dev = 0.0
+    launches = 0
+    for _ in range(args.steps):
+        rb.run()
+        st = algn.stats()
+        ms_align += st["ms_align"]; ms_dev += st["ms_total_device"]; launches += st["kernel_launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    stats = algn.stats()
+    results, ops, ops_off = rb.download()
+    rb.free()
+    ok = int((results["status"] == 0).sum())
+
+    # ---- end to end through the C ABI with host buffers (e2e) ---------------
+    e2e_steps = max(1, min(args.steps, 3))
+    algn.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)    # warm
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r2, o2, off2 = algn.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+    st_e2e = algn.stats()
+    assert np.array_equal(r2["score"], results["score"]) and np.array_equal(o2, ops)
+
+    # ---- max over ranks ------------------------------------------------------
+    vals = torch.tensor([wall, wall_e2e, ms_align, ms_dev], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(n_pairs), float(batch.cells_equiv()), float(ok)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    wall, wall_e2e, ms_align, ms_dev = [float(x) for x in vals.tolist()]
+    pairs_all, cells_all, ok_all = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        sec_step = wall / args.steps
+        hbm_peak, peak_src = peaks()
+        B = algorithmic_bytes(stats, batch)                      # per launch of the align kernel (this rank)
+        k_sec = (ms_align / args.steps) / 1e3
+        achieved = B / k_sec / 1e9
+        int_ops = 32 * stats["cells"] + 10 * stats["cells"] + 8 * stats["cells"]      # O = 32C + 10V + 8W with V,W ~ C
+        line = {
+            "metric": "alignments_per_sec", "value": pairs_all / sec_step, "unit": "alignments/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_step * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "gcups_equiv": cells_all / sec_step / 1e9,
+            "config": {"workload": WORKLOAD_TEXT[workload], "pairs_per_gpu_per_step": n_pairs, "penalties": "4/6/2",
+                       "global": cfgc["global_alignment"], "adaptive": cfgc["adaptive"],
+                       "l2_policy": "inputs+arena larger than L2 (%.0f MB seqs, %.0f MB arena)" % (batch.seq_bytes.nbytes / 1e6, stats["arena_bytes"] / 1e6),
+                       "parallelism": "pairs sharded over %d GPU(s), no collective" % world, "pairs_ok": ok_all},
+            "e2e": {"value": pairs_all / (wall_e2e / e2e_steps), "unit": "alignments/s",
+                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"]), "d2h_bytes_per_step": int(st_e2e["d2h_bytes"]),
+                    "gcups_equiv": cells_all / (wall_e2e / e2e_steps) / 1e9, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "align_kernel<warp>" if stats["pairs_warp"] >= stats["pairs_cta"] else "align_kernel<cta>",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(B),
+                         "kernel_ms": ms_align / args.steps,
+                         "cells_per_s": stats["cells"] / k_sec, "int32_ops_per_s_est": int_ops / k_sec},
+            "device_ms_per_step": ms_dev / args.steps,
+            "work": {"cells": int(stats["cells"]), "cells_written": int(stats["cells_written"]), "score_steps": int(stats["score_steps"]),
+                     "ops": int(stats["ops"]), "retries": int(stats["retries"]), "pairs_warp": int(stats["pairs_warp"]),
+                     "pairs_cta": int(stats["pairs_cta"])},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            class A:
+                pass
+            a = A(); a.pairs = 0; a.warmup = 0; a.steps = 1
+            v, sec, cores, cb, sample = run_cpu(a, workload, cfgc)
+            line["cpu_baseline"] = {"value": v, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample,
+                                    "gcups_equiv": cb.cells_equiv() / sec / 1e9}
+        print(json.dumps(line))
+    algn.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,7 +31,7 @@ enum : uint32_t { T_INS_OPEN = 1, T_INS_EXT = 2, T_DEL_OPEN = 3, T_DEL_EXT = 4, 
 
 /* internal per-pair states (>= 100 never leave the library) */
 enum : uint8_t { ST_OK = 0, ST_EMPTY = 1, ST_TOO_LONG = 2, ST_RESOURCES = 3,
-                 ST_ARENA = 100, ST_RING = 101, ST_OPS = 102, ST_PENDING = 255 };
+                 ST_ARENA = 100, ST_RING = 101, ST_OPS = 102, ST_NEED8 = 103, ST_PENDING = 255 };
 
 struct PairDesc {
     uint64_t q_byte, t_byte;   /* byte offsets into the raw sequence pool */
@@ -82,7 +82,7 @@ struct KParams {
     int32_t  xg, oeg, eg;
     int32_t  dM, dE;           /* ring depths: max(xg,oeg)+1, eg+1 */
     int32_t  ring_cap;         /* diagonals per ring row (WARP kernel) */
-    uint8_t  global_aln, adaptive, semi_literal, force8;
+    uint8_t  global_aln, adaptive, semi_literal, pad8_;
     int32_t  min_wf_len, max_dist_diff;
 };
 
@@ -228,12 +228,12 @@ template <bool CTA> struct Grp {
 struct ArenaView {
     const RowHdr   *hdr;
     const uint32_t *cells;
-    int64_t         s_last;    /* highest score with a header */
-    uint32_t        g;
-    __device__ __forceinline__ uint32_t get(int comp, int64_t s, int k) const
+    int             si_last;   /* index (score / g) of the highest score with a header */
+    /* si = score / g; every score reachable by the backtrace is a multiple of g */
+    __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
     {
-        if (s < 0 || s > s_last || (s % g) != 0) return 0;
-        const RowHdr h = hdr[s / g];
+        if (si < 0 || si > si_last) return 0;
+        const RowHdr h = hdr[si];
         if (k < h.lo || k > h.hi) return 0;
         return cells[h.off + (uint64_t)comp * (uint32_t)h.aw + (uint32_t)(k - h.alo)];
     }
@@ -271,8 +271,10 @@ __device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, in
                                         uint32_t s0, int Ak, Result &res, OpSink &sink)
 {
     const bool semi = !P.global_aln;
-    const int64_t x = P.x, oe = P.oe, e = P.e;
-    int64_t s = s0;
+    /* scores are carried as indices s/g: the reference's uint32 s-x etc. (wfa.go:760-762)
+     * wrap to "absent" exactly when the index goes negative */
+    const int x = P.xg, oe = P.oeg, e = P.eg;
+    int s = (int)(s0 / P.g);
     res.score = s0;
     res.tbegin = res.tend = res.qbegin = res.qend = 0;
     int k = Ak, h, v, tBegin = 0, qBegin = 0;
@@ -288,7 +290,7 @@ __device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, in
     else if (v < n) sink.add('H', (uint32_t)n - (uint32_t)v);
 
     while (v > 0 && h > 0) {                      /* :753 */
-        const int64_t sX = s - x, sO = s - oe, sE = s - e;
+        const int sX = s - x, sO = s - oe, sE = s - e;
         if (type == T_INS_EXT) {                  /* :767-777 */
             const uint32_t r1 = A.get(0, sO, k - 1), r2 = A.get(1, sE, k - 1);
             offset0 = (r1 | r2) ? max(r1 >> T_BITS, r2 >> T_BITS) + 1 : 0;
@@ -407,28 +409,30 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
     const int maxdiff = P.max_dist_diff;
 
     int status = ST_OK;
-    uint32_t s = 0; int si = 0;
+    uint32_t s = 0; int si = 0, cur = 0, cure = 0;
     uint32_t minS = 0; int lastK = Ak;
     unsigned long long c_cells = 0, c_written = 0, c_steps = 0;
 
     /* ---------------- forward: wfa.go:228-251 with next+extend fused per cell */
     for (;;) {
-        if (((uint64_t)(si + 2) * sizeof(RowHdr) + 3) / 4 + 8 > top) { status = ST_ARENA; break; }
+        const uint64_t hdr_words = (uint64_t)(si + 2) * (sizeof(RowHdr) / 4) + 8;     /* headers so far + this one + slack */
+        if (hdr_words > top) { status = ST_ARENA; break; }
         /* loop range (wfa.go:557-563); a superset is harmless, the clamp is not */
         int lo = INT_MAX, hi = INT_MIN;
         RowHdr hX, hO, hE; hX.lo = hO.lo = hE.lo = 1; hX.hi = hO.hi = hE.hi = 0;
         hX.alo = hO.alo = hE.alo = 0; hX.aw = hO.aw = hE.aw = 0; hX.off = hO.off = hE.off = 0;
-        int slX = 0, slO = 0, slE = 0, slEe = 0;
-        if (si - P.xg >= 0)  { slX = (si - P.xg) % dM;  hX = hring[slX]; }
-        if (si - P.oeg >= 0) { slO = (si - P.oeg) % dM; hO = hring[slO]; }
-        if (si - P.eg >= 0)  { slE = (si - P.eg) % dM;  hE = hring[slE]; slEe = (si - P.eg) % dE; }
+        /* ring slots: cur = si mod dM, cure = si mod dE, kept incrementally (no division) */
+        int slX = cur - P.xg, slO = cur - P.oeg, slE = cur - P.eg, slEe = cure - P.eg;
+        slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0; slEe += slEe < 0 ? dE : 0;
+        if (si >= P.xg)  hX = hring[slX];
+        if (si >= P.oeg) hO = hring[slO];
+        if (si >= P.eg)  hE = hring[slE];
         if (hX.lo <= hX.hi) { lo = min(lo, hX.lo); hi = max(hi, hX.hi); }
         if (hO.lo <= hO.hi) { lo = min(lo, hO.lo); hi = max(hi, hO.hi); }
         if (hE.lo <= hE.hi) { lo = min(lo, hE.lo); hi = max(hi, hE.hi); }
         if (lo <= hi) { lo = max(lo - 1, -(n - 1)); hi = min(hi + 1, m - 1); }
         const bool has_init = (s == 0) || (s == (uint32_t)x);
         if (has_init) { lo = min(lo, ilo); hi = max(hi, ihi); }
-        const int cur = si % dM, cure = si % dE;
 
         bool exists = false;
         int wlo = INT_MAX, whi = INT_MIN, endhit = 0;
@@ -437,7 +441,7 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
             aw = hi - lo + 1;
             if (!CTA && aw > cap) { status = ST_RING; break; }
             const uint64_t need = 3ull * (uint32_t)aw;
-            if (((uint64_t)(si + 2) * sizeof(RowHdr) + 3) / 4 + 8 + need > top) { status = ST_ARENA; break; }
+            if (hdr_words + need > top) { status = ST_ARENA; break; }
             off = top - need;
             const uint32_t *srcX, *srcO, *srcI, *srcD;
             if (CTA) { srcX = cells + hX.off; srcO = cells + hO.off; srcI = cells + hE.off + (uint32_t)hE.aw; srcD = cells + hE.off + 2ull * (uint32_t)hE.aw; }
@@ -485,7 +489,7 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
             G::sync();
             if (tid == 0) { hring[cur] = hc; hdrs[si] = hc; }
             G::sync();
-            s += P.g; si++;
+            s += P.g; si++; cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
             continue;
         }
         top = off;
@@ -543,7 +547,7 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
         G::sync();
         if (finished) { minS = s; lastK = Ak; if (hit) lastK = hitK; break; }
         if (hit) { minS = s; lastK = hitK; break; }
-        s += P.g; si++;
+        s += P.g; si++; cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
     }
 
     /* ---------------- semi-global, literal mode: scan every retained score downwards (wfa.go:287-371) */
@@ -581,7 +585,7 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
     if (status == ST_OK) {
         G::sync();
         if (tid == 0) {
-            ArenaView A; A.hdr = hdrs; A.cells = cells; A.s_last = (int64_t)s; A.g = P.g;
+            ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = si;
             OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
             sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
             back_trace(A, P, n, m, minS, lastK, res, sink);
@@ -649,7 +653,10 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
 }
 
 /* ------------------------------------------------------------------ kernels */
-template <bool CTA>
+/* One kernel per (symbol width, worker shape): the 2-bit kernels hand pairs with a
+ * non-ACGT byte back to the host (ST_NEED8), which re-queues them on the 8-bit
+ * kernel -- keeps each kernel's code (and I-cache footprint) to one instantiation. */
+template <int BITS, bool CTA>
 __global__ void __launch_bounds__(CTA ? 512 : 128)
 align_kernel(const KParams P)
 {
@@ -676,9 +683,14 @@ align_kernel(const KParams P)
         }
         if (item >= P.n_work) break;
         const uint32_t pair = P.work[item];
-        const bool eight = P.force8 || (P.pflags[pair] & 1);
-        if (eight) align_pair<8, CTA>(P, pair, smem, slot);
-        else       align_pair<2, CTA>(P, pair, smem, slot);
+        if (BITS == 2 && (P.pflags[pair] & 1)) {
+            if (G::tid() == 0) {
+                const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+                P.retry[r] = (uint64_t)ST_NEED8 << 32 | pair;
+            }
+            continue;
+        }
+        align_pair<BITS, CTA>(P, pair, smem, slot);
     }
 }
 

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -210,7 +211,7 @@ uint64_t arena_budget(wfacuda_ctx *ctx)
 }
 
 /* choose worker count / slot size for one class launch */
-int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint32_t> &order, bool cta,
+int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint32_t> &order, bool cta, int bits,
                 double boost, int min_ring_cap, LaunchPlan *lp)
 {
     uint64_t need_max = 0; int width_max = 1;
@@ -229,7 +230,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     if (cta) {
         wpb = 1; lp->threads = 512; lp->ring_cap = 0;
         lp->smem = worker_smem_bytes<true>(ctx->dM, ctx->dE, 0);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, align_kernel<true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, bits == 2 ? align_kernel<2, true> : align_kernel<8, true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
         blocks_per_sm = std::max(1, std::min(blocks_per_sm, 4));
     } else {
         wpb = 4;
@@ -240,7 +241,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
         while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap); }
         if (per_warp * wpb > ctx->smem_optin) return fail(ctx, WFACUDA_E_INVALID, "penalties need a deeper shared-memory ring than fits");
         lp->ring_cap = cap; lp->threads = wpb * 32; lp->smem = per_warp * wpb;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, align_kernel<false>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, bits == 2 ? align_kernel<2, false> : align_kernel<8, false>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
         blocks_per_sm = std::max(1, blocks_per_sm);
     }
     uint64_t workers = (uint64_t)ctx->sm_count * blocks_per_sm * wpb;
@@ -254,13 +255,14 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
 /* Runs one class of pairs to completion, re-queuing pairs that ran out of
  * ring width (WARP kernel -> wider ring or the CTA kernel through *to_cta),
  * arena (4x slot) or ops pool (pool doubled). */
-int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, bool cta, KParams base, std::vector<uint32_t> *to_cta)
+int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, bool cta, int bits, KParams base,
+              std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit)
 {
     double boost = 1.0; int min_cap = 0;
     for (int attempt = 0; !order.empty(); attempt++) {
         if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
         LaunchPlan lp;
-        int rc = plan_launch(ctx, b, order, cta, boost, min_cap, &lp);
+        int rc = plan_launch(ctx, b, order, cta, bits, boost, min_cap, &lp);
         if (rc) return rc;
         if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.workers))) return rc;
         if ((rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
@@ -276,8 +278,10 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes;
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = lp.ring_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
-        if (cta) align_kernel<true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
-        else     align_kernel<false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
+        if (cta) { if (bits == 2) align_kernel<2, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
+                   else           align_kernel<8, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
+        else     { if (bits == 2) align_kernel<2, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
+                   else           align_kernel<8, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
         CU(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++; ctx->stats.align_launches++;
         ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, lp.slot_bytes * lp.workers);
@@ -294,14 +298,15 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
         }
         std::vector<uint64_t> rl(hc.retry_n);
         CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
-        ctx->stats.retries += (uint32_t)rl.size();
         std::vector<uint32_t> again, wide;
         bool ops_full = false, arena_full = false;
         for (uint64_t r : rl) {
             const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
             if (st == ST_RING) wide.push_back(pair);
+            else if (st == ST_NEED8) { if (to_8bit) to_8bit->push_back(pair); }
             else { again.push_back(pair); if (st == ST_OPS) ops_full = true; else arena_full = true; }
         }
+        ctx->stats.retries += (uint32_t)(again.size() + wide.size());
         if (ops_full) {
             /* grow the completion-order pool; what successful pairs wrote stays valid */
             const uint64_t old_cap = ctx->ops_pool.cap / 8;
@@ -383,8 +388,10 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
         if (cudaEventCreateWithFlags(&ctx->pin_ev[i], cudaEventDisableTiming) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "event creation failed"); return bail(); }
     }
     ctx->smem_optin -= 1024;       /* room for the kernels' static shared memory */
-    if (cudaFuncSetAttribute(align_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
+    if (cudaFuncSetAttribute(align_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(align_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(align_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(align_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
         fail(ctx, WFACUDA_E_CUDA, "cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail();
     }
@@ -520,9 +527,13 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
 
 extern "C" {
 
+static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
+
 int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
 {
     if (!ctx || !b) return fail(ctx, WFACUDA_E_INVALID, "NULL ctx or batch");
+    const bool dbg = getenv("WFACUDA_DEBUG") != nullptr;
+    const double t_begin = now_ms();
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = b->n_pairs;
     int rc;
@@ -560,23 +571,29 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     P.xg = ctx->xg; P.oeg = ctx->oeg; P.eg = ctx->eg; P.dM = ctx->dM; P.dE = ctx->dE;
     P.global_aln = ctx->cfg.global_alignment ? 1 : 0; P.adaptive = ctx->cfg.adaptive ? 1 : 0;
     P.semi_literal = (ctx->cfg.flags & WFACUDA_FLAG_SEMIGLOBAL_LITERAL) ? 1 : 0;
-    P.force8 = (ctx->cfg.flags & WFACUDA_FLAG_FORCE_8BIT) ? 1 : 0;
     P.min_wf_len = (int32_t)std::min<uint32_t>(ctx->cfg.min_wf_len, 0x7fffffffu);
     P.max_dist_diff = (int32_t)std::min<uint32_t>(ctx->cfg.max_dist_diff, 0x7fffffffu);
 
-    std::vector<uint32_t> to_cta;
-    if ((rc = run_class(ctx, b, b->order_warp, false, P, &to_cta))) return rc;
+    const double t_prep = now_ms();
+    /* WARP class first (2-bit, then the pairs it handed back as 8-bit), then the CTA class */
+    const bool force8 = ctx->cfg.flags & WFACUDA_FLAG_FORCE_8BIT;
+    std::vector<uint32_t> to_cta, warp8, cta8;
+    if ((rc = run_class(ctx, b, b->order_warp, false, force8 ? 8 : 2, P, &to_cta, &warp8))) return rc;
+    if ((rc = run_class(ctx, b, warp8, false, 8, P, &to_cta, nullptr))) return rc;
+    const double t_warp = now_ms();
     std::vector<uint32_t> cta_order = b->order_cta;
     cta_order.insert(cta_order.end(), to_cta.begin(), to_cta.end());
     ctx->stats.pairs_warp = (uint32_t)(b->order_warp.size() - to_cta.size());
     ctx->stats.pairs_cta = (uint32_t)cta_order.size();
-    if ((rc = run_class(ctx, b, cta_order, true, P, nullptr))) return rc;
+    if ((rc = run_class(ctx, b, cta_order, true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
+    if ((rc = run_class(ctx, b, cta8, true, 8, P, nullptr, nullptr))) return rc;
+    ctx->stats.pairs_8bit = force8 ? (uint32_t)n_valid : (uint32_t)(warp8.size() + cta8.size());
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
     /* index-order offsets of the ops + total */
-    if ((rc = dev_take(ctx, &b->d_dst, &b->sz_dst, n * 8 + 8))) return rc;
+    if (!b->d_dst && (rc = dev_take(ctx, &b->d_dst, &b->sz_dst, n * 8 + 8))) return rc;
     const uint32_t nb = (uint32_t)((n + 1023) / 1024);
-    if ((rc = dev_take(ctx, &b->d_bsums, &b->sz_bsums, (size_t)nb * 8 + 16))) return rc;
+    if (!b->d_bsums && (rc = dev_take(ctx, &b->d_bsums, &b->sz_bsums, (size_t)nb * 8 + 16))) return rc;
     uint64_t *d_total = (uint64_t *)b->d_bsums + nb;
     if (n) {
         scan_block_kernel<<<nb, 1024, 0, ctx->stream>>>((const Result *)b->d_results, (uint32_t)n, (uint64_t *)b->d_dst, (uint64_t *)b->d_bsums);
@@ -590,7 +607,10 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     CU(ctx, cudaMemcpyAsync(&hc, ctx->ctr.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (b->ops_total) {
-        if ((rc = dev_take(ctx, &b->d_ops_sorted, &b->sz_ops_sorted, b->ops_total * 8))) return rc;
+        if (b->sz_ops_sorted < b->ops_total * 8) {
+            dev_give(ctx, &b->d_ops_sorted, &b->sz_ops_sorted);
+            if ((rc = dev_take(ctx, &b->d_ops_sorted, &b->sz_ops_sorted, b->ops_total * 8))) return rc;
+        }
         const int gb = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);
         gather_ops_kernel<<<gb, 256, 0, ctx->stream>>>((const Result *)b->d_results, (const uint64_t *)b->d_where, (const uint64_t *)b->d_dst,
                                                       (const uint64_t *)ctx->ops_pool.p, (uint64_t *)b->d_ops_sorted, (uint32_t)n);
@@ -606,6 +626,8 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     ctx->stats.score_steps = hc.steps; ctx->stats.ops = hc.ops; ctx->stats.seq_bases = b->seq_bases;
     ctx->last_ops_total = b->ops_total;
     b->ran = true;
+    if (dbg) fprintf(stderr, "[wfacuda] run: prep %.2f ms, warp class %.2f ms, rest %.2f ms | device: pack %.2f align %.2f total %.2f\n",
+                     t_prep - t_begin, t_warp - t_prep, now_ms() - t_warp, ctx->stats.ms_pack, ctx->stats.ms_align, ctx->stats.ms_total_device);
     return 0;
 }
 
