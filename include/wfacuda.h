@@ -153,6 +153,11 @@ int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pa
                               wfacuda_result *results,
                               uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off);
 
+/* The sharding rule of wfacuda_align_batch_multi on its own (pure host logic, no GPU):
+ * cuts[0..n_shards], shard d owns pairs [cuts[d], cuts[d+1]). */
+int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
+                       int adaptive, uint64_t *cuts);
+
 int wfacuda_get_stats(const wfacuda_ctx *ctx, wfacuda_stats *out);
 /* Last error text of the ctx (or of the calling thread when ctx is NULL). */
 const char *wfacuda_last_error(const wfacuda_ctx *ctx);

@@ -131,3 +131,17 @@ def test_seqs_txt_config1(built_lib):
     r = a.Align(*pairs[0])
     assert r.CIGAR() == "1X1I14M1D39M1D31M1D12M" and r.Score == 36
     assert (r.QBegin, r.QEnd, r.TBegin, r.TEnd, r.AlignLen, r.Matches, r.Gaps, r.GapRegions) == (2, 100, 3, 98, 99, 96, 3, 3)
+
+
+def test_align_batch_multi_two_ctx_same_device(built_lib):
+    """wfacuda_align_batch_multi: two ctxs (both on device 0 here) each take a cost-balanced
+    contiguous shard; results and ops must come back in index order, identical to the oracle."""
+    pairs = _random_pairs(21, 500, maxlen=300)
+    batch = datagen.Batch.from_pairs(pairs)
+    a, b = parity.make_aligner(adaptive=(10, 50)), parity.make_aligner(adaptive=(10, 50))
+    try:
+        gpu = a.AlignBatchMulti([b], batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)
+    finally:
+        a.close(); b.close()
+    ref = parity.oracle_batch(batch, adaptive=(10, 50))
+    parity.assert_same(batch, gpu, ref, "multi")

@@ -96,7 +96,7 @@ RESULT_DTYPE = np.dtype([("score", "<u4"), ("tbegin", "<i4"), ("tend", "<i4"), (
 EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda_set_config",
            "wfacuda_align_batch", "wfacuda_last_ops_total", "wfacuda_batch_upload", "wfacuda_batch_run",
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
-           "wfacuda_align_batch_multi", "wfacuda_get_stats", "wfacuda_last_error"]
+           "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error"]
 
 _LIB = None
 
@@ -131,12 +131,24 @@ def load_library():
     L.wfacuda_batch_free.argtypes = [vp, vp]
     L.wfacuda_align_batch_multi.restype = C.c_int
     L.wfacuda_align_batch_multi.argtypes = [C.POINTER(vp), C.c_int, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
+    L.wfacuda_shard_plan.restype = C.c_int
+    L.wfacuda_shard_plan.argtypes = [C.c_int, u64, u32p, u32p, C.c_int, vp]
     L.wfacuda_get_stats.restype = C.c_int
     L.wfacuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.wfacuda_last_error.restype = C.c_char_p
     L.wfacuda_last_error.argtypes = [vp]
     _LIB = L
     return L
+
+
+def shard_plan(n_shards, q_len, t_len, adaptive):
+    """cuts[0..n_shards] of wfacuda_align_batch_multi's static sharding (host logic only)."""
+    q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
+    cuts = np.zeros(n_shards + 1, np.uint64)
+    rc = load_library().wfacuda_shard_plan(n_shards, len(q_len), q_len.ctypes.data, t_len.ctypes.data, int(bool(adaptive)), cuts.ctypes.data)
+    if rc != 0:
+        raise WfaError("wfacuda_shard_plan failed (%d)" % rc)
+    return cuts
 
 
 def device_count():
@@ -280,6 +292,29 @@ class Aligner:
         if errs[0] is not None:
             raise errs[0]
         return res[0]
+
+    def AlignBatchMulti(self, others, seq_bytes, q_off, q_len, t_off, t_len, want_ops=True):
+        """One batch sharded over this Aligner's device and `others` (one ctx per device)."""
+        ctxs = [self._ctx] + [o._ctx for o in others]
+        arr = (C.c_void_p * len(ctxs))(*ctxs)
+        n = len(q_len)
+        seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
+        q_off = np.ascontiguousarray(q_off, np.uint64); t_off = np.ascontiguousarray(t_off, np.uint64)
+        q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
+        results = np.zeros(n, RESULT_DTYPE); ops_off = np.zeros(n, np.uint64)
+        cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64 if want_ops else 0
+        while True:
+            ops = np.empty(max(cap, 1), np.uint64)
+            rc = self._L.wfacuda_align_batch_multi(arr, len(ctxs), n, seq_bytes.ctypes.data, q_off.ctypes.data, q_len.ctypes.data,
+                                                   t_off.ctypes.data, t_len.ctypes.data, results.ctypes.data,
+                                                   ops.ctypes.data if want_ops else None, cap, ops_off.ctypes.data)
+            if rc == -4:
+                cap = int(self._L.wfacuda_last_ops_total(self._ctx))
+                continue
+            if rc != 0:
+                raise WfaError("wfacuda_align_batch_multi failed (%d): %s" % (rc, self._err()))
+            total = int(self._L.wfacuda_last_ops_total(self._ctx)) if want_ops else 0
+            return results, ops[:total], ops_off
 
     def stats(self):
         st = Stats()

@@ -534,6 +534,11 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     if (!ctx || !b) return fail(ctx, WFACUDA_E_INVALID, "NULL ctx or batch");
     const bool dbg = getenv("WFACUDA_DEBUG") != nullptr;
     const double t_begin = now_ms();
+    {   /* per-run counters start from zero; the upload's H2D bytes are kept */
+        const uint64_t h2d = b->ran ? 0 : ctx->stats.h2d_bytes;
+        ctx->stats = wfacuda_stats{};
+        ctx->stats.h2d_bytes = h2d;
+    }
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = b->n_pairs;
     int rc;
@@ -662,25 +667,33 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     return rc;
 }
 
+/* Contiguous index ranges of equal estimated cost: cost ~ (n+m) * band, band ~ (n+m) without
+ * heuristic (work grows with the square of the edit count), constant with wf-adaptive.
+ * cuts[0..n_shards]: shard d owns pairs [cuts[d], cuts[d+1]).  Pure host logic. */
+int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
+                       int adaptive, uint64_t *cuts)
+{
+    if (n_shards < 1 || !cuts || (n_pairs && (!q_len || !t_len))) return WFACUDA_E_INVALID;
+    std::vector<double> pre(n_pairs + 1, 0.0);
+    for (uint64_t i = 0; i < n_pairs; i++) {
+        const double nm = (double)q_len[i] + t_len[i];
+        pre[i + 1] = pre[i] + (adaptive ? nm : nm * nm) + 64.0;
+    }
+    cuts[0] = 0; cuts[n_shards] = n_pairs;
+    for (int d = 1; d < n_shards; d++)
+        cuts[d] = (uint64_t)(std::lower_bound(pre.begin(), pre.end(), pre[n_pairs] * d / n_shards) - pre.begin());
+    for (int d = 1; d <= n_shards; d++) cuts[d] = std::max(cuts[d], cuts[d - 1]);
+    return 0;
+}
+
 int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
                               const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
                               wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
 {
     if (!ctxs || n_ctx < 1) return fail(nullptr, WFACUDA_E_INVALID, "need at least one ctx");
     if (n_ctx == 1) return wfacuda_align_batch(ctxs[0], n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
-    /* contiguous index ranges of equal estimated cost: cost ~ (n+m) * band, band ~ (n+m) without
-     * heuristic (work grows with the square of the edit count), constant with wf-adaptive */
-    const bool quad = !ctxs[0]->cfg.adaptive;
-    std::vector<double> pre(n_pairs + 1, 0.0);
-    for (uint64_t i = 0; i < n_pairs; i++) {
-        const double nm = (double)q_len[i] + t_len[i];
-        pre[i + 1] = pre[i] + (quad ? nm * nm : nm) + 64.0;
-    }
     std::vector<uint64_t> cut(n_ctx + 1, n_pairs);
-    cut[0] = 0;
-    for (int d = 1; d < n_ctx; d++)
-        cut[d] = (uint64_t)(std::lower_bound(pre.begin(), pre.end(), pre[n_pairs] * d / n_ctx) - pre.begin());
-    for (int d = 1; d <= n_ctx; d++) cut[d] = std::max(cut[d], cut[d - 1]);
+    wfacuda_shard_plan(n_ctx, n_pairs, q_len, t_len, ctxs[0]->cfg.adaptive, cut.data());
     std::vector<wfacuda_batch *> bs(n_ctx, nullptr);
     std::vector<int> rcs(n_ctx, 0);
     {

@@ -1,0 +1,198 @@
+/*
+ * wfa.hpp -- C++ host-side mirror of the reference's Go API on top of the C ABI
+ * (include/wfacuda.h).  The reference is compiled Go and no Go toolchain exists
+ * in this image, so the host layer above the C ABI is C++: same names, argument
+ * meaning and error behaviour as /root/reference/wfa.go and wfa_cigar.go, so
+ * that code written against the Go package ports line by line:
+ *
+ *     auto *algn = wfa::New(&wfa::DefaultPenalties, &wfa::DefaultOptions);
+ *     algn->AdaptiveReduction(&wfa::DefaultAdaptiveOption);
+ *     wfa::AlignmentResult *r; wfa::Error err = algn->Align(q, t, &r);
+ *     r->CIGAR(false); r->AlignmentText(q, t, false, &Q, &A, &T);
+ *     wfa::RecycleAlignmentResult(r); wfa::RecycleAligner(algn);
+ *
+ * plus the batched entry point AlignBatch.  Header-only; link with -lwfacuda.
+ * There is no CPU path here: every Align goes through libwfacuda.so.
+ */
+#ifndef WFA_HOST_WFA_HPP
+#define WFA_HOST_WFA_HPP
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/wfacuda.h"
+
+namespace wfa {
+
+struct Penalties { uint32_t Mismatch, GapOpen, GapExt; };                    /* wfa.go:32-36 */
+struct AdaptiveReductionOption { uint32_t MinWFLen, MaxDistDiff, CutoffStep; }; /* wfa.go:46-50 */
+struct Options { bool GlobalAlignment; };                                    /* wfa.go:64-66 */
+
+static Penalties DefaultPenalties = {4, 6, 2};                               /* wfa.go:39-43 */
+static AdaptiveReductionOption DefaultAdaptiveOption = {10, 50, 1};          /* wfa.go:56-60 */
+static Options DefaultOptions = {true};                                      /* wfa.go:69-71 */
+
+constexpr int MaxSeqLen = (1 << 29) - 1;                                     /* wfa.go:190 */
+
+/* Go `error`: nullptr == nil; sentinels compare by identity like the reference's. */
+typedef const char *Error;
+static const char ErrEmptySeqText[] = "wfa: invalid empty sequence";                              /* wfa.go:187 */
+static const char ErrSeqTooLongText[] = "wfa: sequences longer than 536870911 are not supported"; /* wfa.go:193 */
+static const char ErrResourcesText[] = "wfacuda: pair needs more device memory than available";
+static const char ErrCutoffText[] = "cutoff step should not be 0";                                /* wfa.go:136 */
+static const Error ErrEmptySeq = ErrEmptySeqText;
+static const Error ErrSeqTooLong = ErrSeqTooLongText;
+static const Error ErrResources = ErrResourcesText;
+
+constexpr uint64_t OpM = 'M', OpD = 'D', OpI = 'I', OpX = 'X', OpH = 'H';    /* wfa_cigar.go:60-64 */
+constexpr uint64_t MaskLower32 = 4294967295ull;
+
+inline void Op(uint64_t op, char *o, uint32_t *n) { *o = (char)(op >> 32); *n = (uint32_t)(op & MaskLower32); } /* :56-58 */
+
+/* wfa_cigar.go:29-46, as left by process() (:136-214) -- computed on the GPU */
+struct AlignmentResult {
+    std::vector<uint64_t> Ops;
+    uint32_t Score = 0;
+    int TBegin = 0, TEnd = 0, QBegin = 0, QEnd = 0;
+    uint32_t AlignLen = 0, Matches = 0, Gaps = 0, GapRegions = 0;
+
+    /* trimOps, wfa_cigar.go:217-233 */
+    void aligned_range(size_t *b, size_t *e) const
+    {
+        long start = -1, end = -1;
+        for (size_t i = 0; i < Ops.size(); i++) if (Ops[i] >> 32 == OpM) { start = (long)i; break; }
+        for (size_t i = Ops.size(); i-- > 0;) if (Ops[i] >> 32 == OpM) { end = (long)i; break; }
+        *b = start < 0 ? 0 : (size_t)start; *e = (size_t)(end + 1);
+        if (start < 0) *e = 0;
+    }
+    /* wfa_cigar.go:236-255 */
+    std::string CIGAR(bool onlyAignedRegion) const
+    {
+        size_t b = 0, e = Ops.size();
+        if (onlyAignedRegion) aligned_range(&b, &e);
+        std::string s;
+        for (size_t i = b; i < e; i++) { s += std::to_string(Ops[i] & MaskLower32); s += (char)(Ops[i] >> 32); }
+        return s;
+    }
+    /* wfa_cigar.go:259-333 */
+    void AlignmentText(const std::string &q0, const std::string &t0, bool onlyAignedRegion,
+                       std::string *Q, std::string *A, std::string *T) const
+    {
+        size_t b = 0, e = Ops.size();
+        std::string q = q0, t = t0;
+        if (onlyAignedRegion) {
+            q = q0.substr((size_t)QBegin - 1, (size_t)(QEnd - QBegin + 1));
+            t = t0.substr((size_t)TBegin - 1, (size_t)(TEnd - TBegin + 1));
+            aligned_range(&b, &e);
+        }
+        Q->clear(); A->clear(); T->clear();
+        size_t v = 0, h = 0;
+        for (size_t i = b; i < e; i++) {
+            const uint64_t n = Ops[i] & MaskLower32;
+            switch (Ops[i] >> 32) {
+            case OpM: case OpX:
+                Q->append(q, v, n); A->append(n, (Ops[i] >> 32) == OpM ? '|' : ' '); T->append(t, h, n); v += n; h += n; break;
+            case OpI:
+                Q->append(n, '-'); A->append(n, ' '); T->append(t, h, n); h += n; break;
+            case OpD: case OpH:
+                Q->append(q, v, n); A->append(n, ' '); T->append(n, '-'); v += n; break;
+            }
+        }
+    }
+};
+
+class Aligner {
+public:
+    /* wfa.go:79-87: one Aligner per thread, not safe for concurrent Align calls */
+    Aligner(const Penalties *p, const Options *opt, int device) : p_(*p), opt_(*opt)
+    {
+        wfacuda_config c = config();
+        ctx_ = wfacuda_create(device, &c);
+        if (!ctx_) err_ = wfacuda_last_error(nullptr);
+    }
+    ~Aligner() { if (ctx_) wfacuda_destroy(ctx_); }
+    bool ok() const { return ctx_ != nullptr; }
+    const std::string &error() const { return err_; }
+
+    /* wfa.go:134-140 */
+    Error AdaptiveReduction(const AdaptiveReductionOption *ad)
+    {
+        if (ad->MinWFLen == 0) return ErrCutoffText;
+        ad_ = *ad; has_ad_ = true;
+        wfacuda_config c = config();
+        if (wfacuda_set_config(ctx_, &c) != 0) { err_ = wfacuda_last_error(ctx_); return err_.c_str(); }
+        return nullptr;
+    }
+
+    /* wfa.go:196-198 */
+    Error Align(const std::string &q, const std::string &t, AlignmentResult **out)
+    {
+        std::vector<AlignmentResult *> rs; std::vector<Error> es;
+        Error e = AlignBatch({q}, {t}, &rs, &es);
+        if (e) { *out = nullptr; return e; }
+        *out = rs[0];
+        return es[0];
+    }
+
+    /* New: many pairs per call.  results[i] == nullptr where errors[i] != nil. */
+    Error AlignBatch(const std::vector<std::string> &qs, const std::vector<std::string> &ts,
+                     std::vector<AlignmentResult *> *results, std::vector<Error> *errors)
+    {
+        const size_t n = qs.size();
+        std::vector<uint8_t> pool; std::vector<uint64_t> qo(n), to(n); std::vector<uint32_t> ql(n), tl(n);
+        size_t total = 0;
+        for (size_t i = 0; i < n; i++) total += qs[i].size() + ts[i].size();
+        pool.reserve(total + 16);
+        for (size_t i = 0; i < n; i++) {
+            qo[i] = pool.size(); ql[i] = (uint32_t)qs[i].size(); pool.insert(pool.end(), qs[i].begin(), qs[i].end());
+            to[i] = pool.size(); tl[i] = (uint32_t)ts[i].size(); pool.insert(pool.end(), ts[i].begin(), ts[i].end());
+        }
+        pool.resize(pool.size() + 16);
+        std::vector<wfacuda_result> res(n); std::vector<uint64_t> off(n);
+        std::vector<uint64_t> ops(total / 4 + 16 * n + 64);
+        int rc = wfacuda_align_batch(ctx_, n, pool.data(), qo.data(), ql.data(), to.data(), tl.data(), res.data(), ops.data(), ops.size(), off.data());
+        if (rc == WFACUDA_E_OPS_CAPACITY) {
+            ops.resize(wfacuda_last_ops_total(ctx_));
+            rc = wfacuda_align_batch(ctx_, n, pool.data(), qo.data(), ql.data(), to.data(), tl.data(), res.data(), ops.data(), ops.size(), off.data());
+        }
+        if (rc != 0) { err_ = wfacuda_last_error(ctx_); return err_.c_str(); }
+        results->assign(n, nullptr); errors->assign(n, nullptr);
+        for (size_t i = 0; i < n; i++) {
+            switch (res[i].status) {
+            case WFACUDA_OK: {
+                AlignmentResult *r = new AlignmentResult();
+                r->Ops.assign(ops.begin() + (long)off[i], ops.begin() + (long)off[i] + res[i].n_ops);
+                r->Score = res[i].score; r->TBegin = res[i].tbegin; r->TEnd = res[i].tend; r->QBegin = res[i].qbegin; r->QEnd = res[i].qend;
+                r->AlignLen = res[i].align_len; r->Matches = res[i].matches; r->Gaps = res[i].gaps; r->GapRegions = res[i].gap_regions;
+                (*results)[i] = r; break;
+            }
+            case WFACUDA_ERR_EMPTY_SEQ: (*errors)[i] = ErrEmptySeq; break;
+            case WFACUDA_ERR_SEQ_TOO_LONG: (*errors)[i] = ErrSeqTooLong; break;
+            default: (*errors)[i] = ErrResources;
+            }
+        }
+        return nullptr;
+    }
+
+private:
+    wfacuda_config config() const
+    {
+        wfacuda_config c{};
+        c.mismatch = p_.Mismatch; c.gap_open = p_.GapOpen; c.gap_ext = p_.GapExt;
+        c.global_alignment = opt_.GlobalAlignment ? 1 : 0;
+        c.adaptive = has_ad_ ? 1 : 0;
+        if (has_ad_) { c.min_wf_len = ad_.MinWFLen; c.max_dist_diff = ad_.MaxDistDiff; c.cutoff_step = ad_.CutoffStep; }
+        return c;
+    }
+    Penalties p_; Options opt_; AdaptiveReductionOption ad_{}; bool has_ad_ = false;
+    wfacuda_ctx *ctx_ = nullptr; std::string err_;
+};
+
+/* wfa.go:120-131 (ad is reset, unlike the reference's pooled Aligner) / :102-116 / wfa_cigar.go:92-96 */
+inline Aligner *New(const Penalties *p, const Options *opt, int device = 0) { return new Aligner(p, opt, device); }
+inline void RecycleAligner(Aligner *a) { delete a; }
+inline void RecycleAlignmentResult(AlignmentResult *r) { delete r; }
+
+} // namespace wfa
+#endif
