@@ -122,7 +122,8 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg);
  *   ops / ops_capacity   receives the concatenated AlignmentResult.Ops words
  *                        (op<<32|n, already reversed + merged, wfa_cigar.go:32,123,136-169);
  *                        may be NULL with capacity 0 to skip CIGARs
- *   ops_off[n_pairs]     start of pair i's words in ops (pairs in index order)
+ *   ops_off[n_pairs]     start of pair i's n_ops words in ops (regions never overlap; their
+ *                        order in the buffer is unspecified for large, internally chunked batches)
  * Returns 0, or a WFACUDA_E_* code.  On WFACUDA_E_OPS_CAPACITY results are
  * valid and wfacuda_last_ops_total() tells the capacity needed. */
 int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,

@@ -35,16 +35,26 @@ def assert_same(batch, gpu, ref, what=""):
             raise AssertionError("%s: %d/%d pairs differ in %s; first pair %d (n=%d m=%d)\n gpu %s %s\n ref %s %s\n q=%r\n t=%r" % (
                 what, len(bad), len(gr), f, i, len(q), len(t), {k: int(gr[k][i]) for k in FIELDS}, gc,
                 {k: int(rr[k][i]) for k in FIELDS}, rc, q[:200], t[:200]))
-    ok = gr["status"] == 0
-    # ops: both laid out in index order
-    assert np.array_equal(goff[ok], roff[ok]), what + ": ops offsets differ"
-    assert len(gops) == len(rops), what + ": total op count differs"
-    if not np.array_equal(gops, rops):
-        d = int(np.nonzero(gops != rops)[0][0])
-        i = int(np.searchsorted(roff, d, side="right") - 1)
+    # ops: compare pair by pair (the buffer order of pairs is unspecified for chunked batches)
+    gi, ri = ops_in_index_order(gr, gops, goff), ops_in_index_order(rr, rops, roff)
+    if not np.array_equal(gi, ri):
+        d = int(np.nonzero(gi != ri)[0][0])
+        starts = np.concatenate([[0], np.cumsum(np.where(rr["status"] == 0, rr["n_ops"], 0).astype(np.int64))])
+        i = int(np.searchsorted(starts, d, side="right") - 1)
         raise AssertionError("%s: ops differ first at word %d (pair %d)\n gpu %s\n ref %s" % (
             what, d, i, oracle_lib.ops_to_cigar(gops[int(goff[i]):int(goff[i]) + int(gr['n_ops'][i])]),
             oracle_lib.ops_to_cigar(rops[int(roff[i]):int(roff[i]) + int(rr['n_ops'][i])])))
+
+
+def ops_in_index_order(res, ops, off):
+    """Concatenate every pair's ops slice in pair-index order."""
+    cnt = np.where(res["status"] == 0, res["n_ops"], 0).astype(np.int64)
+    total = int(cnt.sum())
+    if total == 0:
+        return np.zeros(0, np.uint64)
+    excl = np.cumsum(cnt) - cnt
+    idx = np.repeat(off.astype(np.int64) - excl, cnt) + np.arange(total, dtype=np.int64)
+    return np.asarray(ops)[idx]
 
 
 def check(batch, what="", threads=8, gpu_kw=None, **cfgkw):

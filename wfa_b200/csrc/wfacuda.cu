@@ -22,6 +22,8 @@
 #include <cstring>
 #include <ctime>
 #include <numeric>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -56,6 +58,7 @@ struct wfacuda_ctx {
     uint64_t last_ops_total = 0;
     int last_rc = 0;
     std::string err;
+    std::vector<wfacuda_ctx *> subs;   /* pipeline workers of wfacuda_align_batch (same device) */
 };
 
 struct wfacuda_batch {
@@ -89,6 +92,8 @@ int fail(wfacuda_ctx *ctx, int code, const char *fmt, ...)
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? WFACUDA_E_NOMEM : WFACUDA_E_CUDA, \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
 
 uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
@@ -164,6 +169,29 @@ int staged_h2d(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
         done += chunk; which ^= 1;
     }
     ctx->stats.h2d_bytes += bytes;
+    return 0;
+}
+
+/* D2H into a host (pageable) region through the two pinned buffers (double buffered) */
+int staged_d2h(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    size_t issued = 0, done = 0, len[2] = {0, 0}, at[2] = {0, 0};
+    auto issue = [&](int w) -> cudaError_t {
+        const size_t chunk = std::min(ctx->pinned_cap, bytes - issued);
+        cudaError_t e = cudaMemcpyAsync(ctx->pinned[w], (const char *)src + issued, chunk, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->pin_ev[w], ctx->stream);
+        len[w] = chunk; at[w] = issued; issued += chunk;
+        return e;
+    };
+    if (bytes) CU(ctx, issue(0));
+    if (issued < bytes) CU(ctx, issue(1));
+    for (int w = 0; done < bytes; w ^= 1) {
+        CU(ctx, cudaEventSynchronize(ctx->pin_ev[w]));
+        memcpy((char *)dst + at[w], ctx->pinned[w], len[w]);
+        done += len[w];
+        if (issued < bytes) CU(ctx, issue(w));
+    }
+    ctx->stats.d2h_bytes += bytes;
     return 0;
 }
 
@@ -401,6 +429,8 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
 void wfacuda_destroy(wfacuda_ctx *ctx)
 {
     if (!ctx) return;
+    for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);
+    ctx->subs.clear();
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool}) if (b->p) cudaFree(b->p);
@@ -416,7 +446,11 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
-    if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) ctx->arena_scale = 1.0;
+    if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
+        ctx->arena_scale = 1.0;
+        for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
+        ctx->subs.clear();
+    }
     return rc;
 }
 
@@ -457,7 +491,9 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
     b->n_pairs = n_pairs;
     b->host_status.assign(n_pairs, ST_PENDING);
     b->descs.resize(n_pairs);
+    const bool dbg = getenv("WFACUDA_DEBUG") != nullptr;
     auto body = [&]() -> int {
+        const double t0 = now_ms();
         ctx->stats = wfacuda_stats{};
         /* validation (wfa.go:202-209) + extent of the byte pool actually referenced */
         uint64_t lo = UINT64_MAX, hi = 0, words = 0;
@@ -481,6 +517,7 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             b->max_nm = std::max<uint64_t>(b->max_nm, (uint64_t)d.n + d.m);
         }
         b->raw_bytes = hi - base; b->packed_words = words;
+        const double t1 = now_ms();
         int rc;
         if ((rc = dev_take(ctx, &b->d_raw, &b->sz_raw, b->raw_bytes + 64))) return rc;
         if ((rc = dev_take(ctx, &b->d_packed, &b->sz_packed, (words + 16) * 4))) return rc;
@@ -492,7 +529,9 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             if ((rc = staged_h2d(ctx, b->d_raw, seq_bytes + base, b->raw_bytes))) return rc;
             CU(ctx, cudaMemsetAsync((char *)b->d_raw + b->raw_bytes, 0, 64, ctx->stream));
         }
+        const double t2 = now_ms();
         if (n_pairs) if ((rc = staged_h2d(ctx, b->d_descs, b->descs.data(), n_pairs * sizeof(PairDesc)))) return rc;
+        const double t3 = now_ms();
         /* cost bins: longest first (counting sort on log2-ish buckets of n+m) */
         const bool force_cta = ctx->cfg.flags & WFACUDA_FLAG_FORCE_CTA;
         const int warp_cap_max = 512;
@@ -516,7 +555,9 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             if (cls[i] == 2) continue;
             (cls[i] ? b->order_cta : b->order_warp)[counts[cls[i]][bucket_of[i]]++] = (uint32_t)i;
         }
+        const double t4 = now_ms();
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (dbg) fprintf(stderr, "[wfacuda] upload: validate+descs %.2f ms, alloc+seq h2d %.2f, descs h2d %.2f, binning %.2f, sync %.2f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now_ms() - t4);
         return 0;
     };
     if (body() != 0) { wfacuda_batch_free(ctx, b); return nullptr; }
@@ -526,8 +567,6 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
 } // extern "C"
 
 extern "C" {
-
-static double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
 
 int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
 {
@@ -643,28 +682,118 @@ int wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *r
     if (!b->ran) return fail(ctx, WFACUDA_E_INVALID, "batch has not been run");
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = b->n_pairs;
-    if (n && results) { CU(ctx, cudaMemcpy(results, b->d_results, n * sizeof(Result), cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += n * sizeof(Result); }
-    if (n && ops_off) { CU(ctx, cudaMemcpy(ops_off, b->d_dst, n * 8, cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += n * 8; }
+    const double t0 = now_ms();
+    int rc;
+    if (n && results) if ((rc = staged_d2h(ctx, results, b->d_results, n * sizeof(Result)))) return rc;
+    if (n && ops_off) if ((rc = staged_d2h(ctx, ops_off, b->d_dst, n * 8))) return rc;
     if (ops) {
         if (b->ops_total > ops_capacity)
             return fail(ctx, WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)b->ops_total);
-        if (b->ops_total) { CU(ctx, cudaMemcpy(ops, b->d_ops_sorted, b->ops_total * 8, cudaMemcpyDeviceToHost)); ctx->stats.d2h_bytes += b->ops_total * 8; }
+        if (b->ops_total) if ((rc = staged_d2h(ctx, ops, b->d_ops_sorted, b->ops_total * 8))) return rc;
     }
+    if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] download: %.2f ms for %.1f MB\n", now_ms() - t0, ctx->stats.d2h_bytes / 1e6);
     return 0;
 }
 
-int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
-                        const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
-                        wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
+static int align_batch_single(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                              const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
+                              wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
 {
-    if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
-    if (n_pairs && !results) return fail(ctx, WFACUDA_E_INVALID, "results is NULL");
     wfacuda_batch *b = wfacuda_batch_upload(ctx, n_pairs, seq_bytes, q_off, q_len, t_off, t_len);
     if (!b) return ctx->last_rc ? ctx->last_rc : WFACUDA_E_CUDA;
     int rc = wfacuda_batch_run(ctx, b);
     if (rc == 0) rc = wfacuda_batch_download(ctx, b, results, ops, ops_capacity, ops_off);
     wfacuda_batch_free(ctx, b);
     return rc;
+}
+
+static void add_stats(wfacuda_stats &a, const wfacuda_stats &s)
+{
+    a.pairs += s.pairs; a.cells += s.cells; a.cells_written += s.cells_written; a.score_steps += s.score_steps;
+    a.ops += s.ops; a.seq_bases += s.seq_bases; a.arena_bytes = std::max(a.arena_bytes, s.arena_bytes);
+    a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes; a.kernel_launches += s.kernel_launches;
+    a.align_launches += s.align_launches; a.retries += s.retries; a.pairs_warp += s.pairs_warp;
+    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
+    a.ms_total_device += s.ms_total_device;
+}
+
+/* Large batches are cut into chunks that flow through a few worker contexts on the same
+ * device (own stream, pinned staging and arena each), so that host staging, H2D, kernels
+ * and D2H of different chunks overlap.  Each chunk's ops land in one contiguous region of
+ * the caller's buffer, claimed when the chunk's op count is known. */
+int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
+                        const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
+                        wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
+{
+    if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
+    if (n_pairs && !results) return fail(ctx, WFACUDA_E_INVALID, "results is NULL");
+    if (n_pairs && (!seq_bytes || !q_off || !q_len || !t_off || !t_len)) return fail(ctx, WFACUDA_E_INVALID, "NULL input array");
+    const uint64_t kMinChunk = 65536;
+    if (n_pairs < 2 * kMinChunk || getenv("WFACUDA_NO_PIPELINE")) {
+        int rc = align_batch_single(ctx, n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
+        if (rc == 0 || rc == WFACUDA_E_OPS_CAPACITY) return rc;
+        return rc;
+    }
+    /* chunk size: >= kMinChunk pairs (fills the persistent grid several times), <= ~192 MB of sequence */
+    uint64_t sample_bytes = 0;
+    const uint64_t sample_n = std::min<uint64_t>(n_pairs, 4096);
+    for (uint64_t i = 0; i < sample_n; i++) sample_bytes += (uint64_t)q_len[i * (n_pairs / sample_n)] + t_len[i * (n_pairs / sample_n)];
+    const double mean_bytes = std::max(1.0, (double)sample_bytes / (double)sample_n);
+    uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)(24e6 / mean_bytes)));
+    if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+    const uint64_t n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    unsigned kmax = std::min<unsigned>(8, hw / 2);
+    if (const char *e = getenv("WFACUDA_PIPE_WORKERS")) kmax = std::max(1, atoi(e));
+    const int K = (int)std::min<uint64_t>(kmax, n_chunks);
+    while ((int)ctx->subs.size() < K) {
+        wfacuda_config c = ctx->cfg;
+        const uint64_t share = arena_budget(ctx) / (uint64_t)K;
+        c.arena_budget_bytes = share;
+        wfacuda_ctx *sub = wfacuda_create(ctx->device, &c);
+        if (!sub) return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: %s", g_tls_error.c_str());
+        ctx->subs.push_back(sub);
+    }
+    std::atomic<uint64_t> next{0}, cursor{0};
+    std::atomic<int> first_err{0};
+    std::mutex mu;
+    wfacuda_stats total{};
+    std::string err_text;
+    const double t_begin = now_ms();
+    auto work = [&](int k) {
+        wfacuda_ctx *sub = ctx->subs[k];
+        for (;;) {
+            const uint64_t c = next.fetch_add(1);
+            if (c >= n_chunks || first_err.load()) break;
+            const uint64_t a = c * chunk_pairs, cnt = std::min(chunk_pairs, n_pairs - a);
+            wfacuda_batch *b = wfacuda_batch_upload(sub, cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
+            int rc = b ? wfacuda_batch_run(sub, b) : (sub->last_rc ? sub->last_rc : WFACUDA_E_CUDA);
+            if (rc == 0) {
+                const uint64_t tot = b->ops_total, base = cursor.fetch_add(tot);
+                const bool fits = ops && base + tot <= ops_capacity;
+                rc = wfacuda_batch_download(sub, b, results + a, fits ? ops + base : nullptr, fits ? tot : 0, ops_off ? ops_off + a : nullptr);
+                if (rc == 0 && ops_off) for (uint64_t i = 0; i < cnt; i++) ops_off[a + i] += base;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                add_stats(total, sub->stats);
+                if (rc != 0 && first_err.load() == 0) { first_err.store(rc); err_text = sub->err; }
+            }
+            if (b) wfacuda_batch_free(sub, b);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < K; k++) th.emplace_back(work, k);
+    work(0);
+    for (auto &t : th) t.join();
+    ctx->stats = total;
+    ctx->last_ops_total = cursor.load();
+    if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] align_batch: %llu chunks of %llu pairs on %d workers, %.2f ms\n",
+                                          (unsigned long long)n_chunks, (unsigned long long)chunk_pairs, K, now_ms() - t_begin);
+    if (first_err.load()) return fail(ctx, first_err.load(), "%s", err_text.c_str());
+    if (ops && cursor.load() > ops_capacity)
+        return fail(ctx, WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)cursor.load());
+    return 0;
 }
 
 /* Contiguous index ranges of equal estimated cost: cost ~ (n+m) * band, band ~ (n+m) without
