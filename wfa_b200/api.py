@@ -190,6 +190,18 @@ class AlignmentResult:
         return bytes(Q), bytes(A), bytes(T)
 
 
+def ops_in_index_order(results, ops, ops_off):
+    """Concatenate every pair's ops slice in pair-index order (the buffer order of pairs is
+    unspecified for internally chunked batches)."""
+    cnt = np.where(results["status"] == 0, results["n_ops"], 0).astype(np.int64)
+    total = int(cnt.sum())
+    if total == 0:
+        return np.zeros(0, np.uint64)
+    excl = np.cumsum(cnt) - cnt
+    idx = np.repeat(np.asarray(ops_off).astype(np.int64) - excl, cnt) + np.arange(total, dtype=np.int64)
+    return np.asarray(ops)[idx]
+
+
 def Op(op):                                     # wfa_cigar.go:56-58
     return chr(int(op) >> 32), int(op) & MaskLower32
 

@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace wfak {
 
@@ -82,6 +83,7 @@ struct KParams {
     int32_t  xg, oeg, eg;
     int32_t  dM, dE;           /* ring depths: max(xg,oeg)+1, eg+1 */
     int32_t  ring_cap;         /* diagonals per ring row (WARP kernel) */
+    int32_t  group;            /* WARP kernel: pairs per group (1..32), slot_bytes = group * sub-slot */
     uint8_t  global_aln, adaptive, semi_literal, pad8_;
     int32_t  min_wf_len, max_dist_diff;
 };
@@ -363,21 +365,33 @@ __device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, in
 }
 
 /* ------------------------------------------------------------------ one pair
- * Shared-memory layout of a worker (32-bit words):
- *   hdrs  RowHdr[dM]         ring of the most recent row headers
+ * Shared-memory layout of a worker:
+ *   meta  int4[dM]           ring of the most recent rows' {alo, lo, hi, aw}
+ *   roff  u64[dM]            their arena offsets (used by the CTA worker)
  *   red   int[96]            block reduction scratch (CTA only)
+ *   bslot u64[2]             broadcast scratch
  *   rM    u32[dM][cap]       WARP only: ring of M rows
  *   rI,rD u32[dE][cap]       WARP only: ring of I / D rows
  */
 template <bool CTA> __host__ __device__ inline size_t worker_smem_bytes(int dM, int dE, int cap)
 {
-    size_t b = (size_t)dM * sizeof(RowHdr) + 96 * sizeof(int) + 16;
+    size_t b = (size_t)dM * 16 + (size_t)dM * 8 + 96 * sizeof(int) + 16;
     if (!CTA) b += (size_t)(dM + 2 * dE) * (size_t)cap * 4;
     return (b + 15) & ~(size_t)15;
 }
 
+/* what the forward pass leaves for the backtrace (uniform over the worker) */
+struct FwdOut {
+    int      status;
+    uint32_t minS;            /* score the backtrace starts from */
+    int      lastK, si;       /* its diagonal; index of the last header written */
+    int      n, m;
+    uint64_t top;             /* first used cell word of the slot (rows occupy [top, slot_words)) */
+    unsigned long long c_cells, c_written, c_steps;
+};
+
 template <int BITS, bool CTA>
-__device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char *smem, uint8_t *slot)
+__device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned char *smem, uint8_t *slot, const uint64_t slot_bytes)
 {
     using G = Grp<CTA>;
     const int tid = G::tid(), gsz = G::size();
@@ -389,8 +403,9 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
     if (BITS == 2) { Q.w = P.packed + pd.q_word; Q.mis = 0; T.w = P.packed + pd.t_word; T.mis = 0; }
     else { Q.w = P.raw + (pd.q_byte >> 2); Q.mis = (uint32_t)(pd.q_byte & 3); T.w = P.raw + (pd.t_byte >> 2); T.mis = (uint32_t)(pd.t_byte & 3); }
 
-    RowHdr   *hring = reinterpret_cast<RowHdr *>(smem);
-    int      *red   = reinterpret_cast<int *>(hring + dM);
+    int4     *meta  = reinterpret_cast<int4 *>(smem);
+    uint64_t *roff  = reinterpret_cast<uint64_t *>(meta + dM);
+    int      *red   = reinterpret_cast<int *>(roff + dM);
     uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 96);          /* 16 bytes of broadcast scratch */
     uint32_t *rM = reinterpret_cast<uint32_t *>(bslot + 2);
     uint32_t *rI = rM + (size_t)dM * cap;
@@ -398,62 +413,72 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
 
     RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);                /* grows up, index s/g */
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);              /* rows grow down from the end */
-    const uint64_t slot_words = P.slot_bytes >> 2;
-    uint64_t top = slot_words;
+    /* word offsets inside the slot: 32 bits are enough for a warp's slot (the host keeps
+     * WARP-class slots below 16 GB), the CTA worker may own more */
+    typedef typename std::conditional<CTA, uint64_t, uint32_t>::type Off;
+    const Off slot_words = (Off)(slot_bytes >> 2);
+    Off top = slot_words;
+    Off hdr_limit = 2 * (sizeof(RowHdr) / 4) + 8;                      /* words used by headers incl. the next one + slack */
 
-    for (int i = tid; i < dM; i += gsz) { RowHdr z; z.alo = 0; z.aw = 0; z.lo = 1; z.hi = 0; z.off = 0; hring[i] = z; }
+    const int4 EMPTY = make_int4(0, 1, 0, 0);
+    for (int i = tid; i < dM; i += gsz) meta[i] = EMPTY;
     G::sync();
 
-    const int x = (int)P.x;
+    const int x = (int)P.x, xg = P.xg, oeg = P.oeg, eg = P.eg;
     const int ilo = P.global_aln ? 0 : -(n - 1), ihi = P.global_aln ? 0 : m - 1;   /* init cells, wfa.go:160-183 */
     const int maxdiff = P.max_dist_diff;
 
     int status = ST_OK;
     uint32_t s = 0; int si = 0, cur = 0, cure = 0;
     uint32_t minS = 0; int lastK = Ak;
-    unsigned long long c_cells = 0, c_written = 0, c_steps = 0;
+    typedef typename std::conditional<CTA, unsigned long long, uint32_t>::type Cnt;   /* per-pair work counters */
+    Cnt c_cells = 0, c_written = 0, c_steps = 0;
 
     /* ---------------- forward: wfa.go:228-251 with next+extend fused per cell */
     for (;;) {
-        const uint64_t hdr_words = (uint64_t)(si + 2) * (sizeof(RowHdr) / 4) + 8;     /* headers so far + this one + slack */
-        if (hdr_words > top) { status = ST_ARENA; break; }
+        /* source rows s-x, s-o-e, s-e: ring slots kept incrementally (no division) */
+        int slX = cur - xg, slO = cur - oeg, slE = cur - eg, slEe = cure - eg;
+        slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0; slEe += slEe < 0 ? dE : 0;
+        const int4 hX = si >= xg ? meta[slX] : EMPTY;
+        const int4 hO = si >= oeg ? meta[slO] : EMPTY;
+        const int4 hE = si >= eg ? meta[slE] : EMPTY;
         /* loop range (wfa.go:557-563); a superset is harmless, the clamp is not */
         int lo = INT_MAX, hi = INT_MIN;
-        RowHdr hX, hO, hE; hX.lo = hO.lo = hE.lo = 1; hX.hi = hO.hi = hE.hi = 0;
-        hX.alo = hO.alo = hE.alo = 0; hX.aw = hO.aw = hE.aw = 0; hX.off = hO.off = hE.off = 0;
-        /* ring slots: cur = si mod dM, cure = si mod dE, kept incrementally (no division) */
-        int slX = cur - P.xg, slO = cur - P.oeg, slE = cur - P.eg, slEe = cure - P.eg;
-        slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0; slEe += slEe < 0 ? dE : 0;
-        if (si >= P.xg)  hX = hring[slX];
-        if (si >= P.oeg) hO = hring[slO];
-        if (si >= P.eg)  hE = hring[slE];
-        if (hX.lo <= hX.hi) { lo = min(lo, hX.lo); hi = max(hi, hX.hi); }
-        if (hO.lo <= hO.hi) { lo = min(lo, hO.lo); hi = max(hi, hO.hi); }
-        if (hE.lo <= hE.hi) { lo = min(lo, hE.lo); hi = max(hi, hE.hi); }
+        if (hX.y <= hX.z) { lo = min(lo, hX.y); hi = max(hi, hX.z); }
+        if (hO.y <= hO.z) { lo = min(lo, hO.y); hi = max(hi, hO.z); }
+        if (hE.y <= hE.z) { lo = min(lo, hE.y); hi = max(hi, hE.z); }
         if (lo <= hi) { lo = max(lo - 1, -(n - 1)); hi = min(hi + 1, m - 1); }
         const bool has_init = (s == 0) || (s == (uint32_t)x);
         if (has_init) { lo = min(lo, ilo); hi = max(hi, ihi); }
 
         bool exists = false;
         int wlo = INT_MAX, whi = INT_MIN, endhit = 0;
-        int aw = 0; uint64_t off = 0;
+        int aw = 0; Off off = 0;
         if (lo <= hi) {
             aw = hi - lo + 1;
             if (!CTA && aw > cap) { status = ST_RING; break; }
-            const uint64_t need = 3ull * (uint32_t)aw;
-            if (hdr_words + need > top) { status = ST_ARENA; break; }
+            const Off need = (Off)3 * (Off)aw;
+            if (top < hdr_limit || top - hdr_limit < need) { status = ST_ARENA; break; }
             off = top - need;
             const uint32_t *srcX, *srcO, *srcI, *srcD;
-            if (CTA) { srcX = cells + hX.off; srcO = cells + hO.off; srcI = cells + hE.off + (uint32_t)hE.aw; srcD = cells + hE.off + 2ull * (uint32_t)hE.aw; }
-            else { srcX = rM + (size_t)slX * cap; srcO = rM + (size_t)slO * cap; srcI = rI + (size_t)slEe * cap; srcD = rD + (size_t)slEe * cap; }
-            (void)slE;
+            if (CTA) {
+                const uint64_t oX = roff[slX], oO = roff[slO], oE = roff[slE];
+                srcX = cells + oX; srcO = cells + oO; srcI = cells + oE + (uint32_t)hE.w; srcD = cells + oE + 2ull * (uint32_t)hE.w;
+            } else {
+                srcX = rM + slX * cap; srcO = rM + slO * cap; srcI = rI + slEe * cap; srcD = rD + slEe * cap;
+            }
+            /* bias the row pointers so that diagonal k indexes directly; presence = unsigned range test */
+            srcX -= hX.x; srcO -= hO.x; srcI -= hE.x; srcD -= hE.x;
+            const uint32_t cntX = (uint32_t)max(hX.z - hX.y + 1, 0), cntO = (uint32_t)max(hO.z - hO.y + 1, 0), cntE = (uint32_t)max(hE.z - hE.y + 1, 0);
+            uint32_t *dstM = cells + off - lo, *dstI = dstM + aw, *dstD = dstI + aw;
+            uint32_t *ringM = rM + cur * cap - lo, *ringI = rI + cure * cap - lo, *ringD = rD + cure * cap - lo;
             for (int k = lo + tid; k <= hi; k += gsz) {
                 uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
-                if (k - 1 >= hO.lo && k - 1 <= hO.hi) mo_l = srcO[k - 1 - hO.alo];
-                if (k + 1 >= hO.lo && k + 1 <= hO.hi) mo_r = srcO[k + 1 - hO.alo];
-                if (k - 1 >= hE.lo && k - 1 <= hE.hi) ie_l = srcI[k - 1 - hE.alo];
-                if (k + 1 >= hE.lo && k + 1 <= hE.hi) de_r = srcD[k + 1 - hE.alo];
-                if (k >= hX.lo && k <= hX.hi) mx = srcX[k - hX.alo];
+                if ((uint32_t)(k - 1 - hO.y) < cntO) mo_l = srcO[k - 1];
+                if ((uint32_t)(k + 1 - hO.y) < cntO) mo_r = srcO[k + 1];
+                if ((uint32_t)(k - 1 - hE.y) < cntE) ie_l = srcI[k - 1];
+                if ((uint32_t)(k + 1 - hE.y) < cntE) de_r = srcD[k + 1];
+                if ((uint32_t)(k - hX.y) < cntX) mx = srcX[k];
                 Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
                 if (has_init && c.M == 0 && k >= ilo && k <= ihi) {
                     /* initComponents (wfa.go:155-183): cell (k) of the first row / column;
@@ -473,11 +498,8 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
                     wlo = min(wlo, k); whi = max(whi, k);
                     if (k == Ak && h >= m) endhit = 1;            /* wfa.go:235-239 */
                 }
-                const int idx = k - lo;
-                if (!CTA) { rM[(size_t)cur * cap + idx] = c.M; rI[(size_t)cure * cap + idx] = c.I; rD[(size_t)cure * cap + idx] = c.D; }
-                cells[off + idx] = c.M;
-                cells[off + (uint32_t)aw + idx] = c.I;
-                cells[off + 2ull * (uint32_t)aw + idx] = c.D;
+                if (!CTA) { ringM[k] = c.M; ringI[k] = c.I; ringD[k] = c.D; }
+                dstM[k] = c.M; dstI[k] = c.I; dstD[k] = c.D;
             }
             G::reduce3(wlo, whi, endhit, red);
             exists = wlo <= whi;
@@ -487,17 +509,18 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
         if (!exists) {
             hc.alo = 0; hc.aw = 0; hc.off = 0;
             G::sync();
-            if (tid == 0) { hring[cur] = hc; hdrs[si] = hc; }
+            if (tid == 0) { meta[cur] = EMPTY; hdrs[si] = hc; }
             G::sync();
-            s += P.g; si++; cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
+            s += P.g; si++; hdr_limit += sizeof(RowHdr) / 4;
+            cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
             continue;
         }
         top = off;
-        c_steps++; c_cells += (unsigned)(whi - wlo + 1); c_written += (unsigned)aw;
+        c_steps++; c_cells += (Cnt)(whi - wlo + 1); c_written += (Cnt)aw;
         int elo = wlo, ehi = whi;
         const uint32_t *rowM;
         if (CTA) { G::sync(); rowM = cells + off; }                     /* arena row visible to the block */
-        else { __syncwarp(); rowM = rM + (size_t)cur * cap; }
+        else { __syncwarp(); rowM = rM + cur * cap; }
 
         bool finished = endhit != 0;
         if (!finished && P.adaptive && whi - wlo + 1 >= P.min_wf_len) {
@@ -543,11 +566,12 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
         }
         hc.lo = elo; hc.hi = ehi;
         G::sync();
-        if (tid == 0) { hring[cur] = hc; hdrs[si] = hc; }
+        if (tid == 0) { meta[cur] = make_int4(lo, elo, ehi, aw); if (CTA) roff[cur] = (uint64_t)off; hdrs[si] = hc; }
         G::sync();
         if (finished) { minS = s; lastK = Ak; if (hit) lastK = hitK; break; }
         if (hit) { minS = s; lastK = hitK; break; }
-        s += P.g; si++; cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
+        s += P.g; si++; hdr_limit += sizeof(RowHdr) / 4;
+        cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
     }
 
     /* ---------------- semi-global, literal mode: scan every retained score downwards (wfa.go:287-371) */
@@ -573,7 +597,27 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
         }
     }
 
-    /* ---------------- backtrace + result (one thread), then the group copies the ops out */
+    FwdOut f;
+    f.status = status; f.minS = minS; f.lastK = lastK; f.si = si; f.n = n; f.m = m; f.top = (uint64_t)top;
+    f.c_cells = c_cells; f.c_written = c_written; f.c_steps = c_steps;
+    return f;
+}
+
+/* ---------------- backtrace + result, one thread per pair, then the whole group copies the
+ * ops out and reduces the stats (CTA worker). */
+template <bool CTA>
+__device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOut &f, unsigned char *smem, uint8_t *slot, const uint64_t slot_bytes)
+{
+    using G = Grp<CTA>;
+    const int tid = G::tid(), gsz = G::size();
+    int      *red   = reinterpret_cast<int *>(reinterpret_cast<uint64_t *>(reinterpret_cast<int4 *>(smem) + P.dM) + P.dM);
+    uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 96);
+    RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);
+    uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
+    const uint64_t slot_words = slot_bytes >> 2, top = f.top;
+    const int si = f.si;
+    int status = f.status;
+
     Result res;
     res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
     res.align_len = res.matches = res.gaps = res.gap_regions = 0; res.n_ops = 0;
@@ -588,7 +632,7 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
             ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = si;
             OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
             sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
-            back_trace(A, P, n, m, minS, lastK, res, sink);
+            back_trace(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
             res.n_ops = sink.n;
             if (sink.overflow) res.status = ST_ARENA;
         }
@@ -618,7 +662,6 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
                 if (o == 'M') matches += cnt;
                 else if (o == 'I' || o == 'D') { gaps += cnt; regions++; }
             }
-            /* sums via the same all-reduce shape: use warp adds, then block */
             for (int d = 16; d > 0; d >>= 1) {
                 alen += __shfl_xor_sync(0xffffffffu, alen, d); matches += __shfl_xor_sync(0xffffffffu, matches, d);
                 gaps += __shfl_xor_sync(0xffffffffu, gaps, d); regions += __shfl_xor_sync(0xffffffffu, regions, d);
@@ -642,8 +685,8 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
             const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
             P.retry[r] = (uint64_t)status << 32 | pair;
         } else {
-            atomicAdd(&P.ctr->cells, c_cells); atomicAdd(&P.ctr->cells_written, c_written);
-            atomicAdd(&P.ctr->steps, c_steps); atomicAdd(&P.ctr->ops, (unsigned long long)n_ops);
+            atomicAdd(&P.ctr->cells, f.c_cells); atomicAdd(&P.ctr->cells_written, f.c_written);
+            atomicAdd(&P.ctr->steps, f.c_steps); atomicAdd(&P.ctr->ops, (unsigned long long)n_ops);
             atomicMax(&P.ctr->arena_used_max, (unsigned long long)((slot_words - top + scratch_w) * 4 + 8ull * n_ops));
         }
         /* score/begin/end live in thread 0's res; stats were reduced to every thread */
@@ -652,16 +695,103 @@ __device__ void align_pair(const KParams &P, const uint32_t pair, unsigned char 
     G::sync();
 }
 
+/* ---------------- WARP worker: the forward passes of up to 32 pairs are followed by their
+ * backtraces run lane-parallel (lane j owns pair j and its sub-slot): the pointer-chasing
+ * backtrace costs one warp instruction stream for the whole group instead of one per pair. */
+__device__ __noinline__ void finish_group(const KParams &P, const bool have, const uint32_t pair, const FwdOut &f, uint8_t *slot, const uint64_t slot_bytes)
+{
+    const int lane = threadIdx.x & 31;
+    RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);
+    uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
+    const uint64_t slot_words = slot_bytes >> 2, top = f.top;
+    const uint64_t scratch_w = (((uint64_t)(f.si + 1) * sizeof(RowHdr) + 7) / 8) * 2;
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w);
+    int status = have ? f.status : ST_PENDING;
+
+    Result res;
+    res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
+    res.align_len = res.matches = res.gaps = res.gap_regions = 0; res.n_ops = 0;
+    res.status = (uint8_t)status; res.pad_[0] = res.pad_[1] = res.pad_[2] = 0;
+    uint32_t n_ops = 0;
+    __syncwarp();
+    if (status == ST_OK) {
+        ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = f.si;
+        OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
+        sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
+        back_trace(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
+        n_ops = sink.n;
+        if (sink.overflow) { status = ST_ARENA; n_ops = 0; }
+    }
+    __syncwarp();
+    /* one pool reservation per group: exclusive scan of n_ops over the lanes */
+    uint32_t incl = n_ops;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const uint32_t group_total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && group_total) base = atomicAdd(&P.ctr->ops_cursor, (unsigned long long)group_total);
+    base = __shfl_sync(0xffffffffu, base, 0) + (incl - n_ops);
+    if (status == ST_OK) {
+        if (P.ops_pool != nullptr && base + n_ops > P.ops_cap) status = ST_OPS;
+        else {
+            /* process() (wfa_cigar.go:136-214) in one pass: copy reversed, and take the stats
+             * between the first and the last M as a difference of running sums */
+            unsigned alen = 0, matches = 0, gaps = 0, regions = 0;
+            unsigned a0 = 0, m0 = 0, g0 = 0, r0 = 0, a1 = 0, m1 = 0, g1 = 0, r1 = 0;
+            bool seenM = false;
+            for (uint32_t i = 0; i < n_ops; i++) {
+                const uint64_t op = scratch[n_ops - 1 - i];
+                if (P.ops_pool) P.ops_pool[base + i] = op;
+                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
+                if (o == 'M' && !seenM) { seenM = true; a0 = alen; m0 = matches; g0 = gaps; r0 = regions; }
+                alen += cnt;
+                if (o == 'M') matches += cnt;
+                else if (o == 'I' || o == 'D') { gaps += cnt; regions++; }
+                if (o == 'M') { a1 = alen; m1 = matches; g1 = gaps; r1 = regions; }
+            }
+            if (seenM) { res.align_len = a1 - a0; res.matches = m1 - m0; res.gaps = g1 - g0; res.gap_regions = r1 - r0; }
+            else if (n_ops) {                                      /* no M: begin = end = 0 (:170-186) */
+                const uint64_t op = scratch[n_ops - 1];
+                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
+                res.align_len = cnt; res.matches = 0;
+                res.gaps = (o == 'I' || o == 'D') ? cnt : 0; res.gap_regions = (o == 'I' || o == 'D') ? 1 : 0;
+            }
+            res.n_ops = n_ops;
+            P.ops_where[pair] = base;
+        }
+    }
+    if (have) {
+        res.status = (uint8_t)status;
+        if (status != ST_OK) {
+            const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+            P.retry[r] = (uint64_t)status << 32 | pair;
+        } else {
+            atomicMax(&P.ctr->arena_used_max, (unsigned long long)((slot_words - top + scratch_w) * 4 + 8ull * n_ops));
+        }
+        P.results[pair] = res;
+    }
+    /* work counters: one atomic per group */
+    unsigned long long c0 = (have && status == ST_OK) ? f.c_cells : 0, c1 = (have && status == ST_OK) ? f.c_written : 0;
+    unsigned long long c2 = (have && status == ST_OK) ? f.c_steps : 0, c3 = (have && status == ST_OK) ? n_ops : 0;
+    for (int d = 16; d > 0; d >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.ctr->cells, c0); atomicAdd(&P.ctr->cells_written, c1);
+        atomicAdd(&P.ctr->steps, c2); atomicAdd(&P.ctr->ops, c3);
+    }
+    __syncwarp();
+}
+
 /* ------------------------------------------------------------------ kernels */
 /* One kernel per (symbol width, worker shape): the 2-bit kernels hand pairs with a
  * non-ACGT byte back to the host (ST_NEED8), which re-queues them on the 8-bit
  * kernel -- keeps each kernel's code (and I-cache footprint) to one instantiation. */
 template <int BITS, bool CTA>
-__global__ void __launch_bounds__(CTA ? 512 : 128)
+__global__ void __launch_bounds__(CTA ? 512 : 128, CTA ? 1 : 7)
 align_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    using G = Grp<CTA>;
     const int wpb = CTA ? 1 : (int)(blockDim.x >> 5);
     const int wib = CTA ? 0 : (int)(threadIdx.x >> 5);
     const size_t wbytes = worker_smem_bytes<CTA>(P.dM, P.dE, P.ring_cap);
@@ -670,27 +800,53 @@ align_kernel(const KParams P)
     uint8_t *slot = P.arena + worker * P.slot_bytes;
     __shared__ uint32_t next_item[4];
 
-    for (;;) {
-        uint32_t item = 0;
-        if (G::tid() == 0) item = (uint32_t)atomicAdd(&P.ctr->work_next, 1ull);
-        if (CTA) {
+    if (CTA) {
+        for (;;) {
             __syncthreads();
-            if (threadIdx.x == 0) next_item[0] = item;
+            if (threadIdx.x == 0) next_item[0] = (uint32_t)atomicAdd(&P.ctr->work_next, 1ull);
             __syncthreads();
-            item = next_item[0];
-        } else {
-            item = __shfl_sync(0xffffffffu, item, 0);
-        }
-        if (item >= P.n_work) break;
-        const uint32_t pair = P.work[item];
-        if (BITS == 2 && (P.pflags[pair] & 1)) {
-            if (G::tid() == 0) {
-                const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
-                P.retry[r] = (uint64_t)ST_NEED8 << 32 | pair;
+            const uint32_t item = next_item[0];
+            if (item >= P.n_work) break;
+            const uint32_t pair = P.work[item];
+            if (BITS == 2 && (P.pflags[pair] & 1)) {
+                if (threadIdx.x == 0) {
+                    const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+                    P.retry[r] = (uint64_t)ST_NEED8 << 32 | pair;
+                }
+                continue;
             }
-            continue;
+            const FwdOut f = forward_pair<BITS, CTA>(P, pair, smem, slot, P.slot_bytes);
+            finish_single<CTA>(P, pair, f, smem, slot, P.slot_bytes);
         }
-        align_pair<BITS, CTA>(P, pair, smem, slot);
+    } else {
+        /* groups of P.group pairs: forward passes one after the other (sub-slot j of the
+         * warp's slot), then the backtraces of the whole group lane-parallel */
+        const int lane = threadIdx.x & 31;
+        const uint32_t G = (uint32_t)P.group;
+        const uint64_t sub_bytes = P.slot_bytes / G;
+        for (;;) {
+            uint32_t first = 0;
+            if (lane == 0) first = (uint32_t)atomicAdd(&P.ctr->work_next, (unsigned long long)G);
+            first = __shfl_sync(0xffffffffu, first, 0);
+            if (first >= P.n_work) break;
+            const uint32_t cnt = min(G, P.n_work - first);
+            FwdOut mine; mine.status = ST_PENDING; mine.minS = 0; mine.lastK = 0; mine.si = 0; mine.n = mine.m = 0; mine.top = 0;
+            mine.c_cells = mine.c_written = mine.c_steps = 0;
+            bool have = false; uint32_t my_pair = 0;
+            for (uint32_t j = 0; j < cnt; j++) {
+                const uint32_t pair = P.work[first + j];
+                if (BITS == 2 && (P.pflags[pair] & 1)) {
+                    if (lane == 0) {
+                        const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+                        P.retry[r] = (uint64_t)ST_NEED8 << 32 | pair;
+                    }
+                    continue;
+                }
+                const FwdOut f = forward_pair<BITS, CTA>(P, pair, smem, slot + (uint64_t)j * sub_bytes, sub_bytes);
+                if (lane == (int)j) { mine = f; have = true; my_pair = pair; }
+            }
+            finish_group(P, have, my_pair, mine, slot + (uint64_t)lane * sub_bytes, sub_bytes);
+        }
     }
 }
 

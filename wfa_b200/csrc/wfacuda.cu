@@ -226,6 +226,7 @@ Need estimate(const wfacuda_ctx *ctx, uint32_t n, uint32_t m)
 
 struct LaunchPlan {
     bool cta; int threads; int blocks; int ring_cap; size_t smem; uint64_t slot_bytes; uint64_t workers; bool slot_at_max;
+    int group;               /* WARP class: pairs per warp group; slot_bytes is per pair, a warp owns group * slot_bytes */
 };
 
 uint64_t arena_budget(wfacuda_ctx *ctx)
@@ -276,6 +277,17 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     workers = std::min<uint64_t>(workers, ((order.size() + wpb - 1) / wpb) * wpb);
     if (slot * workers > budget) workers = std::max<uint64_t>(wpb, (budget / slot) / wpb * wpb);
     if (slot * workers > budget) { slot = (budget / workers) & ~255ull; lp->slot_at_max = true; }
+    const uint64_t kWarpSlotMax = 15ull << 30;      /* the WARP worker indexes its slot with 32-bit word offsets */
+    if (!cta && slot > kWarpSlotMax) { slot = kWarpSlotMax; lp->slot_at_max = true; }
+    lp->group = 1;
+    if (!cta) {
+        /* as many pairs per group as the budget allows (lane-parallel backtrace), at most 32,
+         * and no more than keeps every warp busy */
+        uint64_t g = std::min<uint64_t>(32, budget / std::max<uint64_t>(1, slot * workers));
+        g = std::min<uint64_t>(g, std::max<uint64_t>(1, order.size() / std::max<uint64_t>(1, workers)));
+        if (const char *e = getenv("WFACUDA_GROUP")) g = std::min<uint64_t>(g, (uint64_t)std::max(1, atoi(e)));
+        lp->group = (int)std::max<uint64_t>(1, g);
+    }
     lp->blocks = (int)(workers / wpb); lp->workers = workers; lp->slot_bytes = slot;
     return 0;
 }
@@ -292,7 +304,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
         LaunchPlan lp;
         int rc = plan_launch(ctx, b, order, cta, bits, boost, min_cap, &lp);
         if (rc) return rc;
-        if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.workers))) return rc;
+        if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.group * lp.workers))) return rc;
         if ((rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
         CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -303,7 +315,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
         CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
         KParams P = base;
         P.work = (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
-        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes;
+        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = lp.ring_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         if (cta) { if (bits == 2) align_kernel<2, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
@@ -312,10 +324,11 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
                    else           align_kernel<8, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
         CU(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++; ctx->stats.align_launches++;
-        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, lp.slot_bytes * lp.workers);
+        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, lp.slot_bytes * lp.group * lp.workers);
         Counters hc;
         CU(ctx, cudaMemcpyAsync(&hc, dc, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch %s bits=%d attempt %d: %zu pairs, %d blocks x %d thr, ring_cap %d, group %d, smem %zu, slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", cta ? "cta" : "warp", bits, attempt, order.size(), lp.blocks, lp.threads, lp.ring_cap, lp.group, lp.smem, lp.slot_bytes / 1024.0, ctx->arena_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
         if (hc.retry_n == 0) {
             /* learn: aim the next batch's slots at 1.5x the largest slot use seen */
             if (attempt == 0 && !lp.slot_at_max && lp.slot_bytes > 16384 && hc.arena_used_max) {
@@ -352,7 +365,14 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
             else if (to_cta) to_cta->insert(to_cta->end(), wide.begin(), wide.end());
         }
         if (arena_full) {
-            if (lp.slot_at_max && lp.workers <= (uint64_t)(cta ? 1 : 4)) {
+            if (!cta && lp.slot_at_max && lp.slot_bytes >= (15ull << 30) && to_cta) {
+                /* beyond a warp slot's 32-bit reach: the CTA worker takes them */
+                for (uint64_t r : rl) if ((uint32_t)(r >> 32) == ST_ARENA) to_cta->push_back((uint32_t)r);
+                std::vector<uint32_t> keep;
+                for (uint64_t r : rl) if ((uint32_t)(r >> 32) == ST_OPS) keep.push_back((uint32_t)r);
+                if (min_cap) keep.insert(keep.end(), wide.begin(), wide.end());
+                again.swap(keep);
+            } else if (lp.slot_at_max && lp.workers <= (uint64_t)(cta ? 1 : 4)) {
                 /* one worker already owns the whole budget: these pairs cannot be aligned on this device */
                 std::vector<uint32_t> keep;
                 for (uint64_t r : rl) {
