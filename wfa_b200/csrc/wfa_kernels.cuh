@@ -191,7 +191,7 @@ template <bool CTA> struct Grp {
     __device__ static __forceinline__ int tid()  { return CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31); }
     __device__ static __forceinline__ int size() { return CTA ? (int)blockDim.x : 32; }
     __device__ static __forceinline__ void sync() { if (CTA) __syncthreads(); else __syncwarp(); }
-    /* all-reduce of (min a, max b, or c) over the group; red = 3*32 ints of block scratch */
+    /* all-reduce of (min a, max b, or c) over the group; red = 4*32 ints of block scratch */
     __device__ static __forceinline__ void reduce3(int &a, int &b, int &c, int *red)
     {
         a = __reduce_min_sync(0xffffffffu, a);
@@ -368,14 +368,14 @@ __device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, in
  * Shared-memory layout of a worker:
  *   meta  int4[dM]           ring of the most recent rows' {alo, lo, hi, aw}
  *   roff  u64[dM]            their arena offsets (used by the CTA worker)
- *   red   int[96]            block reduction scratch (CTA only)
+ *   red   int[128]           block reduction scratch (CTA only)
  *   bslot u64[2]             broadcast scratch
  *   rM    u32[dM][cap]       WARP only: ring of M rows
  *   rI,rD u32[dE][cap]       WARP only: ring of I / D rows
  */
 template <bool CTA> __host__ __device__ inline size_t worker_smem_bytes(int dM, int dE, int cap)
 {
-    size_t b = (size_t)dM * 16 + (size_t)dM * 8 + 96 * sizeof(int) + 16;
+    size_t b = (size_t)dM * 16 + (size_t)dM * 8 + 128 * sizeof(int) + 16;
     if (!CTA) b += (size_t)(dM + 2 * dE) * (size_t)cap * 4;
     return (b + 15) & ~(size_t)15;
 }
@@ -406,7 +406,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     int4     *meta  = reinterpret_cast<int4 *>(smem);
     uint64_t *roff  = reinterpret_cast<uint64_t *>(meta + dM);
     int      *red   = reinterpret_cast<int *>(roff + dM);
-    uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 96);          /* 16 bytes of broadcast scratch */
+    uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 128);         /* 16 bytes of broadcast scratch */
     uint32_t *rM = reinterpret_cast<uint32_t *>(bslot + 2);
     uint32_t *rI = rM + (size_t)dM * cap;
     uint32_t *rD = rI + (size_t)dE * cap;
@@ -611,7 +611,7 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
     using G = Grp<CTA>;
     const int tid = G::tid(), gsz = G::size();
     int      *red   = reinterpret_cast<int *>(reinterpret_cast<uint64_t *>(reinterpret_cast<int4 *>(smem) + P.dM) + P.dM);
-    uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 96);
+    uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 128);
     RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
     const uint64_t slot_words = slot_bytes >> 2, top = f.top;
@@ -670,10 +670,10 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
                 const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
                 unsigned *ured = reinterpret_cast<unsigned *>(red);
                 __syncthreads();
-                if (lane == 0 && wid < 24) { ured[wid] = alen; ured[24 + wid] = matches; ured[48 + wid] = gaps; ured[72 + wid] = regions; }
+                if (lane == 0) { ured[wid] = alen; ured[32 + wid] = matches; ured[64 + wid] = gaps; ured[96 + wid] = regions; }
                 __syncthreads();
                 alen = matches = gaps = regions = 0;
-                for (int w = 0; w < nw && w < 24; w++) { alen += ured[w]; matches += ured[24 + w]; gaps += ured[48 + w]; regions += ured[72 + w]; }
+                for (int w = 0; w < nw; w++) { alen += ured[w]; matches += ured[32 + w]; gaps += ured[64 + w]; regions += ured[96 + w]; }
             }
             res.align_len = alen; res.matches = matches; res.gaps = gaps; res.gap_regions = regions;
             if (tid == 0) P.ops_where[pair] = base;
@@ -788,7 +788,7 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
  * non-ACGT byte back to the host (ST_NEED8), which re-queues them on the 8-bit
  * kernel -- keeps each kernel's code (and I-cache footprint) to one instantiation. */
 template <int BITS, bool CTA>
-__global__ void __launch_bounds__(CTA ? 512 : 128, CTA ? 1 : 7)
+__global__ void __launch_bounds__(CTA ? 1024 : 128, CTA ? 1 : 7)
 align_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

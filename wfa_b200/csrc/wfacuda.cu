@@ -54,6 +54,7 @@ struct wfacuda_ctx {
     void *pinned[2] = {nullptr, nullptr}; size_t pinned_cap = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
+    int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
     wfacuda_stats stats{};
     uint64_t last_ops_total = 0;
     int last_rc = 0;
@@ -257,7 +258,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     uint64_t slot = (std::max<uint64_t>(need_max, 16384) + 255) & ~255ull;
     int wpb, blocks_per_sm = 1;
     if (cta) {
-        wpb = 1; lp->threads = 512; lp->ring_cap = 0;
+        wpb = 1; lp->threads = 1024; lp->ring_cap = 0;
         lp->smem = worker_smem_bytes<true>(ctx->dM, ctx->dE, 0);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, bits == 2 ? align_kernel<2, true> : align_kernel<8, true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
         blocks_per_sm = std::max(1, std::min(blocks_per_sm, 4));
@@ -265,7 +266,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
         wpb = 4;
         int cap = 64;
         while (cap < (int)(width_max * 0.6) + 8 && cap < 512) cap *= 2;
-        cap = std::max(cap, min_ring_cap);
+        cap = std::max(cap, std::max(min_ring_cap, ctx->ring_cap_learned));
         size_t per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap);
         while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap); }
         if (per_warp * wpb > ctx->smem_optin) return fail(ctx, WFACUDA_E_INVALID, "penalties need a deeper shared-memory ring than fits");
@@ -331,7 +332,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch %s bits=%d attempt %d: %zu pairs, %d blocks x %d thr, ring_cap %d, group %d, smem %zu, slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", cta ? "cta" : "warp", bits, attempt, order.size(), lp.blocks, lp.threads, lp.ring_cap, lp.group, lp.smem, lp.slot_bytes / 1024.0, ctx->arena_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
         if (hc.retry_n == 0) {
             /* learn: aim the next batch's slots at 1.5x the largest slot use seen */
-            if (attempt == 0 && !lp.slot_at_max && lp.slot_bytes > 16384 && hc.arena_used_max) {
+            if (boost == 1.0 && !lp.slot_at_max && lp.slot_bytes > 16384 && hc.arena_used_max) {
                 const double r = 1.5 * (double)hc.arena_used_max / (double)lp.slot_bytes;
                 ctx->arena_scale = std::min(64.0, std::max(1.0 / 64, ctx->arena_scale * std::min(1.0, std::max(r, 0.25))));
             }
@@ -361,7 +362,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
         if (!wide.empty()) {
             /* many pairs too wide for the ring: double it once if shared memory allows; else the CTA kernel */
             const bool can_double = !cta && lp.ring_cap < 512 && worker_smem_bytes<false>(ctx->dM, ctx->dE, lp.ring_cap * 2) * 4 <= ctx->smem_optin;
-            if (can_double && wide.size() > 256) { min_cap = lp.ring_cap * 2; again.insert(again.end(), wide.begin(), wide.end()); }
+            if (can_double && wide.size() > 256) { min_cap = lp.ring_cap * 2; ctx->ring_cap_learned = min_cap; again.insert(again.end(), wide.begin(), wide.end()); }
             else if (to_cta) to_cta->insert(to_cta->end(), wide.begin(), wide.end());
         }
         if (arena_full) {
@@ -467,7 +468,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0;
+        ctx->arena_scale = 1.0; ctx->ring_cap_learned = 0;
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -766,10 +767,19 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     unsigned kmax = std::min<unsigned>(8, hw / 2);
     if (const char *e = getenv("WFACUDA_PIPE_WORKERS")) kmax = std::max(1, atoi(e));
     const int K = (int)std::min<uint64_t>(kmax, n_chunks);
+    if ((int)ctx->subs.size() < K && ctx->arena.p) {
+        /* the workers need the room: drop this ctx's own arena (re-grown on demand) */
+        cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+        cudaFree(ctx->arena.p); ctx->arena.p = nullptr; ctx->arena.cap = 0;
+    }
     while ((int)ctx->subs.size() < K) {
         wfacuda_config c = ctx->cfg;
-        const uint64_t share = arena_budget(ctx) / (uint64_t)K;
-        c.arena_budget_bytes = share;
+        size_t free_b = 0, total_b = 0;
+        cudaSetDevice(ctx->device);
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 8ull << 30; }
+        uint64_t share = (uint64_t)(0.80 * (double)free_b) / (uint64_t)(K - (int)ctx->subs.size());
+        if (ctx->cfg.arena_budget_bytes) share = std::min<uint64_t>(share, ctx->cfg.arena_budget_bytes / (uint64_t)K);
+        c.arena_budget_bytes = std::max<uint64_t>(share, 64u << 20);
         wfacuda_ctx *sub = wfacuda_create(ctx->device, &c);
         if (!sub) return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: %s", g_tls_error.c_str());
         ctx->subs.push_back(sub);
