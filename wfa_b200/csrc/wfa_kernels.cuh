@@ -231,13 +231,15 @@ struct ArenaView {
     const RowHdr   *hdr;
     const uint32_t *cells;
     int             si_last;   /* index (score / g) of the highest score with a header */
+    bool            aos;       /* row layout: cell-major M,I,D triples (WARP worker) or three arrays (CTA worker) */
     /* si = score / g; every score reachable by the backtrace is a multiple of g */
     __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
     {
         if (si < 0 || si > si_last) return 0;
         const RowHdr h = hdr[si];
         if (k < h.lo || k > h.hi) return 0;
-        return cells[h.off + (uint64_t)comp * (uint32_t)h.aw + (uint32_t)(k - h.alo)];
+        const uint32_t d = (uint32_t)(k - h.alo);
+        return cells[h.off + (aos ? 3ull * d + (uint32_t)comp : (uint64_t)comp * (uint32_t)h.aw + d)];
     }
 };
 
@@ -364,19 +366,36 @@ __device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, in
     sink.flush();
 }
 
+/* ------------------------------------------------------------------ explicit shared-memory access
+ * The WARP worker addresses its ring with 32-bit shared-window byte addresses kept in
+ * registers (made opaque to the compiler, which otherwise re-derives them from the kernel
+ * parameters inside the diagonal loop). */
+template <int OFF> __device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0+%1], %2;" :: "r"(addr), "n"(OFF), "r"(v) : "memory");
+}
+__device__ __forceinline__ void keep(uint32_t &x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void keep(int &x) { asm volatile("" : "+r"(x)); }
+template <typename T> __device__ __forceinline__ void keep_ptr(T *&p) { asm volatile("" : "+l"(p)); }
+
 /* ------------------------------------------------------------------ one pair
  * Shared-memory layout of a worker:
  *   meta  int4[dM]           ring of the most recent rows' {alo, lo, hi, aw}
  *   roff  u64[dM]            their arena offsets (used by the CTA worker)
  *   red   int[128]           block reduction scratch (CTA only)
  *   bslot u64[2]             broadcast scratch
- *   rM    u32[dM][cap]       WARP only: ring of M rows
- *   rI,rD u32[dE][cap]       WARP only: ring of I / D rows
+ *   ring  u32[dM][cap][3]    WARP only: ring of rows, cell-major {M, I, D} triples
  */
 template <bool CTA> __host__ __device__ inline size_t worker_smem_bytes(int dM, int dE, int cap)
 {
     size_t b = (size_t)dM * 16 + (size_t)dM * 8 + 128 * sizeof(int) + 16;
-    if (!CTA) b += (size_t)(dM + 2 * dE) * (size_t)cap * 4;
+    if (!CTA) b += (size_t)dM * (size_t)cap * 12;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -397,7 +416,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     const int tid = G::tid(), gsz = G::size();
     const PairDesc pd = P.pairs[pair];
     const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
-    const int dM = P.dM, dE = P.dE, cap = P.ring_cap;
+    const int dM = P.dM, cap = P.ring_cap;
 
     SeqView<BITS> Q, T;
     if (BITS == 2) { Q.w = P.packed + pd.q_word; Q.mis = 0; T.w = P.packed + pd.t_word; T.mis = 0; }
@@ -407,9 +426,14 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     uint64_t *roff  = reinterpret_cast<uint64_t *>(meta + dM);
     int      *red   = reinterpret_cast<int *>(roff + dM);
     uint64_t *bslot = reinterpret_cast<uint64_t *>(red + 128);         /* 16 bytes of broadcast scratch */
-    uint32_t *rM = reinterpret_cast<uint32_t *>(bslot + 2);
-    uint32_t *rI = rM + (size_t)dM * cap;
-    uint32_t *rD = rI + (size_t)dE * cap;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(bslot + 2);
+    /* Row layout.  WARP worker: cell-major triples {M,I,D} in the ring and in the arena, so one
+     * address register per row serves all three components at immediate offsets.  CTA worker:
+     * three arrays per row (its source rows are re-read from L2, where triples would triple the
+     * sectors touched by the M-only reads). */
+    constexpr int KS = CTA ? 1 : 3;                                     /* words between neighbouring diagonals */
+    uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
+    keep(ring_sa);
 
     RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);                /* grows up, index s/g */
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);              /* rows grow down from the end */
@@ -429,7 +453,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     const int maxdiff = P.max_dist_diff;
 
     int status = ST_OK;
-    uint32_t s = 0; int si = 0, cur = 0, cure = 0;
+    uint32_t s = 0; int si = 0, cur = 0;
     uint32_t minS = 0; int lastK = Ak;
     typedef typename std::conditional<CTA, unsigned long long, uint32_t>::type Cnt;   /* per-pair work counters */
     Cnt c_cells = 0, c_written = 0, c_steps = 0;
@@ -437,8 +461,8 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     /* ---------------- forward: wfa.go:228-251 with next+extend fused per cell */
     for (;;) {
         /* source rows s-x, s-o-e, s-e: ring slots kept incrementally (no division) */
-        int slX = cur - xg, slO = cur - oeg, slE = cur - eg, slEe = cure - eg;
-        slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0; slEe += slEe < 0 ? dE : 0;
+        int slX = cur - xg, slO = cur - oeg, slE = cur - eg;
+        slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0;
         const int4 hX = si >= xg ? meta[slX] : EMPTY;
         const int4 hO = si >= oeg ? meta[slO] : EMPTY;
         const int4 hE = si >= eg ? meta[slE] : EMPTY;
@@ -460,26 +484,9 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
             const Off need = (Off)3 * (Off)aw;
             if (top < hdr_limit || top - hdr_limit < need) { status = ST_ARENA; break; }
             off = top - need;
-            const uint32_t *srcX, *srcO, *srcI, *srcD;
-            if (CTA) {
-                const uint64_t oX = roff[slX], oO = roff[slO], oE = roff[slE];
-                srcX = cells + oX; srcO = cells + oO; srcI = cells + oE + (uint32_t)hE.w; srcD = cells + oE + 2ull * (uint32_t)hE.w;
-            } else {
-                srcX = rM + slX * cap; srcO = rM + slO * cap; srcI = rI + slEe * cap; srcD = rD + slEe * cap;
-            }
-            /* bias the row pointers so that diagonal k indexes directly; presence = unsigned range test */
-            srcX -= hX.x; srcO -= hO.x; srcI -= hE.x; srcD -= hE.x;
             const uint32_t cntX = (uint32_t)max(hX.z - hX.y + 1, 0), cntO = (uint32_t)max(hO.z - hO.y + 1, 0), cntE = (uint32_t)max(hE.z - hE.y + 1, 0);
-            uint32_t *dstM = cells + off - lo, *dstI = dstM + aw, *dstD = dstI + aw;
-            uint32_t *ringM = rM + cur * cap - lo, *ringI = rI + cure * cap - lo, *ringD = rD + cure * cap - lo;
-            for (int k = lo + tid; k <= hi; k += gsz) {
-                uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
-                if ((uint32_t)(k - 1 - hO.y) < cntO) mo_l = srcO[k - 1];
-                if ((uint32_t)(k + 1 - hO.y) < cntO) mo_r = srcO[k + 1];
-                if ((uint32_t)(k - 1 - hE.y) < cntE) ie_l = srcI[k - 1];
-                if ((uint32_t)(k + 1 - hE.y) < cntE) de_r = srcD[k + 1];
-                if ((uint32_t)(k - hX.y) < cntX) mx = srcX[k];
-                Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
+            /* one diagonal after its five source words are in: init overlay, extend, bookkeeping */
+            auto finish_cell = [&](Cell3 &c, const int k) {
                 if (has_init && c.M == 0 && k >= ilo && k <= ihi) {
                     /* initComponents (wfa.go:155-183): cell (k) of the first row / column;
                      * next's Set overwrites it when both write (wfa_wavefront.go:93) */
@@ -498,8 +505,48 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                     wlo = min(wlo, k); whi = max(whi, k);
                     if (k == Ak && h >= m) endhit = 1;            /* wfa.go:235-239 */
                 }
-                if (!CTA) { ringM[k] = c.M; ringI[k] = c.I; ringD[k] = c.D; }
-                dstM[k] = c.M; dstI[k] = c.I; dstD[k] = c.D;
+            };
+            if (CTA) {
+                /* source rows from the arena (three arrays per row), diagonal k indexes directly */
+                const uint64_t oX = roff[slX], oO = roff[slO], oE = roff[slE];
+                const uint32_t *srcX = cells + oX - hX.x, *srcO = cells + oO - hO.x;
+                const uint32_t *srcI = cells + oE + (uint32_t)hE.w - hE.x, *srcD = cells + oE + 2ull * (uint32_t)hE.w - hE.x;
+                uint32_t *dstM = cells + off - lo, *dstI = dstM + aw, *dstD = dstI + aw;
+                for (int k = lo + tid; k <= hi; k += gsz) {
+                    uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
+                    if ((uint32_t)(k - 1 - hO.y) < cntO) mo_l = srcO[k - 1];
+                    if ((uint32_t)(k + 1 - hO.y) < cntO) mo_r = srcO[k + 1];
+                    if ((uint32_t)(k - 1 - hE.y) < cntE) ie_l = srcI[k - 1];
+                    if ((uint32_t)(k + 1 - hE.y) < cntE) de_r = srcD[k + 1];
+                    if ((uint32_t)(k - hX.y) < cntX) mx = srcX[k];
+                    Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
+                    finish_cell(c, k);
+                    dstM[k] = c.M; dstI[k] = c.I; dstD[k] = c.D;
+                }
+            } else {
+                /* source rows from the shared-memory ring: cell-major {M,I,D} triples, 12 bytes per
+                 * diagonal; one byte address per row and lane, advanced by 32 diagonals per pass */
+                int k = lo + tid;
+                uint32_t pO = ring_sa + (uint32_t)((slO * cap - hO.x + k) * 12);
+                uint32_t pE = ring_sa + (uint32_t)((slE * cap - hE.x + k) * 12);
+                uint32_t pX = ring_sa + (uint32_t)((slX * cap - hX.x + k) * 12);
+                uint32_t pC = ring_sa + (uint32_t)((cur * cap - lo + k) * 12);
+                uint32_t *gC = cells + off + 3 * (k - lo);
+                int rO = k - 1 - hO.y, rE = k - 1 - hE.y, rX = k - hX.y;      /* unsigned range tests: r < cnt */
+                keep(pO); keep(pE); keep(pX); keep(pC); keep_ptr(gC); keep(rO); keep(rE); keep(rX);
+                for (; k <= hi; k += 32) {
+                    uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
+                    if ((uint32_t)rO < cntO) mo_l = lds32<-12>(pO);
+                    if ((uint32_t)(rO + 2) < cntO) mo_r = lds32<12>(pO);
+                    if ((uint32_t)rE < cntE) ie_l = lds32<-12 + 4>(pE);
+                    if ((uint32_t)(rE + 2) < cntE) de_r = lds32<12 + 8>(pE);
+                    if ((uint32_t)rX < cntX) mx = lds32<0>(pX);
+                    Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
+                    finish_cell(c, k);
+                    sts32<0>(pC, c.M); sts32<4>(pC, c.I); sts32<8>(pC, c.D);
+                    gC[0] = c.M; gC[1] = c.I; gC[2] = c.D;
+                    pO += 384; pE += 384; pX += 384; pC += 384; gC += 96; rO += 32; rE += 32; rX += 32;
+                }
             }
             G::reduce3(wlo, whi, endhit, red);
             exists = wlo <= whi;
@@ -512,7 +559,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
             if (tid == 0) { meta[cur] = EMPTY; hdrs[si] = hc; }
             G::sync();
             s += P.g; si++; hdr_limit += sizeof(RowHdr) / 4;
-            cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
+            cur = cur + 1 == dM ? 0 : cur + 1;
             continue;
         }
         top = off;
@@ -520,27 +567,27 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
         int elo = wlo, ehi = whi;
         const uint32_t *rowM;
         if (CTA) { G::sync(); rowM = cells + off; }                     /* arena row visible to the block */
-        else { __syncwarp(); rowM = rM + cur * cap; }
+        else { __syncwarp(); rowM = ring + cur * cap * 3; }
 
         bool finished = endhit != 0;
         if (!finished && P.adaptive && whi - wlo + 1 >= P.min_wf_len) {
             /* reduce (wfa.go:461-540) as three group reductions; see DESIGN.md 4.3 */
             int mind = INT_MAX, dummy1 = INT_MIN, dummy2 = 0;
             for (int k = wlo + tid; k <= whi; k += gsz) {
-                const int d = dist_of(rowM[k - lo], k, n, m);
+                const int d = dist_of(rowM[KS * (k - lo)], k, n, m);
                 if (d >= 0) mind = min(mind, d);
             }
             G::reduce3(mind, dummy1, dummy2, red);
             int f = INT_MAX, L = INT_MIN, anyfar = 0;
             for (int k = wlo + tid; k <= whi; k += gsz) {
-                const int d = dist_of(rowM[k - lo], k, n, m);
+                const int d = dist_of(rowM[KS * (k - lo)], k, n, m);
                 if (d >= 0) { if (d - mind > maxdiff) anyfar = 1; else { f = min(f, k); L = max(L, k); } }
             }
             G::reduce3(f, L, anyfar, red);
             if (anyfar) {
                 int lf = INT_MIN, d0 = INT_MAX, d2 = 0;
                 for (int k = wlo + tid; k <= whi && k < f; k += gsz)
-                    if (dist_of(rowM[k - lo], k, n, m) >= 0) lf = max(lf, k);
+                    if (dist_of(rowM[KS * (k - lo)], k, n, m) >= 0) lf = max(lf, k);
                 G::reduce3(d0, lf, d2, red);
                 if (lf != INT_MIN) elo = lf + 1;
                 ehi = L;
@@ -553,7 +600,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
             int ka = INT_MIN, kb = INT_MAX, d2 = 0;
             const int a_hi = min(Ak, ehi), b_lo = max(Ak + 1, elo);
             for (int k = elo + tid; k <= ehi; k += gsz) {
-                const int c = hit_class(rowM[k - lo], k, n, m);
+                const int c = hit_class(rowM[KS * (k - lo)], k, n, m);
                 if (c) {
                     const int key = (k + n) * 2 + (c == 2);
                     if (k <= a_hi) ka = max(ka, key);
@@ -571,7 +618,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
         if (finished) { minS = s; lastK = Ak; if (hit) lastK = hitK; break; }
         if (hit) { minS = s; lastK = hitK; break; }
         s += P.g; si++; hdr_limit += sizeof(RowHdr) / 4;
-        cur = cur + 1 == dM ? 0 : cur + 1; cure = cure + 1 == dE ? 0 : cure + 1;
+        cur = cur + 1 == dM ? 0 : cur + 1;
     }
 
     /* ---------------- semi-global, literal mode: scan every retained score downwards (wfa.go:287-371) */
@@ -584,7 +631,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
             int ka = INT_MIN, kb = INT_MAX, d2 = 0;
             const int a_hi = min(Ak, h.hi), b_lo = max(Ak + 1, h.lo);
             for (int k = h.lo + tid; k <= h.hi; k += gsz) {
-                const int c = hit_class(rowM[k - h.alo], k, n, m);
+                const int c = hit_class(rowM[KS * (k - h.alo)], k, n, m);
                 if (c) {
                     const int key = (k + n) * 2 + (c == 2);
                     if (k <= a_hi) ka = max(ka, key);
@@ -629,7 +676,7 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
     if (status == ST_OK) {
         G::sync();
         if (tid == 0) {
-            ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = si;
+            ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = si; A.aos = !CTA;
             OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
             sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
             back_trace(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
@@ -715,7 +762,7 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
     uint32_t n_ops = 0;
     __syncwarp();
     if (status == ST_OK) {
-        ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = f.si;
+        ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = f.si; A.aos = true;
         OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
         sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
         back_trace(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
@@ -787,8 +834,11 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
 /* One kernel per (symbol width, worker shape): the 2-bit kernels hand pairs with a
  * non-ACGT byte back to the host (ST_NEED8), which re-queues them on the 8-bit
  * kernel -- keeps each kernel's code (and I-cache footprint) to one instantiation. */
+#ifndef WFA_WARP_MINB
+#define WFA_WARP_MINB 7
+#endif
 template <int BITS, bool CTA>
-__global__ void __launch_bounds__(CTA ? 1024 : 128, CTA ? 1 : 7)
+__global__ void __launch_bounds__(CTA ? 1024 : 128, CTA ? 1 : WFA_WARP_MINB)
 align_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -265,7 +265,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     } else {
         wpb = 4;
         int cap = 64;
-        while (cap < (int)(width_max * 0.6) + 8 && cap < 512) cap *= 2;
+        while (cap < (int)(width_max * 0.33) + 8 && cap < 512) cap *= 2;
         cap = std::max(cap, std::max(min_ring_cap, ctx->ring_cap_learned));
         size_t per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap);
         while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap); }
@@ -360,10 +360,14 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
             ctx->ops_pool = nb;
         }
         if (!wide.empty()) {
-            /* many pairs too wide for the ring: double it once if shared memory allows; else the CTA kernel */
+            /* too wide for the ring: retry them with a ring twice as wide while shared memory
+             * allows (remembered for later batches when it was more than a few), else the CTA kernel */
             const bool can_double = !cta && lp.ring_cap < 512 && worker_smem_bytes<false>(ctx->dM, ctx->dE, lp.ring_cap * 2) * 4 <= ctx->smem_optin;
-            if (can_double && wide.size() > 256) { min_cap = lp.ring_cap * 2; ctx->ring_cap_learned = min_cap; again.insert(again.end(), wide.begin(), wide.end()); }
-            else if (to_cta) to_cta->insert(to_cta->end(), wide.begin(), wide.end());
+            if (can_double) {
+                min_cap = lp.ring_cap * 2;
+                if (wide.size() * 50 > order.size()) ctx->ring_cap_learned = min_cap;
+                again.insert(again.end(), wide.begin(), wide.end());
+            } else if (to_cta) to_cta->insert(to_cta->end(), wide.begin(), wide.end());
         }
         if (arena_full) {
             if (!cta && lp.slot_at_max && lp.slot_bytes >= (15ull << 30) && to_cta) {
