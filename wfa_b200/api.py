@@ -260,17 +260,28 @@ class Aligner:
     __del__ = close
 
     # ---- batched entry point (new API) -------------------------------------
-    def align_arrays(self, seq_bytes, q_off, q_len, t_off, t_len, want_ops=True):
-        """Raw C-ABI call on numpy arrays -> (results, ops, ops_off)."""
+    def _out_buffers(self, n, cap):
+        """Output buffers are kept across calls (a real caller reuses its result arrays too):
+        fresh numpy memory would be page-faulted in inside every call."""
+        bufs = getattr(self, "_bufs", None)
+        if bufs is None or len(bufs[0]) < n or len(bufs[2]) < cap:
+            grow = lambda old, need: max(need, int(1.25 * len(old)) if old is not None else 0)
+            bufs = (np.zeros(grow(bufs[0] if bufs else None, n), RESULT_DTYPE),
+                    np.zeros(grow(bufs[1] if bufs else None, n), np.uint64),
+                    np.zeros(max(grow(bufs[2] if bufs else None, cap), 1), np.uint64))
+            self._bufs = bufs
+        return bufs[0][:n], bufs[1][:n], bufs[2]
+
+    def align_arrays(self, seq_bytes, q_off, q_len, t_off, t_len, want_ops=True, copy=False):
+        """Raw C-ABI call on numpy arrays -> (results, ops, ops_off).  The returned arrays are
+        views of buffers owned by the Aligner, valid until its next call (copy=True detaches)."""
         n = len(q_len)
         seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
         q_off = np.ascontiguousarray(q_off, np.uint64); t_off = np.ascontiguousarray(t_off, np.uint64)
         q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
-        results = np.zeros(n, RESULT_DTYPE)
-        ops_off = np.zeros(n, np.uint64)
         cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64 if want_ops else 0
         while True:
-            ops = np.empty(max(cap, 1), np.uint64)
+            results, ops_off, ops = self._out_buffers(n, cap)
             rc = self._L.wfacuda_align_batch(self._ctx, n, seq_bytes.ctypes.data, q_off.ctypes.data, q_len.ctypes.data,
                                              t_off.ctypes.data, t_len.ctypes.data, results.ctypes.data,
                                              ops.ctypes.data if want_ops else None, cap, ops_off.ctypes.data)
@@ -280,13 +291,15 @@ class Aligner:
             if rc != 0:
                 raise WfaError("wfacuda_align_batch failed (%d): %s" % (rc, self._err()))
             total = int(self._L.wfacuda_last_ops_total(self._ctx)) if want_ops else 0
+            if copy:
+                return results.copy(), ops[:total].copy(), ops_off.copy()
             return results, ops[:total], ops_off
 
     def AlignBatch(self, qs, ts):
         """[]*AlignmentResult, []error for many pairs in one call."""
         from .datagen import Batch
         b = Batch.from_pairs(zip(qs, ts))
-        results, ops, ops_off = self.align_arrays(b.seq_bytes, b.q_off, b.q_len, b.t_off, b.t_len)
+        results, ops, ops_off = self.align_arrays(b.seq_bytes, b.q_off, b.q_len, b.t_off, b.t_len, copy=True)
         out, errs = [], []
         for i in range(len(results)):
             st = int(results["status"][i])

@@ -55,6 +55,8 @@ struct wfacuda_ctx {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
     int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
+    int occ_cache[2][2][8] = {};   /* [cta][bits==8][log2(ring_cap/64)+1]: blocks per SM, 0 = unknown */
+    uint64_t budget_cache = 0;     /* arena budget; refreshed when the arena has to grow */
     wfacuda_stats stats{};
     uint64_t last_ops_total = 0;
     int last_rc = 0;
@@ -230,14 +232,16 @@ struct LaunchPlan {
     int group;               /* WARP class: pairs per warp group; slot_bytes is per pair, a warp owns group * slot_bytes */
 };
 
-uint64_t arena_budget(wfacuda_ctx *ctx)
+uint64_t arena_budget(wfacuda_ctx *ctx, bool refresh = true)
 {
+    if (!refresh && ctx->budget_cache) return ctx->budget_cache;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 1ull << 30; }
     const uint64_t avail = (uint64_t)free_b + ctx->arena.cap;
     uint64_t budget = (uint64_t)(avail * 0.85);
     if (ctx->cfg.arena_budget_bytes) budget = std::min<uint64_t>(budget, ctx->cfg.arena_budget_bytes);
-    return std::max<uint64_t>(budget, 1u << 20);
+    ctx->budget_cache = std::max<uint64_t>(budget, 1u << 20);
+    return ctx->budget_cache;
 }
 
 /* choose worker count / slot size for one class launch */
@@ -254,13 +258,16 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     }
     need_max = (uint64_t)((double)need_max * boost);
     lp->cta = cta; lp->slot_at_max = false;
-    const uint64_t budget = arena_budget(ctx);
+    /* the device is only asked for its free memory when the arena may have to grow */
     uint64_t slot = (std::max<uint64_t>(need_max, 16384) + 255) & ~255ull;
+    const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
     int wpb, blocks_per_sm = 1;
     if (cta) {
         wpb = 1; lp->threads = 1024; lp->ring_cap = 0;
         lp->smem = worker_smem_bytes<true>(ctx->dM, ctx->dE, 0);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, bits == 2 ? align_kernel<2, true> : align_kernel<8, true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
+        int &oc = ctx->occ_cache[1][bits == 8][0];
+        if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, bits == 2 ? align_kernel<2, true> : align_kernel<8, true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
+        blocks_per_sm = oc;
         blocks_per_sm = std::max(1, std::min(blocks_per_sm, 4));
     } else {
         wpb = 4;
@@ -271,7 +278,10 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
         while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap); }
         if (per_warp * wpb > ctx->smem_optin) return fail(ctx, WFACUDA_E_INVALID, "penalties need a deeper shared-memory ring than fits");
         lp->ring_cap = cap; lp->threads = wpb * 32; lp->smem = per_warp * wpb;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, bits == 2 ? align_kernel<2, false> : align_kernel<8, false>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); blocks_per_sm = 1; }
+        int ci = 1; for (int c = 64; c < cap && ci < 7; c *= 2) ci++;
+        int &oc = ctx->occ_cache[0][bits == 8][cap < 64 ? 0 : ci];
+        if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, bits == 2 ? align_kernel<2, false> : align_kernel<8, false>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
+        blocks_per_sm = oc;
         blocks_per_sm = std::max(1, blocks_per_sm);
     }
     uint64_t workers = (uint64_t)ctx->sm_count * blocks_per_sm * wpb;
@@ -472,7 +482,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->ring_cap_learned = 0;
+        ctx->arena_scale = 1.0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -557,28 +567,51 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         const double t2 = now_ms();
         if (n_pairs) if ((rc = staged_h2d(ctx, b->d_descs, b->descs.data(), n_pairs * sizeof(PairDesc)))) return rc;
         const double t3 = now_ms();
-        /* cost bins: longest first (counting sort on log2-ish buckets of n+m) */
+        /* cost bins: longest first (counting sort on half-octave buckets of n+m).  A pair goes to
+         * the CTA class when its wavefront cannot fit the widest shared-memory ring: width is
+         * n+m-1 for semi-global, bounded by the score guess otherwise (same guess as estimate()) */
         const bool force_cta = ctx->cfg.flags & WFACUDA_FLAG_FORCE_CTA;
         const int warp_cap_max = 512;
-        std::vector<uint32_t> bucket_of(n_pairs);
+        const wfacuda_config &c = ctx->cfg;
+        const double oe = (double)c.gap_open + c.gap_ext, per_edit = (c.mismatch + 2.0 * oe) / 3.0;
+        const bool narrow_always = c.global_alignment && c.adaptive && 1.5 * c.max_dist_diff + c.min_wf_len + 16.0 <= warp_cap_max;
+        std::vector<uint8_t> key(n_pairs);                       /* bucket | class << 7; 255 = not aligned */
         uint32_t counts[2][130] = {{0}};
-        std::vector<uint8_t> cls(n_pairs, 2);
+        int first_key = -1; bool uniform = true;
         for (uint64_t i = 0; i < n_pairs; i++) {
-            if (b->host_status[i] != ST_PENDING) continue;
+            if (b->host_status[i] != ST_PENDING) { key[i] = 255; uniform = false; continue; }
             const PairDesc &d = b->descs[i];
             const uint64_t nm = (uint64_t)d.n + d.m;
-            int lg = 63 - __builtin_clzll(nm | 1);
-            int bk = 2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1);     /* half-octave buckets */
-            bucket_of[i] = 127 - bk;
-            const Need nd = estimate(ctx, d.n, d.m);
-            cls[i] = (force_cta || nd.width > warp_cap_max) ? 1 : 0;
-            counts[cls[i]][bucket_of[i] + 1]++;
+            const int lg = 63 - __builtin_clzll(nm | 1);
+            const int bk = 127 - (2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1));
+            int cls = force_cta ? 1 : 0;
+            if (!cls && !narrow_always && nm - 1 > (uint64_t)warp_cap_max) {
+                if (!c.global_alignment) cls = 1;
+                else {
+                    const double L = std::min(d.n, d.m);
+                    const double score = 0.10 * L * per_edit + oe + std::abs((double)d.m - d.n) * c.gap_ext + 4.0 * c.mismatch;
+                    double w = std::min((double)nm - 1, 2.0 * score / c.gap_ext + 3);
+                    if (c.adaptive) w = std::min(w, 1.5 * c.max_dist_diff + c.min_wf_len + 16.0);
+                    cls = w > warp_cap_max;
+                }
+            }
+            key[i] = (uint8_t)(bk | cls << 7);
+            if (first_key < 0) first_key = key[i]; else if (key[i] != first_key) uniform = false;
+            counts[cls][bk + 1]++;
         }
-        for (int c = 0; c < 2; c++) for (int k = 1; k < 130; k++) counts[c][k] += counts[c][k - 1];
-        b->order_warp.resize(counts[0][129]); b->order_cta.resize(counts[1][129]);
-        for (uint64_t i = 0; i < n_pairs; i++) {
-            if (cls[i] == 2) continue;
-            (cls[i] ? b->order_cta : b->order_warp)[counts[cls[i]][bucket_of[i]]++] = (uint32_t)i;
+        if (uniform && n_pairs) {
+            /* one bucket, one class (the usual batch of equal-length reads): identity order */
+            std::vector<uint32_t> &ord = (first_key & 128) ? b->order_cta : b->order_warp;
+            ord.resize(n_pairs);
+            std::iota(ord.begin(), ord.end(), 0u);
+        } else {
+            for (int k2 = 0; k2 < 2; k2++) for (int k = 1; k < 130; k++) counts[k2][k] += counts[k2][k - 1];
+            b->order_warp.resize(counts[0][129]); b->order_cta.resize(counts[1][129]);
+            for (uint64_t i = 0; i < n_pairs; i++) {
+                if (key[i] == 255) continue;
+                const int cls = key[i] >> 7, bk = key[i] & 127;
+                (cls ? b->order_cta : b->order_warp)[counts[cls][bk]++] = (uint32_t)i;
+            }
         }
         const double t4 = now_ms();
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -794,20 +827,26 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     wfacuda_stats total{};
     std::string err_text;
     const double t_begin = now_ms();
+    std::vector<double> t_up(K, 0.0), t_run(K, 0.0), t_down(K, 0.0);
     auto work = [&](int k) {
         wfacuda_ctx *sub = ctx->subs[k];
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= n_chunks || first_err.load()) break;
             const uint64_t a = c * chunk_pairs, cnt = std::min(chunk_pairs, n_pairs - a);
+            const double w0 = now_ms();
             wfacuda_batch *b = wfacuda_batch_upload(sub, cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
+            const double w1 = now_ms();
             int rc = b ? wfacuda_batch_run(sub, b) : (sub->last_rc ? sub->last_rc : WFACUDA_E_CUDA);
+            const double w2 = now_ms();
+            t_up[k] += w1 - w0; t_run[k] += w2 - w1;
             if (rc == 0) {
                 const uint64_t tot = b->ops_total, base = cursor.fetch_add(tot);
                 const bool fits = ops && base + tot <= ops_capacity;
                 rc = wfacuda_batch_download(sub, b, results + a, fits ? ops + base : nullptr, fits ? tot : 0, ops_off ? ops_off + a : nullptr);
                 if (rc == 0 && ops_off) for (uint64_t i = 0; i < cnt; i++) ops_off[a + i] += base;
             }
+            t_down[k] += now_ms() - w2;
             {
                 std::lock_guard<std::mutex> lk(mu);
                 add_stats(total, sub->stats);
@@ -822,8 +861,12 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     for (auto &t : th) t.join();
     ctx->stats = total;
     ctx->last_ops_total = cursor.load();
-    if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] align_batch: %llu chunks of %llu pairs on %d workers, %.2f ms\n",
-                                          (unsigned long long)n_chunks, (unsigned long long)chunk_pairs, K, now_ms() - t_begin);
+    if (getenv("WFACUDA_DEBUG")) {
+        fprintf(stderr, "[wfacuda] align_batch: %llu chunks of %llu pairs on %d workers, %.2f ms; per worker upload/run/download ms:",
+                (unsigned long long)n_chunks, (unsigned long long)chunk_pairs, K, now_ms() - t_begin);
+        for (int k = 0; k < K; k++) fprintf(stderr, " %.1f/%.1f/%.1f", t_up[k], t_run[k], t_down[k]);
+        fprintf(stderr, "\n");
+    }
     if (first_err.load()) return fail(ctx, first_err.load(), "%s", err_text.c_str());
     if (ops && cursor.load() > ops_capacity)
         return fail(ctx, WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)cursor.load());
