@@ -132,36 +132,43 @@ __device__ __forceinline__ int lcp(const SeqView<BITS> &Q, const SeqView<BITS> &
  * the one-past-the-end phantom cells are produced identically. */
 struct Cell3 { uint32_t M, I, D; };
 
+/* Every candidate is packed as value<<p | priority so that one max() picks both the offset
+ * and, on equal offsets, the provenance the reference prefers:
+ *   I:  M[s-o-e][k-1] (Open) beats I[s-e][k-1] (Ext) on ties   -- "v1 >= v2" (:592-596)
+ *   D:  M[s-o-e][k+1] (Open) beats D[s-e][k+1] (Ext) on ties   -- (:628-632)
+ *   M:  Mismatch > I > D on ties                                -- (:656-693)
+ * A source is valid iff raw != 0 and its offset is within the bound; with raw = off<<3|type,
+ * off in [1, bound]  <=>  (raw - 8) < (bound << 3) as unsigned (raw == 0 wraps to huge). */
 __device__ __forceinline__ Cell3 next_cell(uint32_t mo_l, uint32_t ie_l, uint32_t mo_r, uint32_t de_r,
                                            uint32_t mx, int k, int n, int m)
 {
     Cell3 r;
+    const uint32_t bm = (uint32_t)m << T_BITS;                    /* offset <= m         (:581,:585,:651) */
+    /* offset - k <= n (:616,:620,:651); n + k >= 1; offsets never exceed 2^29, so the bound saturates there */
+    const uint32_t bk = min((uint32_t)(n + k), 0x1fffffffu) << T_BITS;
     /* insertion (:579-609) */
-    uint32_t a = mo_l >> T_BITS, b = ie_l >> T_BITS;
-    bool fa = mo_l != 0 && (int)a <= m, fb = ie_l != 0 && (int)b <= m;
-    a = fa ? a : 0; b = fb ? b : 0;
-    const bool updI = fa || fb;
-    const uint32_t Isk = updI ? max(a, b) + 1 : 0;
-    const uint32_t tI = (fa && (!fb || a >= b)) ? T_INS_OPEN : T_INS_EXT;
-    r.I = updI ? (Isk << T_BITS | tI) : 0;
+    uint32_t ca = (mo_l - 8u) < bm ? ((mo_l >> T_BITS) << 1 | 1u) : 0u;
+    uint32_t cb = (ie_l - 8u) < bm ? ((ie_l >> T_BITS) << 1) : 0u;
+    uint32_t best = max(ca, cb);
+    const uint32_t Isk = best ? (best >> 1) + 1u : 0u;
+    const uint32_t tI = T_INS_EXT - (best & 1u);                  /* 1 = Open, 2 = Ext */
+    r.I = best ? (Isk << T_BITS | tI) : 0u;
     /* deletion (:614-645) */
-    a = mo_r >> T_BITS; b = de_r >> T_BITS;
-    fa = mo_r != 0 && (int)a - k <= n; fb = de_r != 0 && (int)b - k <= n;
-    a = fa ? a : 0; b = fb ? b : 0;
-    const bool updD = fa || fb;
-    const uint32_t Dsk = updD ? max(a, b) : 0;
-    const uint32_t tD = (fa && (!fb || a >= b)) ? T_DEL_OPEN : T_DEL_EXT;
-    r.D = updD ? (Dsk << T_BITS | tD) : 0;
-    /* mismatch + provenance priority Mismatch > I > D on ties (:650-698) */
-    uint32_t c = mx >> T_BITS;
-    const bool fx = mx != 0 && (int)c <= m && (int)c - k <= n;
-    c = fx ? c : 0;
-    const uint32_t Msk = max(max(Isk, Dsk), c + 1);
-    uint32_t tM;
-    if (fx && Msk == c + 1) tM = T_MISMATCH;
-    else if (updI && (Msk == Isk || !updD)) tM = tI;
-    else tM = tD;
-    r.M = (updI || updD || fx) ? (Msk << T_BITS | tM) : 0;
+    ca = (mo_r - 8u) < bk ? ((mo_r >> T_BITS) << 1 | 1u) : 0u;
+    cb = (de_r - 8u) < bk ? ((de_r >> T_BITS) << 1) : 0u;
+    best = max(ca, cb);
+    const uint32_t Dsk = best >> 1;
+    const uint32_t tD = T_DEL_EXT - (best & 1u);                  /* 3 = Open, 4 = Ext */
+    r.D = best ? (Dsk << T_BITS | tD) : 0u;
+    /* mismatch + provenance priority (:650-698).  Msk = max(Isk, Dsk, v1+1); when M[s-x][k] is
+     * not usable v1+1 = 1 never beats an existing I (>= 2) or D (>= 1) */
+    const uint32_t cx = (mx - 8u) < min(bm, bk) ? (((mx >> T_BITS) + 1u) << 2 | 2u) : 0u;
+    const uint32_t ci = Isk ? (Isk << 2 | 1u) : 0u;
+    const uint32_t cd = Dsk << 2;                                 /* Dsk >= 1 when present */
+    const uint32_t bestM = max(max(cx, ci), cd);
+    const uint32_t src = bestM & 3u;
+    const uint32_t tM = src == 2u ? T_MISMATCH : (src == 1u ? tI : tD);
+    r.M = bestM ? ((bestM >> 2) << T_BITS | tM) : 0u;
     return r;
 }
 
@@ -507,21 +514,68 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                 }
             };
             if (CTA) {
-                /* source rows from the arena (three arrays per row), diagonal k indexes directly */
+                /* source rows from the arena (three arrays per row), diagonal k indexes directly.
+                 * The block is latency-bound on these L2/HBM reads, so each thread handles U
+                 * diagonals per pass: all 5*U source words are requested first, then the 4*U
+                 * sequence words of the first extend step, and only then anything is consumed. */
                 const uint64_t oX = roff[slX], oO = roff[slO], oE = roff[slE];
                 const uint32_t *srcX = cells + oX - hX.x, *srcO = cells + oO - hO.x;
                 const uint32_t *srcI = cells + oE + (uint32_t)hE.w - hE.x, *srcD = cells + oE + 2ull * (uint32_t)hE.w - hE.x;
                 uint32_t *dstM = cells + off - lo, *dstI = dstM + aw, *dstD = dstI + aw;
-                for (int k = lo + tid; k <= hi; k += gsz) {
-                    uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
-                    if ((uint32_t)(k - 1 - hO.y) < cntO) mo_l = srcO[k - 1];
-                    if ((uint32_t)(k + 1 - hO.y) < cntO) mo_r = srcO[k + 1];
-                    if ((uint32_t)(k - 1 - hE.y) < cntE) ie_l = srcI[k - 1];
-                    if ((uint32_t)(k + 1 - hE.y) < cntE) de_r = srcD[k + 1];
-                    if ((uint32_t)(k - hX.y) < cntX) mx = srcX[k];
-                    Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
-                    finish_cell(c, k);
-                    dstM[k] = c.M; dstI[k] = c.I; dstD[k] = c.D;
+                constexpr int U = 4;
+                constexpr int PW = 32 / BITS;
+                for (int k0 = lo + tid; k0 <= hi; k0 += U * gsz) {
+                    uint32_t w[U][5];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int k = k0 + u * gsz;
+                        w[u][0] = w[u][1] = w[u][2] = w[u][3] = w[u][4] = 0;
+                        if (k <= hi) {
+                            if ((uint32_t)(k - 1 - hO.y) < cntO) w[u][0] = srcO[k - 1];
+                            if ((uint32_t)(k - 1 - hE.y) < cntE) w[u][1] = srcI[k - 1];
+                            if ((uint32_t)(k + 1 - hO.y) < cntO) w[u][2] = srcO[k + 1];
+                            if ((uint32_t)(k + 1 - hE.y) < cntE) w[u][3] = srcD[k + 1];
+                            if ((uint32_t)(k - hX.y) < cntX) w[u][4] = srcX[k];
+                        }
+                    }
+                    Cell3 c[U]; int ext[U]; uint32_t xr[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int k = k0 + u * gsz;
+                        c[u] = next_cell(w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], k, n, m);
+                        ext[u] = 0; xr[u] = 0;
+                        if (k <= hi) {
+                            if (has_init && c[u].M == 0 && k >= ilo && k <= ihi) {
+                                const bool eq = Q.sym(k < 0 ? -k : 0) == T.sym(k > 0 ? k : 0);
+                                if (eq ? (s == 0) : (s == (uint32_t)x))
+                                    c[u].M = (uint32_t)((k > 0 ? k : 0) + 1) << T_BITS | (eq ? T_MATCH : T_MISMATCH);
+                            }
+                            const int h = (int)(c[u].M >> T_BITS), v = h - k;
+                            if (c[u].M && v > 0 && v < n && h < m) {            /* extend applies (wfa.go:404) */
+                                ext[u] = min(n - v, m - h);
+                                xr[u] = Q.chunk(v) ^ T.chunk(h);                 /* first 16 bases / 4 bytes */
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int k = k0 + u * gsz;
+                        if (k > hi) continue;
+                        if (c[u].M) {
+                            int h = (int)(c[u].M >> T_BITS);
+                            if (ext[u]) {
+                                int l;
+                                if (xr[u]) l = (__ffs((int)xr[u]) - 1) / BITS;
+                                else l = PW + (ext[u] > PW ? lcp<BITS>(Q, T, h - k + PW, h + PW, ext[u] - PW) : 0);
+                                l = min(l, ext[u]);
+                                c[u].M += (uint32_t)l << T_BITS;
+                                h += l;
+                            }
+                            wlo = min(wlo, k); whi = max(whi, k);
+                            if (k == Ak && h >= m) endhit = 1;            /* wfa.go:235-239 */
+                        }
+                        dstM[k] = c[u].M; dstI[k] = c[u].I; dstD[k] = c[u].D;
+                    }
                 }
             } else {
                 /* source rows from the shared-memory ring: cell-major {M,I,D} triples, 12 bytes per
@@ -837,8 +891,11 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
 #ifndef WFA_WARP_MINB
 #define WFA_WARP_MINB 7
 #endif
+#ifndef WFA_CTA_THREADS
+#define WFA_CTA_THREADS 768
+#endif
 template <int BITS, bool CTA>
-__global__ void __launch_bounds__(CTA ? 1024 : 128, CTA ? 1 : WFA_WARP_MINB)
+__global__ void __launch_bounds__(CTA ? WFA_CTA_THREADS : 128, CTA ? 1 : WFA_WARP_MINB)
 align_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -30,6 +30,7 @@
 
 using namespace wfak;
 
+
 static_assert(sizeof(Result) == sizeof(wfacuda_result), "result layout");
 static_assert(sizeof(RowHdr) == 24, "row header layout");
 
@@ -263,7 +264,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
     int wpb, blocks_per_sm = 1;
     if (cta) {
-        wpb = 1; lp->threads = 1024; lp->ring_cap = 0;
+        wpb = 1; lp->threads = WFA_CTA_THREADS; lp->ring_cap = 0;
         lp->smem = worker_smem_bytes<true>(ctx->dM, ctx->dE, 0);
         int &oc = ctx->occ_cache[1][bits == 8][0];
         if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, bits == 2 ? align_kernel<2, true> : align_kernel<8, true>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
