@@ -70,6 +70,8 @@ typedef struct wfacuda_config {
 #define WFACUDA_FLAG_FORCE_CTA          2u
 /* Force every pair through the 8-bit symbol path (testing). */
 #define WFACUDA_FLAG_FORCE_8BIT         4u
+/* Keep short pairs off the LANE kernel (32 pairs per warp in lockstep); testing / comparison. */
+#define WFACUDA_FLAG_NO_LANE            8u
 
 /* AlignmentResult (wfa_cigar.go:29-46) after process() (wfa_cigar.go:136-214).
  * tend/qend are 0 when the alignment has no match run (the reference leaves
@@ -99,6 +101,8 @@ typedef struct wfacuda_stats {
     uint32_t retries;            /* pairs re-queued with a bigger arena / wider kernel */
     uint32_t pairs_warp, pairs_cta, pairs_8bit;
     float    ms_pack, ms_align, ms_total_device;   /* CUDA-event times on the ctx stream */
+    uint32_t pairs_lane;         /* pairs aligned by the LANE kernel (not counted in pairs_warp) */
+    uint32_t reserved_;
 } wfacuda_stats;
 
 typedef struct wfacuda_ctx   wfacuda_ctx;
@@ -158,6 +162,16 @@ int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pa
  * cuts[0..n_shards], shard d owns pairs [cuts[d], cuts[d+1]). */
 int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
                        int adaptive, uint64_t *cuts);
+
+/* Page-locked host memory for the caller's input / output arrays.  Every entry point accepts
+ * any host pointer; arrays that live in memory from wfacuda_host_alloc (or registered with
+ * wfacuda_host_register) are moved by the DMA engines directly, without the staging copy
+ * through the ctx's own pinned buffers.  The cgo shim keeps its sequence pool and result
+ * arrays here (Go memory cannot be pinned, and the cgo pointer rule forbids keeping it). */
+void *wfacuda_host_alloc(size_t bytes);
+void  wfacuda_host_free(void *p);
+int   wfacuda_host_register(void *p, size_t bytes);
+int   wfacuda_host_unregister(void *p);
 
 int wfacuda_get_stats(const wfacuda_ctx *ctx, wfacuda_stats *out);
 /* Last error text of the ctx (or of the calling thread when ctx is NULL). */

@@ -65,14 +65,51 @@ CONFIGS = [(glob, ad, pen) for glob in (True, False) for ad in (None, (10, 50), 
            for pen in ((4, 6, 2), (1, 0, 1), (3, 1, 2), (2, 3, 1), (5, 2, 3), (4, 4, 4), (7, 11, 3))]
 
 
-@pytest.mark.parametrize("cta", [False, True])
-def test_random_small_all_configs(built_lib, cta):
+@pytest.mark.parametrize("worker", ["auto", "warp", "cta"])
+def test_random_small_all_configs(built_lib, worker):
+    """auto = LANE worker for global/no-heuristic configs (32 pairs per warp in lockstep), WARP
+    worker otherwise; warp = LANE switched off; cta = every pair on the CTA worker."""
     pairs = _random_pairs(7, 300)
     batch = datagen.Batch.from_pairs(pairs)
+    flags = {"auto": 0, "warp": api.FLAG_NO_LANE, "cta": api.FLAG_FORCE_CTA}[worker]
     for glob, ad, pen in CONFIGS:
-        parity.check(batch, what="glob=%s ad=%s pen=%s cta=%s" % (glob, ad, pen, cta), mismatch=pen[0], gap_open=pen[1],
-                     gap_ext=pen[2], global_alignment=glob, adaptive=ad,
-                     gpu_kw=dict(flags=api.FLAG_FORCE_CTA if cta else 0))
+        gpu, ref, stats = parity.check(batch, what="glob=%s ad=%s pen=%s worker=%s" % (glob, ad, pen, worker), mismatch=pen[0],
+                                       gap_open=pen[1], gap_ext=pen[2], global_alignment=glob, adaptive=ad, gpu_kw=dict(flags=flags))
+        if worker == "auto" and glob and ad is None and pen in ((4, 6, 2), (1, 0, 1), (2, 3, 1)):
+            assert stats["pairs_lane"] > 0, stats
+        if worker != "auto":
+            assert stats["pairs_lane"] == 0, stats
+        if glob:
+            assert stats["cells"] == ref[3]["cells"], (worker, glob, ad, pen, stats, ref[3])
+
+
+def test_lane_worker_boundaries(built_lib):
+    """LANE worker limits: lengths around 254 (byte offsets), wavefronts wider than its 64-column
+    ring (handed to the WARP worker), groups that are not a multiple of 32, lanes that finish at
+    very different scores, non-ACGT pairs inside a group (8-bit hand-over)."""
+    rng = random.Random(31)
+    rnd = lambda n, al=b"ACGT": bytes(rng.choice(al) for _ in range(n))
+    pairs = []
+    for L in (250, 253, 254, 255, 256, 300):
+        q = rnd(L)
+        pairs += [(q, q), (q, _mutate(rng, q, 0.03, b"ACGT")), (q[:L - 3], q), (q, q[2:]), (q, rnd(L))]
+    for _ in range(40):                                           # unrelated: score > 64 columns can hold
+        pairs.append((rnd(rng.randint(60, 200)), rnd(rng.randint(60, 200))))
+    for _ in range(150):                                          # related, mixed error rates and lengths
+        q = rnd(rng.randint(1, 254))
+        pairs.append((q, _mutate(rng, q, rng.choice([0.0, 0.01, 0.05, 0.1, 0.2]), b"ACGT")))
+    for _ in range(20):
+        q = rnd(100)
+        t = bytearray(q); t[rng.randrange(100)] = ord("N")
+        pairs.append((q, bytes(t)))
+    pairs += [(b"A", b"A"), (b"A", b"C"), (b"AC", b"A"), (b"A", b"ACGTACGT"), (b"ACGTACGTAC", b"A")]
+    rng.shuffle(pairs)
+    batch = datagen.Batch.from_pairs(pairs)
+    for pen in ((4, 6, 2), (1, 0, 1), (3, 1, 2), (2, 3, 1), (5, 2, 3)):
+        gpu, ref, stats = parity.check(batch, what="lane boundaries pen=%s" % (pen,), mismatch=pen[0], gap_open=pen[1], gap_ext=pen[2])
+        assert stats["pairs_lane"] > 0 and stats["pairs_warp"] > 0 and stats["pairs_8bit"] > 0, stats
+        assert stats["cells"] == ref[3]["cells"], (pen, stats, ref[3])
+    parity.check(batch, what="lane boundaries, LANE off", gpu_kw=dict(flags=api.FLAG_NO_LANE))
 
 
 def test_text_and_8bit_path(built_lib):

@@ -68,6 +68,7 @@ MaskLower32 = 4294967295
 FLAG_SEMIGLOBAL_LITERAL = 1
 FLAG_FORCE_CTA = 2
 FLAG_FORCE_8BIT = 4
+FLAG_NO_LANE = 8
 
 
 class _Config(C.Structure):
@@ -83,7 +84,8 @@ class Stats(C.Structure):
                 ("arena_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("align_launches", C.c_uint32), ("retries", C.c_uint32),
                 ("pairs_warp", C.c_uint32), ("pairs_cta", C.c_uint32), ("pairs_8bit", C.c_uint32),
-                ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_total_device", C.c_float)]
+                ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_total_device", C.c_float),
+                ("pairs_lane", C.c_uint32), ("reserved_", C.c_uint32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -96,7 +98,8 @@ RESULT_DTYPE = np.dtype([("score", "<u4"), ("tbegin", "<i4"), ("tend", "<i4"), (
 EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda_set_config",
            "wfacuda_align_batch", "wfacuda_last_ops_total", "wfacuda_batch_upload", "wfacuda_batch_run",
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
-           "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error"]
+           "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error",
+           "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister"]
 
 _LIB = None
 
@@ -137,8 +140,48 @@ def load_library():
     L.wfacuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.wfacuda_last_error.restype = C.c_char_p
     L.wfacuda_last_error.argtypes = [vp]
+    L.wfacuda_host_alloc.restype = vp
+    L.wfacuda_host_alloc.argtypes = [C.c_size_t]
+    L.wfacuda_host_free.argtypes = [vp]
+    L.wfacuda_host_register.restype = C.c_int
+    L.wfacuda_host_register.argtypes = [vp, C.c_size_t]
+    L.wfacuda_host_unregister.restype = C.c_int
+    L.wfacuda_host_unregister.argtypes = [vp]
     _LIB = L
     return L
+
+
+class _PinnedBlock:
+    """Owner of one wfacuda_host_alloc region; freed when the last numpy view of it dies."""
+
+    def __init__(self, nbytes):
+        self._L = load_library()
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = self._L.wfacuda_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise WfaError("wfacuda_host_alloc(%d) failed: %s" % (nbytes, (self._L.wfacuda_last_error(None) or b"").decode()))
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self._L.wfacuda_host_free(self.ptr)
+            self.ptr = None
+
+
+def pinned_empty(n, dtype):
+    """numpy array of n elements in page-locked host memory (wfacuda_host_alloc): the library
+    DMAs such arrays directly instead of staging them through its own pinned buffers."""
+    dtype = np.dtype(dtype)
+    blk = _PinnedBlock(int(n) * dtype.itemsize)
+    buf = (C.c_uint8 * blk.nbytes).from_address(blk.ptr)
+    buf._owner = blk                                # numpy holds buf, buf holds the block
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
+def pinned_copy(a):
+    a = np.ascontiguousarray(a)
+    out = pinned_empty(a.size, a.dtype)
+    out[:] = a.reshape(-1)
+    return out
 
 
 def shard_plan(n_shards, q_len, t_len, adaptive):
@@ -222,8 +265,9 @@ def trimOps(ops):                               # wfa_cigar.go:217-233
 class Aligner:
     """wfa.go:79-268 backed by one wfacuda ctx (one Aligner per thread, wfa.go:73-78)."""
 
-    def __init__(self, p, opt, device=0, flags=0, arena_budget_bytes=0):
+    def __init__(self, p, opt, device=0, flags=0, arena_budget_bytes=0, pinned_outputs=True):
         self.p, self.opt, self.ad = p, opt, None
+        self._pinned_out = pinned_outputs
         self._flags, self._budget, self._device = flags, arena_budget_bytes, device
         self._L = load_library()
         cfg = self._config()
@@ -256,6 +300,7 @@ class Aligner:
         if getattr(self, "_ctx", None):
             self._L.wfacuda_destroy(self._ctx)
             self._ctx = None
+        self._bufs = None
 
     __del__ = close
 
@@ -266,9 +311,16 @@ class Aligner:
         bufs = getattr(self, "_bufs", None)
         if bufs is None or len(bufs[0]) < n or len(bufs[2]) < cap:
             grow = lambda old, need: max(need, int(1.25 * len(old)) if old is not None else 0)
-            bufs = (np.zeros(grow(bufs[0] if bufs else None, n), RESULT_DTYPE),
-                    np.zeros(grow(bufs[1] if bufs else None, n), np.uint64),
-                    np.zeros(max(grow(bufs[2] if bufs else None, cap), 1), np.uint64))
+            sizes = (grow(bufs[0] if bufs else None, n), grow(bufs[1] if bufs else None, n),
+                     max(grow(bufs[2] if bufs else None, cap), 1))
+            self._bufs = bufs = None
+            # large result arrays live in page-locked memory: D2H lands in them directly
+            big = self._pinned_out and sizes[0] * RESULT_DTYPE.itemsize >= (1 << 20)
+            mk = (lambda k, dt: pinned_empty(k, dt)) if big else (lambda k, dt: np.zeros(k, dt))
+            bufs = (mk(sizes[0], RESULT_DTYPE), mk(sizes[1], np.uint64), mk(sizes[2], np.uint64))
+            if big:
+                for b in bufs:
+                    b.view(np.uint8)[:] = 0
             self._bufs = bufs
         return bufs[0][:n], bufs[1][:n], bufs[2]
 

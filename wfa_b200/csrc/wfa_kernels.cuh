@@ -255,6 +255,7 @@ struct ArenaView {
  * reversal, so runs are merged as they are produced. */
 struct OpSink {
     uint64_t *buf; uint32_t cap, n; uint32_t cur_op, cur_n; bool overflow;
+    uint32_t stride;               /* words between consecutive ops (1, or 32 for lane-interleaved scratch) */
     __device__ __forceinline__ void add(uint32_t op, uint32_t cnt)
     {
         if (op == cur_op) { cur_n += cnt; return; }
@@ -264,7 +265,7 @@ struct OpSink {
     __device__ __forceinline__ void flush()
     {
         if (cur_op == 0) return;
-        if (n < cap) buf[n] = (uint64_t)cur_op << 32 | cur_n; else overflow = true;
+        if (n < cap) buf[(size_t)n * stride] = (uint64_t)cur_op << 32 | cur_n; else overflow = true;
         n++;
         cur_op = 0;
     }
@@ -278,7 +279,8 @@ __device__ __forceinline__ uint32_t op_of_type(uint32_t t)
 
 /* backTrace, wfa.go:703-983, executed by one thread.  Returns ops (reversed
  * order, merged) in sink; fills score/begin/end of res. */
-__device__ __noinline__ void back_trace(const ArenaView &A, const KParams &P, int n, int m,
+template <class View>
+__device__ __noinline__ void back_trace(const View &A, const KParams &P, int n, int m,
                                         uint32_t s0, int Ak, Result &res, OpSink &sink)
 {
     const bool semi = !P.global_aln;
@@ -732,7 +734,7 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
         if (tid == 0) {
             ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = si; A.aos = !CTA;
             OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
-            sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
+            sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false; sink.stride = 1;
             back_trace(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
             res.n_ops = sink.n;
             if (sink.overflow) res.status = ST_ARENA;
@@ -796,6 +798,75 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
     G::sync();
 }
 
+/* ---------------- result of up to 32 pairs (lane j owns pair j): one ops-pool reservation per
+ * group, process() (wfa_cigar.go:136-214) in one pass per lane, result records and work
+ * counters.  `scratch` holds the lane's reversed, run-merged ops, `stride` words apart. */
+__device__ __forceinline__ void group_emit(const KParams &P, const bool have, const uint32_t pair, int status, Result &res,
+                                           uint32_t n_ops, const uint64_t *scratch, const uint32_t stride,
+                                           const unsigned long long arena_used, const unsigned long long c_cells,
+                                           const unsigned long long c_written, const unsigned long long c_steps)
+{
+    const int lane = threadIdx.x & 31;
+    /* one pool reservation per group: exclusive scan of n_ops over the lanes */
+    uint32_t incl = n_ops;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    const uint32_t group_total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && group_total) base = atomicAdd(&P.ctr->ops_cursor, (unsigned long long)group_total);
+    base = __shfl_sync(0xffffffffu, base, 0) + (incl - n_ops);
+    if (status == ST_OK) {
+        if (P.ops_pool != nullptr && base + n_ops > P.ops_cap) status = ST_OPS;
+        else {
+            /* process() (wfa_cigar.go:136-214) in one pass: copy reversed, and take the stats
+             * between the first and the last M as a difference of running sums */
+            unsigned alen = 0, matches = 0, gaps = 0, regions = 0;
+            unsigned a0 = 0, m0 = 0, g0 = 0, r0 = 0, a1 = 0, m1 = 0, g1 = 0, r1 = 0;
+            bool seenM = false;
+            for (uint32_t i = 0; i < n_ops; i++) {
+                const uint64_t op = scratch[(size_t)(n_ops - 1 - i) * stride];
+                if (P.ops_pool) P.ops_pool[base + i] = op;
+                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
+                if (o == 'M' && !seenM) { seenM = true; a0 = alen; m0 = matches; g0 = gaps; r0 = regions; }
+                alen += cnt;
+                if (o == 'M') matches += cnt;
+                else if (o == 'I' || o == 'D') { gaps += cnt; regions++; }
+                if (o == 'M') { a1 = alen; m1 = matches; g1 = gaps; r1 = regions; }
+            }
+            if (seenM) { res.align_len = a1 - a0; res.matches = m1 - m0; res.gaps = g1 - g0; res.gap_regions = r1 - r0; }
+            else if (n_ops) {                                      /* no M: begin = end = 0 (:170-186) */
+                const uint64_t op = scratch[(size_t)(n_ops - 1) * stride];
+                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
+                res.align_len = cnt; res.matches = 0;
+                res.gaps = (o == 'I' || o == 'D') ? cnt : 0; res.gap_regions = (o == 'I' || o == 'D') ? 1 : 0;
+            }
+            res.n_ops = n_ops;
+            P.ops_where[pair] = base;
+        }
+    }
+    if (have) {
+        res.status = (uint8_t)status;
+        if (status != ST_OK) {
+            const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+            P.retry[r] = (uint64_t)status << 32 | pair;
+        } else {
+            atomicMax(&P.ctr->arena_used_max, arena_used);
+        }
+        P.results[pair] = res;
+    }
+    /* work counters: one atomic per group */
+    unsigned long long c0 = (have && status == ST_OK) ? c_cells : 0, c1 = (have && status == ST_OK) ? c_written : 0;
+    unsigned long long c2 = (have && status == ST_OK) ? c_steps : 0, c3 = (have && status == ST_OK) ? n_ops : 0;
+    for (int d = 16; d > 0; d >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.ctr->cells, c0); atomicAdd(&P.ctr->cells_written, c1);
+        atomicAdd(&P.ctr->steps, c2); atomicAdd(&P.ctr->ops, c3);
+    }
+    __syncwarp();
+}
+
 /* ---------------- WARP worker: the forward passes of up to 32 pairs are followed by their
  * backtraces run lane-parallel (lane j owns pair j and its sub-slot): the pointer-chasing
  * backtrace costs one warp instruction stream for the whole group instead of one per pair. */
@@ -818,70 +889,14 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
     if (status == ST_OK) {
         ArenaView A; A.hdr = hdrs; A.cells = cells; A.si_last = f.si; A.aos = true;
         OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, (top - scratch_w) / 2);
-        sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
+        sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false; sink.stride = 1;
         back_trace(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
         n_ops = sink.n;
         if (sink.overflow) { status = ST_ARENA; n_ops = 0; }
     }
     __syncwarp();
-    /* one pool reservation per group: exclusive scan of n_ops over the lanes */
-    uint32_t incl = n_ops;
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    const uint32_t group_total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 0 && group_total) base = atomicAdd(&P.ctr->ops_cursor, (unsigned long long)group_total);
-    base = __shfl_sync(0xffffffffu, base, 0) + (incl - n_ops);
-    if (status == ST_OK) {
-        if (P.ops_pool != nullptr && base + n_ops > P.ops_cap) status = ST_OPS;
-        else {
-            /* process() (wfa_cigar.go:136-214) in one pass: copy reversed, and take the stats
-             * between the first and the last M as a difference of running sums */
-            unsigned alen = 0, matches = 0, gaps = 0, regions = 0;
-            unsigned a0 = 0, m0 = 0, g0 = 0, r0 = 0, a1 = 0, m1 = 0, g1 = 0, r1 = 0;
-            bool seenM = false;
-            for (uint32_t i = 0; i < n_ops; i++) {
-                const uint64_t op = scratch[n_ops - 1 - i];
-                if (P.ops_pool) P.ops_pool[base + i] = op;
-                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
-                if (o == 'M' && !seenM) { seenM = true; a0 = alen; m0 = matches; g0 = gaps; r0 = regions; }
-                alen += cnt;
-                if (o == 'M') matches += cnt;
-                else if (o == 'I' || o == 'D') { gaps += cnt; regions++; }
-                if (o == 'M') { a1 = alen; m1 = matches; g1 = gaps; r1 = regions; }
-            }
-            if (seenM) { res.align_len = a1 - a0; res.matches = m1 - m0; res.gaps = g1 - g0; res.gap_regions = r1 - r0; }
-            else if (n_ops) {                                      /* no M: begin = end = 0 (:170-186) */
-                const uint64_t op = scratch[n_ops - 1];
-                const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
-                res.align_len = cnt; res.matches = 0;
-                res.gaps = (o == 'I' || o == 'D') ? cnt : 0; res.gap_regions = (o == 'I' || o == 'D') ? 1 : 0;
-            }
-            res.n_ops = n_ops;
-            P.ops_where[pair] = base;
-        }
-    }
-    if (have) {
-        res.status = (uint8_t)status;
-        if (status != ST_OK) {
-            const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
-            P.retry[r] = (uint64_t)status << 32 | pair;
-        } else {
-            atomicMax(&P.ctr->arena_used_max, (unsigned long long)((slot_words - top + scratch_w) * 4 + 8ull * n_ops));
-        }
-        P.results[pair] = res;
-    }
-    /* work counters: one atomic per group */
-    unsigned long long c0 = (have && status == ST_OK) ? f.c_cells : 0, c1 = (have && status == ST_OK) ? f.c_written : 0;
-    unsigned long long c2 = (have && status == ST_OK) ? f.c_steps : 0, c3 = (have && status == ST_OK) ? n_ops : 0;
-    for (int d = 16; d > 0; d >>= 1) {
-        c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
-        c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
-    }
-    if (lane == 0) {
-        atomicAdd(&P.ctr->cells, c0); atomicAdd(&P.ctr->cells_written, c1);
-        atomicAdd(&P.ctr->steps, c2); atomicAdd(&P.ctr->ops, c3);
-    }
-    __syncwarp();
+    group_emit(P, have, pair, status, res, n_ops, scratch, 1u,
+               (unsigned long long)((slot_words - top + scratch_w) * 4 + 8ull * n_ops), f.c_cells, f.c_written, f.c_steps);
 }
 
 /* ------------------------------------------------------------------ kernels */

@@ -14,6 +14,7 @@
  */
 #include "../../include/wfacuda.h"
 #include "wfa_kernels.cuh"
+#include "wfa_lane.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -55,6 +56,8 @@ struct wfacuda_ctx {
     void *pinned[2] = {nullptr, nullptr}; size_t pinned_cap = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
+    double lane_scale = 1.0;       /* the same for the LANE class's group slots */
+    int lane_occ = 0;              /* LANE kernel: resident blocks per SM, 0 = unknown */
     int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
     int occ_cache[2][2][8] = {};   /* [cta][bits==8][log2(ring_cap/64)+1]: blocks per SM, 0 = unknown */
     uint64_t budget_cache = 0;     /* arena budget; refreshed when the arena has to grow */
@@ -68,7 +71,7 @@ struct wfacuda_ctx {
 struct wfacuda_batch {
     uint64_t n_pairs = 0;
     std::vector<uint8_t> host_status;       /* EMPTY / TOO_LONG decided on the host */
-    std::vector<uint32_t> order_warp, order_cta;
+    std::vector<uint32_t> order_warp, order_cta, order_lane;
     std::vector<PairDesc> descs;
     uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
     void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
@@ -160,9 +163,24 @@ void dev_give(wfacuda_ctx *ctx, void **p, size_t *sz)
     *p = nullptr; *sz = 0;
 }
 
-/* H2D of a host (pageable) region through two pinned buffers, copy overlapped with DMA */
+/* true when the host range starts in page-locked memory known to CUDA (wfacuda_host_alloc,
+ * cudaHostAlloc, cudaHostRegister): the DMA engine can then read / write it directly */
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+/* H2D of a host region: straight from the caller's memory when it is page-locked, else
+ * through two pinned staging buffers (host copy overlapped with the DMA) */
 int staged_h2d(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
 {
+    if (bytes >= 65536 && is_pinned(src)) {
+        CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->stats.h2d_bytes += bytes;
+        return 0;
+    }
     size_t done = 0; int which = 0;
     while (done < bytes) {
         const size_t chunk = std::min(ctx->pinned_cap, bytes - done);
@@ -177,8 +195,14 @@ int staged_h2d(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
 }
 
 /* D2H into a host (pageable) region through the two pinned buffers (double buffered) */
-int staged_d2h(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
+int staged_d2h(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes, bool defer_sync = false)
 {
+    if (bytes >= 65536 && is_pinned(dst)) {
+        CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (!defer_sync) CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.d2h_bytes += bytes;
+        return 0;
+    }
     size_t issued = 0, done = 0, len[2] = {0, 0}, at[2] = {0, 0};
     auto issue = [&](int w) -> cudaError_t {
         const size_t chunk = std::min(ctx->pinned_cap, bytes - issued);
@@ -408,6 +432,131 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
     return 0;
 }
 
+
+/* ---- LANE class: 32 short pairs per warp in lockstep (wfa_lane.cuh) ---------------------- */
+
+constexpr int kLaneW = 64;                       /* ring columns: diagonals -32..31 */
+
+bool lane_class_enabled(const wfacuda_ctx *ctx)
+{
+    const wfacuda_config &c = ctx->cfg;
+    if (!c.global_alignment || c.adaptive) return false;
+    if (c.flags & (WFACUDA_FLAG_FORCE_CTA | WFACUDA_FLAG_FORCE_8BIT | WFACUDA_FLAG_NO_LANE)) return false;
+    if (getenv("WFACUDA_NO_LANE")) return false;
+    /* at least two resident blocks per SM */
+    return lane_smem_bytes(ctx->dM, ctx->dE, kLaneW) * WFA_LANE_WARPS * 2 <= ctx->smem_optin;
+}
+
+/* arena bytes of one group of 32 pairs as long as (n, m): 128 bytes per (score, diagonal) */
+uint64_t estimate_lane(const wfacuda_ctx *ctx, uint32_t n, uint32_t m)
+{
+    const wfacuda_config &c = ctx->cfg;
+    const double L = std::min(n, m), diag = (double)n + m - 1;
+    const double oe = (double)c.gap_open + c.gap_ext;
+    const double per_edit = (c.mismatch + 2.0 * oe) / 3.0;
+    const double score = 0.10 * L * per_edit + oe + std::abs((double)m - n) * c.gap_ext + 4.0 * c.mismatch;
+    const double rows = score / ctx->g + 2;
+    const double width_final = std::min(std::min(diag, 2.0 * score / c.gap_ext + 3), (double)kLaneW);
+    double bytes = rows * ((0.55 * width_final + 3) * 128.0 + 16.0) + 256.0 * ((n + m) / 8.0 + 16.0) + 64 * 32 * 4 + 4096;
+    return (uint64_t)(bytes * 1.3 * ctx->lane_scale);
+}
+
+int grow_ops_pool(wfacuda_ctx *ctx, uint64_t cursor)
+{
+    /* grow the completion-order pool; what successful pairs wrote stays valid */
+    const uint64_t old_cap = ctx->ops_pool.cap / 8;
+    const uint64_t new_cap = std::max<uint64_t>(2 * old_cap, 2 * cursor + (1u << 20));
+    DevBuf nb;
+    int rc;
+    if ((rc = ensure(ctx, nb, new_cap * 8))) return rc;
+    CU(ctx, cudaMemcpy(nb.p, ctx->ops_pool.p, std::min<uint64_t>(old_cap, cursor) * 8, cudaMemcpyDeviceToDevice));
+    cudaFree(ctx->ops_pool.p);
+    ctx->ops_pool = nb;
+    return 0;
+}
+
+/* Runs the LANE class; pairs whose wavefront outgrows the byte ring go to *to_warp, pairs
+ * with a non-ACGT byte to *to_8bit, pairs out of arena / ops pool are re-queued here. */
+int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, KParams base,
+                   std::vector<uint32_t> *to_warp, std::vector<uint32_t> *to_8bit)
+{
+    double boost = 1.0;
+    const size_t per_warp = lane_smem_bytes(ctx->dM, ctx->dE, kLaneW), smem = per_warp * WFA_LANE_WARPS;
+    const int threads = 32 * WFA_LANE_WARPS;
+    for (int attempt = 0; !order.empty(); attempt++) {
+        if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
+        if (!ctx->lane_occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ, lane_kernel, threads, smem) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ = 1; }
+        uint64_t need = 0;
+        const size_t sample = std::min<size_t>(order.size(), 4096);
+        for (size_t i = 0; i < sample; i++) need = std::max(need, estimate_lane(ctx, b->descs[order[i]].n, b->descs[order[i]].m));
+        uint64_t slot = ((uint64_t)((double)std::max<uint64_t>(need, 65536) * boost) + 255) & ~255ull;
+        const uint64_t groups = (order.size() + 31) / 32;
+        uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ) * WFA_LANE_WARPS;
+        workers = std::min<uint64_t>(workers, ((groups + WFA_LANE_WARPS - 1) / WFA_LANE_WARPS) * WFA_LANE_WARPS);
+        const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
+        bool slot_at_max = false;
+        if (slot * workers > budget) workers = std::max<uint64_t>(WFA_LANE_WARPS, (budget / slot) / WFA_LANE_WARPS * WFA_LANE_WARPS);
+        if (slot * workers > budget) { slot = (budget / workers) & ~255ull; slot_at_max = true; }
+        slot = std::min<uint64_t>(slot, 15ull << 30);
+        int rc;
+        if ((rc = ensure(ctx, ctx->arena, slot * workers))) return rc;
+        if ((rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
+        CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        Counters *dc = (Counters *)ctx->ctr.p;
+        CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
+        KParams P = base;
+        P.work = (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
+        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = 32;
+        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
+        P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+        const int blocks = (int)(workers / WFA_LANE_WARPS);
+        lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++; ctx->stats.align_launches++;
+        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, slot * workers);
+        Counters hc;
+        CU(ctx, cudaMemcpyAsync(&hc, dc, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d blocks x %d thr (%d/SM), smem %zu, group slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", attempt, order.size(), blocks, threads, ctx->lane_occ, smem, slot / 1024.0, ctx->lane_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
+        if (hc.retry_n == 0) {
+            if (boost == 1.0 && !slot_at_max && slot > 65536 && hc.arena_used_max) {
+                const double r = 1.5 * (double)hc.arena_used_max / (double)slot;
+                ctx->lane_scale = std::min(64.0, std::max(1.0 / 64, ctx->lane_scale * std::min(1.0, std::max(r, 0.25))));
+            }
+            break;
+        }
+        std::vector<uint64_t> rl(hc.retry_n);
+        CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> again;
+        bool ops_full = false, arena_full = false;
+        for (uint64_t r : rl) {
+            const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
+            if (st == ST_RING) to_warp->push_back(pair);
+            else if (st == ST_NEED8) to_8bit->push_back(pair);
+            else { again.push_back(pair); if (st == ST_OPS) ops_full = true; else arena_full = true; }
+        }
+        ctx->stats.retries += (uint32_t)again.size();
+        if (ops_full && (rc = grow_ops_pool(ctx, hc.ops_cursor))) return rc;
+        if (arena_full) {
+            if (slot_at_max && workers <= (uint64_t)WFA_LANE_WARPS) {
+                /* the whole budget is not enough for one group: let the WARP class place them */
+                std::vector<uint32_t> keep;
+                for (uint64_t r : rl) {
+                    if ((uint32_t)(r >> 32) == ST_ARENA) to_warp->push_back((uint32_t)r);
+                    else if ((uint32_t)(r >> 32) == ST_OPS) keep.push_back((uint32_t)r);
+                }
+                again.swap(keep);
+            } else boost *= 4.0;
+            ctx->lane_scale = std::min(64.0, ctx->lane_scale * 2.0);
+        }
+        order.swap(again);
+    }
+    return 0;
+}
+
 } // namespace
 
 /* ========================================================================== API */
@@ -455,7 +604,8 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
     if (cudaFuncSetAttribute(align_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
         cudaFuncSetAttribute(align_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
         cudaFuncSetAttribute(align_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
-        cudaFuncSetAttribute(align_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
+        cudaFuncSetAttribute(align_kernel<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin) != cudaSuccess) {
         fail(ctx, WFACUDA_E_CUDA, "cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail();
     }
@@ -477,13 +627,39 @@ void wfacuda_destroy(wfacuda_ctx *ctx)
     delete ctx;
 }
 
+void *wfacuda_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+        fail(nullptr, WFACUDA_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+
+void wfacuda_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int wfacuda_host_register(void *p, size_t bytes)
+{
+    if (!p || !bytes) return fail(nullptr, WFACUDA_E_INVALID, "nothing to register");
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess)
+        return fail(nullptr, WFACUDA_E_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+int wfacuda_host_unregister(void *p)
+{
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return WFACUDA_E_INVALID; }
+    return 0;
+}
+
 int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
 {
     if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->lane_scale = 1.0; ctx->lane_occ = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -576,17 +752,19 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         const wfacuda_config &c = ctx->cfg;
         const double oe = (double)c.gap_open + c.gap_ext, per_edit = (c.mismatch + 2.0 * oe) / 3.0;
         const bool narrow_always = c.global_alignment && c.adaptive && 1.5 * c.max_dist_diff + c.min_wf_len + 16.0 <= warp_cap_max;
-        std::vector<uint8_t> key(n_pairs);                       /* bucket | class << 7; 255 = not aligned */
-        uint32_t counts[2][130] = {{0}};
+        const bool lane_ok = lane_class_enabled(ctx);
+        std::vector<uint8_t> key(n_pairs);                       /* bucket | class << 6; 255 = not aligned */
+        uint32_t counts[3][66] = {{0}};
         int first_key = -1; bool uniform = true;
         for (uint64_t i = 0; i < n_pairs; i++) {
             if (b->host_status[i] != ST_PENDING) { key[i] = 255; uniform = false; continue; }
             const PairDesc &d = b->descs[i];
             const uint64_t nm = (uint64_t)d.n + d.m;
             const int lg = 63 - __builtin_clzll(nm | 1);
-            const int bk = 127 - (2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1));
+            const int bk = 63 - (2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1));
             int cls = force_cta ? 1 : 0;
-            if (!cls && !narrow_always && nm - 1 > (uint64_t)warp_cap_max) {
+            if (lane_ok && d.n <= (uint32_t)LANE_MAX_LEN && d.m <= (uint32_t)LANE_MAX_LEN) cls = 2;
+            else if (!cls && !narrow_always && nm - 1 > (uint64_t)warp_cap_max) {
                 if (!c.global_alignment) cls = 1;
                 else {
                     const double L = std::min(d.n, d.m);
@@ -596,22 +774,23 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
                     cls = w > warp_cap_max;
                 }
             }
-            key[i] = (uint8_t)(bk | cls << 7);
+            key[i] = (uint8_t)(bk | cls << 6);
             if (first_key < 0) first_key = key[i]; else if (key[i] != first_key) uniform = false;
             counts[cls][bk + 1]++;
         }
+        std::vector<uint32_t> *ords[3] = {&b->order_warp, &b->order_cta, &b->order_lane};
         if (uniform && n_pairs) {
             /* one bucket, one class (the usual batch of equal-length reads): identity order */
-            std::vector<uint32_t> &ord = (first_key & 128) ? b->order_cta : b->order_warp;
+            std::vector<uint32_t> &ord = *ords[first_key >> 6];
             ord.resize(n_pairs);
             std::iota(ord.begin(), ord.end(), 0u);
         } else {
-            for (int k2 = 0; k2 < 2; k2++) for (int k = 1; k < 130; k++) counts[k2][k] += counts[k2][k - 1];
-            b->order_warp.resize(counts[0][129]); b->order_cta.resize(counts[1][129]);
+            for (int k2 = 0; k2 < 3; k2++) for (int k = 1; k < 66; k++) counts[k2][k] += counts[k2][k - 1];
+            for (int k2 = 0; k2 < 3; k2++) ords[k2]->resize(counts[k2][65]);
             for (uint64_t i = 0; i < n_pairs; i++) {
                 if (key[i] == 255) continue;
-                const int cls = key[i] >> 7, bk = key[i] & 127;
-                (cls ? b->order_cta : b->order_warp)[counts[cls][bk]++] = (uint32_t)i;
+                const int cls = key[i] >> 6, bk = key[i] & 63;
+                (*ords[cls])[counts[cls][bk]++] = (uint32_t)i;
             }
         }
         const double t4 = now_ms();
@@ -652,7 +831,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
         if ((rc = staged_h2d(ctx, b->d_results, init.data(), n * sizeof(Result)))) return rc;
         CU(ctx, cudaStreamSynchronize(ctx->stream));     /* init goes out of scope */
     } else if (n) CU(ctx, cudaMemsetAsync(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
-    const uint64_t n_valid = b->order_warp.size() + b->order_cta.size();
+    const uint64_t n_valid = b->order_warp.size() + b->order_cta.size() + b->order_lane.size();
     if (n_valid) {
         const int pack_blocks = (int)std::min<uint64_t>((2 * n_valid + 7) / 8, (uint64_t)ctx->sm_count * 16);
         pack_kernel<<<pack_blocks, 256, 0, ctx->stream>>>((const PairDesc *)b->d_descs, (uint32_t)n, (const uint32_t *)b->d_raw,
@@ -680,13 +859,19 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     const double t_prep = now_ms();
     /* WARP class first (2-bit, then the pairs it handed back as 8-bit), then the CTA class */
     const bool force8 = ctx->cfg.flags & WFACUDA_FLAG_FORCE_8BIT;
-    std::vector<uint32_t> to_cta, warp8, cta8;
-    if ((rc = run_class(ctx, b, b->order_warp, false, force8 ? 8 : 2, P, &to_cta, &warp8))) return rc;
+    /* LANE class first (short global pairs, 2-bit only), then the WARP class incl. what the LANE
+     * class handed over (2-bit, then 8-bit), then the CTA class */
+    std::vector<uint32_t> to_warp, to_cta, warp8, cta8;
+    if ((rc = run_lane_class(ctx, b, b->order_lane, P, &to_warp, &warp8))) return rc;
+    ctx->stats.pairs_lane = (uint32_t)(b->order_lane.size() - to_warp.size() - warp8.size());
+    std::vector<uint32_t> warp_order = b->order_warp;
+    warp_order.insert(warp_order.end(), to_warp.begin(), to_warp.end());
+    if ((rc = run_class(ctx, b, warp_order, false, force8 ? 8 : 2, P, &to_cta, &warp8))) return rc;
     if ((rc = run_class(ctx, b, warp8, false, 8, P, &to_cta, nullptr))) return rc;
     const double t_warp = now_ms();
     std::vector<uint32_t> cta_order = b->order_cta;
     cta_order.insert(cta_order.end(), to_cta.begin(), to_cta.end());
-    ctx->stats.pairs_warp = (uint32_t)(b->order_warp.size() - to_cta.size());
+    ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size());
     ctx->stats.pairs_cta = (uint32_t)cta_order.size();
     if ((rc = run_class(ctx, b, cta_order, true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
     if ((rc = run_class(ctx, b, cta8, true, 8, P, nullptr, nullptr))) return rc;
@@ -743,13 +928,16 @@ int wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *r
     const uint64_t n = b->n_pairs;
     const double t0 = now_ms();
     int rc;
-    if (n && results) if ((rc = staged_d2h(ctx, results, b->d_results, n * sizeof(Result)))) return rc;
-    if (n && ops_off) if ((rc = staged_d2h(ctx, ops_off, b->d_dst, n * 8))) return rc;
+    if (n && results) if ((rc = staged_d2h(ctx, results, b->d_results, n * sizeof(Result), true))) return rc;
+    if (n && ops_off) if ((rc = staged_d2h(ctx, ops_off, b->d_dst, n * 8, true))) return rc;
     if (ops) {
-        if (b->ops_total > ops_capacity)
+        if (b->ops_total > ops_capacity) {
+            cudaStreamSynchronize(ctx->stream);
             return fail(ctx, WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)b->ops_total);
-        if (b->ops_total) if ((rc = staged_d2h(ctx, ops, b->d_ops_sorted, b->ops_total * 8))) return rc;
+        }
+        if (b->ops_total) if ((rc = staged_d2h(ctx, ops, b->d_ops_sorted, b->ops_total * 8, true))) return rc;
     }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));       /* copies into page-locked caller memory were left in flight */
     if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] download: %.2f ms for %.1f MB\n", now_ms() - t0, ctx->stats.d2h_bytes / 1e6);
     return 0;
 }
@@ -772,7 +960,7 @@ static void add_stats(wfacuda_stats &a, const wfacuda_stats &s)
     a.ops += s.ops; a.seq_bases += s.seq_bases; a.arena_bytes = std::max(a.arena_bytes, s.arena_bytes);
     a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes; a.kernel_launches += s.kernel_launches;
     a.align_launches += s.align_launches; a.retries += s.retries; a.pairs_warp += s.pairs_warp;
-    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
+    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.pairs_lane += s.pairs_lane; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
     a.ms_total_device += s.ms_total_device;
 }
 
