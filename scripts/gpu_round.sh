@@ -24,7 +24,7 @@ bench)
 ncu)
   WFACUDA_NO_PIPELINE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_cfg2.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_cfg2.log 2>&1
-  WFACUDA_NO_PIPELINE=1 timeout 1200 ncu --set full --clock-control none --import-source on -k "regex:lane_kernel|align_kernel" -s 3 -c 1 -f -o $OUT/prof_cfg2 \
+  WFACUDA_NO_PIPELINE=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:lane_kernel -s 3 -c 1 -f -o $OUT/prof_cfg2 \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg2.log 2>&1
   WFACUDA_NO_PIPELINE=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:align_kernel -s 3 -c 1 -f -o $OUT/prof_cfg3 \
       python bench.py --workload cfg3_1kbp_e10_global_adaptive --pairs 100000 --steps 1 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_cfg3.log 2>&1

@@ -248,6 +248,9 @@ struct ArenaView {
         const uint32_t d = (uint32_t)(k - h.alo);
         return cells[h.off + (aos ? 3ull * d + (uint32_t)comp : (uint64_t)comp * (uint32_t)h.aw + d)];
     }
+    /* the backtrace reads the provenance code only of the cell it stands on; views that do
+     * not store codes re-derive them there (LaneView) */
+    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k) const { return get(comp, si, k); }
 };
 
 /* Reversed, run-merged op emitter: AddN (wfa_cigar.go:118-124) followed by
@@ -295,7 +298,7 @@ __device__ __noinline__ void back_trace(const View &A, const KParams &P, int n, 
     uint32_t offset0 = 0, Isk = 0, Dsk = 0;
     int M0 = 0;                                   /* component of the next cell: 0 M, 1 I, 2 D */
 
-    uint32_t raw = A.get(0, s, k);                /* :738 */
+    uint32_t raw = A.get_typed(0, s, k);          /* :738; get_typed = raw word incl. its provenance code */
     uint32_t type = raw & T_MASK;
     h = (int)(raw >> T_BITS);
     v = h - k;
@@ -350,7 +353,7 @@ __device__ __noinline__ void back_trace(const View &A, const KParams &P, int n, 
         }
         if (leave) break;
         v = h - k;
-        raw = A.get(M0, s, k);                    /* :915-920 */
+        raw = A.get_typed(M0, s, k);              /* :915-920 */
         if (raw == 0) break;
         type = raw & T_MASK;
     }
@@ -929,7 +932,7 @@ align_kernel(const KParams P)
             __syncthreads();
             const uint32_t item = next_item[0];
             if (item >= P.n_work) break;
-            const uint32_t pair = P.work[item];
+            const uint32_t pair = P.work ? P.work[item] : item;
             if (BITS == 2 && (P.pflags[pair] & 1)) {
                 if (threadIdx.x == 0) {
                     const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
@@ -956,7 +959,7 @@ align_kernel(const KParams P)
             mine.c_cells = mine.c_written = mine.c_steps = 0;
             bool have = false; uint32_t my_pair = 0;
             for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t pair = P.work[first + j];
+                const uint32_t pair = P.work ? P.work[first + j] : first + j;
                 if (BITS == 2 && (P.pflags[pair] & 1)) {
                     if (lane == 0) {
                         const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);

@@ -14,17 +14,23 @@
  *
  * Per-lane private data (shared memory, lane-interleaved so that every access is conflict
  * free whatever the lane's own index):
- *   seqQ, seqT   u32 [17][32]          2-bit packed sequences (<= 254 bases)
- *   ringM        u8  [dM][W][32]       offsets of the last max(x,o+e)/g+1 scores of M
- *   ringI, ringD u8  [dE][W][32]       offsets of the last e/g+1 scores of I and D
+ *   seqQ, seqT   u32 [SW][32]          2-bit packed sequences (<= 254 bases; SW = words + 1)
+ *   ringM        u8  [max(x,o+e)/g][W][32]   offsets of the scores of M still needed
+ *   ringI, ringD u8  [e/g][W][32]            the same for I and D
  * Offsets fit a byte (<= m+1 <= 255); the 3-bit provenance codes are not needed by `next`.
- * Diagonal k lives at column k + W/2 of every row.
+ * Diagonal k lives at column k + W/2 of every row.  A row is replaced in place by the row
+ * max(x,o+e) (resp. e) scores later, and everything outside a row's written range is kept
+ * "absent" (0), so the diagonal loop reads its five sources without any range test.
  *
  * Backtrace arena (HBM, one slot per warp, reused group after group):
  *   hdr   int4 {lo, hi, off, aw} per score index, shared by the 32 pairs
- *   cell  u32 [aw][32] per score: M | I<<8 | D<<16 | codeM<<24 | extI<<27 | extD<<28
- * i.e. 4 bytes per (score, diagonal, pair) instead of the 12 of three raw words; `LaneView::get`
- * rebuilds the reference's raw word offset<<3|code for the unchanged literal backtrace.
+ *   cell  u32 [aw][32] per score: M | I<<8 | D<<16 (offsets)
+ * i.e. 4 bytes per (score, diagonal, pair) instead of the 12 of three raw words.  The 3-bit
+ * provenance codes are not stored: `next` picks them as a function of the five source offsets,
+ * which are all in the arena, so `LaneView::get_typed` re-derives the code of the ~20 cells the
+ * backtrace stands on (same validity tests, same tie order) instead of the forward pass
+ * computing and packing it for all ~530 cells of a pair.  The backtrace itself is the shared
+ * literal one (back_trace in wfa_kernels.cuh).
  *
  * Semantics follow the reference at /root/reference (cited as wfa.go:LINE).
  */
@@ -39,11 +45,12 @@ constexpr int LANE_MAX_LEN = 254;           /* offsets up to m+1 must fit a byte
 #define WFA_LANE_WARPS 2
 #endif
 
-__host__ __device__ inline size_t lane_smem_bytes(int dM, int dE, int W)
+/* dM, dE as in KParams (max(x,o+e)/g+1, e/g+1); W ring columns; SW words per sequence */
+__host__ __device__ inline size_t lane_smem_bytes(int dM, int dE, int W, int SW)
 {
-    size_t b = (((size_t)dM * 8) + 15) & ~(size_t)15;                 /* meta int2[dM] */
-    b += 2 * (size_t)LANE_SEQ_WORDS * 128;                             /* seqQ, seqT */
-    b += ((size_t)dM + 2 * (size_t)dE) * (size_t)W * 32;               /* rings */
+    size_t b = (((size_t)dM * 8) + 15) & ~(size_t)15;                 /* meta int2[] */
+    b += 2 * (size_t)SW * 128;                                         /* seqQ, seqT */
+    b += ((size_t)(dM - 1) + 2 * (size_t)(dE - 1)) * (size_t)W * 32;   /* rings (in place: one row less than the WARP worker) */
     return (b + 127) & ~(size_t)127;
 }
 
@@ -57,6 +64,16 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
+template <int OFF> __device__ __forceinline__ uint32_t lds_u8o(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF> __device__ __forceinline__ void sts_u8o(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u8 [%0+%1], %2;" :: "r"(addr), "n"(OFF), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -68,27 +85,10 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
 }
 
-/* Component.Get on the packed group arena (see the header comment) */
-struct LaneView {
-    const int4     *hdr;
-    const uint32_t *cells;     /* already offset by the lane */
-    int             si_last;
-    __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
-    {
-        if (si < 0 || si > si_last) return 0;
-        const int4 h = hdr[si];
-        if (k < h.x || k > h.y) return 0;
-        const uint32_t w = cells[(uint32_t)h.z + (uint32_t)(k - h.x) * 32u];
-        if (comp == 0) { const uint32_t o = w & 255u; return o ? (o << T_BITS | ((w >> 24) & 7u)) : 0u; }
-        if (comp == 1) { const uint32_t o = (w >> 8) & 255u; return o ? (o << T_BITS | (T_INS_OPEN + ((w >> 27) & 1u))) : 0u; }
-        const uint32_t o = (w >> 16) & 255u;
-        return o ? (o << T_BITS | (T_DEL_OPEN + ((w >> 28) & 1u))) : 0u;
-    }
-};
-
 /* One diagonal of `next` (wfa.go:572-699) on bare offsets (0 = absent); same candidate packing
  * as next_cell: value<<p | priority, one max() picks offset and provenance.
- *   um = m (offset <= m, :581,:585,:651), ubk = n + k (offset - k <= n, :616,:620,:651) */
+ *   um = m (offset <= m, :581,:585,:651), ubk = n + k (offset - k <= n, :616,:620,:651)
+ * Used by the backtrace to re-derive the provenance codes the forward pass does not store. */
 struct CellO { uint32_t M, I, D, code; };   /* code = codeM | extI<<3 | extD<<4 */
 
 __device__ __forceinline__ CellO next_off(uint32_t mo_l, uint32_t ie_l, uint32_t mo_r, uint32_t de_r, uint32_t mx,
@@ -116,11 +116,83 @@ __device__ __forceinline__ CellO next_off(uint32_t mo_l, uint32_t ie_l, uint32_t
     return r;
 }
 
+/* The same recurrence, offsets only (forward pass): I = max(valid sources) + 1, D = max(valid
+ * sources), M = max(I, D, valid M[s-x][k] + 1).  Which source won -- the provenance code --
+ * is a function of the same five stored offsets and is re-derived by the backtrace for the
+ * few cells it visits (LaneView::get_typed) instead of being computed for every cell here. */
+struct Cell3O { uint32_t M, I, D; };
+__device__ __forceinline__ Cell3O next_off3(uint32_t mo_l, uint32_t ie_l, uint32_t mo_r, uint32_t de_r, uint32_t mx,
+                                            uint32_t um, uint32_t ubk)
+{
+    Cell3O r;
+    const uint32_t a = (mo_l - 1u) < um ? mo_l : 0u, b = (ie_l - 1u) < um ? ie_l : 0u;
+    const uint32_t mi = max(a, b);
+    r.I = mi + (mi != 0u);
+    const uint32_t c = (mo_r - 1u) < ubk ? mo_r : 0u, d = (de_r - 1u) < ubk ? de_r : 0u;
+    r.D = max(c, d);
+    const uint32_t e = (mx - 1u) < min(um, ubk) ? mx + 1u : 0u;
+    r.M = max(max(e, r.I), r.D);
+    return r;
+}
+
+/* Component.Get on the packed group arena (see the header comment) */
+struct LaneView {
+    const int4     *hdr;
+    const uint32_t *cells;     /* already offset by the lane */
+    int             si_last;
+    int             n, m, xg, oeg, eg;
+    bool            first_eq;
+    __device__ __forceinline__ uint32_t word(int si, int k) const
+    {
+        if (si < 0 || si > si_last) return 0;
+        const int4 h = hdr[si];
+        if (k < h.x || k > h.y) return 0;
+        return cells[(uint32_t)h.z + (uint32_t)(k - h.x) * 32u];
+    }
+    /* offset << 3, code bits zero: all the backtrace needs of a source cell */
+    __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
+    {
+        return ((word(si, k) >> (8 * comp)) & 255u) << T_BITS;
+    }
+    /* raw word of the cell the backtrace stands on: offset << 3 | provenance code, the code
+     * re-derived from the cell's five sources exactly as `next` chose it (wfa.go:579-698), or
+     * the init code when `next` wrote nothing there (wfa.go:155-158) */
+    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k) const
+    {
+        const uint32_t o = (word(si, k) >> (8 * comp)) & 255u;
+        if (o == 0) return 0;
+        const uint32_t wl = word(si - oeg, k - 1), wr = word(si - oeg, k + 1);
+        const uint32_t el = word(si - eg, k - 1), er = word(si - eg, k + 1);
+        const CellO c = next_off(wl & 255u, (el >> 8) & 255u, wr & 255u, (er >> 16) & 255u, word(si - xg, k) & 255u,
+                                 (uint32_t)m, (uint32_t)(n + k));
+        uint32_t code;
+        if (comp == 1) code = T_INS_OPEN + ((c.code >> 3) & 1u);
+        else if (comp == 2) code = T_DEL_OPEN + ((c.code >> 4) & 1u);
+        else code = c.M ? (c.code & 7u) : (first_eq ? T_MATCH : T_MISMATCH);
+        return o << T_BITS | code;
+    }
+};
+
 /* 16 bases starting at base `pos` of a lane's sequence in shared memory (base pos in the low bits) */
 __device__ __forceinline__ uint32_t lane_chunk(uint32_t seq_sa, int pos)
 {
     const uint32_t a = seq_sa + ((uint32_t)pos >> 4) * 128u;
     return __funnelshift_r(lds_u32(a), lds_u32(a + 128u), ((uint32_t)pos & 15u) * 2u);
+}
+
+/* extend (wfa.go:394-455) of one M offset on diagonal k: returns the extended offset */
+__device__ __forceinline__ uint32_t lane_extend(uint32_t sQ, uint32_t sT, uint32_t M, int k, int n, int m)
+{
+    const int h = (int)M, v = h - k;
+    if (M == 0 || v <= 0 || v >= n || h >= m) return M;
+    const int ext = min(n - v, m - h);
+    int l = 0;
+    while (l < ext) {
+        const uint32_t xx = lane_chunk(sQ, v + l) ^ lane_chunk(sT, h + l);
+        if (xx) { l += (__ffs((int)xx) - 1) >> 1; break; }
+        l += 16;
+    }
+    return M + (uint32_t)min(l, ext);
 }
 
 /* Forward pass + backtrace of one group of up to 32 pairs. */
@@ -129,16 +201,19 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
 {
     const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int dM = P.dM, dE = P.dE, W = P.ring_cap, KC = W >> 1;
-    const int xg = P.xg, oeg = P.oeg, eg = P.eg, x = (int)P.x;
+    /* rings are written in place: the row of score s replaces the oldest row still needed,
+     * M[s - max(x,o+e)] resp. I/D[s - e]; sources ahead of the write position are read first and
+     * the ones behind it are carried in registers */
+    const int RM = P.dM - 1, RE = P.dE - 1, W = P.ring_cap, KC = W >> 1, SW = P.group;
+    const int xg = P.xg, oeg = P.oeg, x = (int)P.x;
 
     int2 *meta = reinterpret_cast<int2 *>(smem);
-    unsigned char *p = smem + ((((size_t)dM * 8) + 15) & ~(size_t)15);
+    unsigned char *p = smem + ((((size_t)P.dM * 8) + 15) & ~(size_t)15);
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)lane * 4u;
-    const uint32_t sT = sQ + LANE_SEQ_WORDS * 128u;
-    const uint32_t rM = sQ - (uint32_t)lane * 4u + 2u * LANE_SEQ_WORDS * 128u + (uint32_t)lane;   /* column of this lane */
+    const uint32_t sT = sQ + (uint32_t)SW * 128u;
     const uint32_t rowB = (uint32_t)W * 32u;
-    const uint32_t rI = rM + (uint32_t)dM * rowB, rD = rI + (uint32_t)dE * rowB;
+    const uint32_t rM = sQ - (uint32_t)lane * 4u + 2u * (uint32_t)SW * 128u + (uint32_t)lane + (uint32_t)KC * 32u;   /* column of this lane, diagonal 0 */
+    const uint32_t rI = rM + (uint32_t)RM * rowB, rD = rI + (uint32_t)RE * rowB;
 
     int status = have ? ST_OK : ST_PENDING;
     PairDesc pd; pd.q_byte = pd.t_byte = pd.q_word = pd.t_word = 0; pd.n = pd.m = 0;
@@ -147,23 +222,33 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
         if (P.pflags[pair] & 1) status = ST_NEED8;
     }
     const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
-    bool act = status == ST_OK;
+    const bool act = status == ST_OK;
 
-    /* sequences -> lane-private shared memory columns */
+    /* sequences -> lane-private shared memory columns; rings start all "absent" */
     {
         const uint32_t *gq = P.packed + pd.q_word, *gt = P.packed + pd.t_word;
         const int wq = act ? (n + 15) >> 4 : 0, wt = act ? (m + 15) >> 4 : 0;
 #pragma unroll 1
-        for (int w = 0; w < LANE_SEQ_WORDS; w++) {
+        for (int w = 0; w < SW; w++) {
             sts_u32(sQ + (uint32_t)w * 128u, w < wq ? __ldg(gq + w) : 0u);
             sts_u32(sT + (uint32_t)w * 128u, w < wt ? __ldg(gt + w) : 0u);
         }
+        const uint32_t ring0 = sQ + 2u * (uint32_t)SW * 128u;           /* rings are a multiple of 128 bytes per 4 columns */
+        const int ring_words = (RM + 2 * RE) * W * 8;
+#pragma unroll 1
+        for (int w = 0; w < ring_words; w += 32) sts_u32(ring0 + (uint32_t)w * 4u, 0u);
     }
+    for (int i = lane; i < RM; i += 32) meta[i] = make_int2(1, 0);
+    __syncwarp();
     const bool first_eq = ((lds_u32(sQ) ^ lds_u32(sT)) & 3u) == 0u;       /* q[0] == t[0], wfa.go:155-158 */
     /* a lane works on diagonals [klo, klo + kspan] = [-(n-1), m-1] (wfa.go:562-563); an idle or
      * finished lane gets an empty range and computes nothing but "absent" */
-    int klo = act ? -(n - 1) : 0x3fffffff;
-    const uint32_t kspan = act ? (uint32_t)(n + m - 2) : 0u;
+    const int klo = -(n - 1);
+    const uint32_t kspan = (uint32_t)(n + m - 2);
+    /* rows inside [clamp_lo, clamp_hi] need no per-pair clamp.  Idle and finished lanes are not
+     * masked at all: what they compute is never read (their counters, end test and results are
+     * guarded, their arena column past the final score is not visited by the backtrace). */
+    const int clamp_lo = -(__reduce_min_sync(FULL, act ? n : INT_MAX) - 1), clamp_hi = __reduce_min_sync(FULL, act ? m : INT_MAX) - 1;
     const int ulo = -(__reduce_max_sync(FULL, act ? n : 1) - 1), uhi = __reduce_max_sync(FULL, act ? m : 1) - 1;
 
     int4     *hdrs  = reinterpret_cast<int4 *>(slot);
@@ -172,22 +257,19 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     uint32_t top = slot_words;
     uint32_t hdr_limit = 2 * 4 + 64 * 32;              /* header words incl. the next one + a minimum of op scratch */
 
-    for (int i = lane; i < dM; i += 32) meta[i] = make_int2(1, 0);
-    __syncwarp();
-
     uint32_t s = 0; int si = 0, cur = 0, curE = 0;
     bool done = false; uint32_t minS = 0; int my_si = 0;
     uint32_t c_cells = 0, c_written = 0, c_steps = 0;
     int group_fail = 0;
+    const int2 EMPTY = make_int2(1, 0);
 
     if (__any_sync(FULL, act)) for (;;) {
-        int slX = cur - xg, slO = cur - oeg, slE = cur - eg;
-        slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0;
-        const int2 EMPTY = make_int2(1, 0);
-        const int2 hX = si >= xg ? meta[slX] : EMPTY;
-        const int2 hO = si >= oeg ? meta[slO] : EMPTY;
-        const int2 hE = si >= eg ? meta[slE] : EMPTY;
-        int slEe = curE - eg; slEe += slEe < 0 ? dE : 0;
+        int slX = cur - xg, slO = cur - oeg;
+        slX += slX < 0 ? RM : 0; slO += slO < 0 ? RM : 0;
+        const int2 hX = meta[slX], hO = meta[slO];
+        int slE = cur - P.eg; slE += slE < 0 ? RM : 0;
+        const int2 hE = meta[slE];                     /* also the range held by the I/D slot about to be replaced */
+        const int2 hP = meta[cur];                     /* range held by the M slot about to be replaced */
         /* union loop range (wfa.go:557-563), clamped with the longest sequences of the group */
         int lo = INT_MAX, hi = INT_MIN;
         if (hX.x <= hX.y) { lo = min(lo, hX.x); hi = max(hi, hX.y); }
@@ -197,56 +279,40 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
         const bool has_init = (s == 0) || (s == (uint32_t)x);          /* global: the one cell k = 0 */
         if (has_init) { lo = min(lo, 0); hi = max(hi, 0); }
 
-        bool seen = false; int wlo = 0, whi = 0;
+        int wlo = INT_MAX, whi = INT_MIN;
         int aw = 0; uint32_t off = 0;
+        const uint32_t bCM = rM + (uint32_t)cur * rowB, bCI = rI + (uint32_t)curE * rowB, bCD = rD + (uint32_t)curE * rowB;
         if (lo <= hi) {
             aw = hi - lo + 1;
-            if (lo < -KC || hi > KC - 1) { group_fail = ST_RING; break; }
+            if (lo < -KC + 1 || hi > KC - 2) { group_fail = ST_RING; break; }
             const uint32_t need = (uint32_t)aw * 32u;
             if (top < hdr_limit || top - hdr_limit < need) { group_fail = ST_ARENA; break; }
             off = top - need;
-            /* lane-private byte columns; cell k of a row is 32*k bytes further */
-            const uint32_t bO = rM + (uint32_t)(slO * W + KC) * 32u, bX = rM + (uint32_t)(slX * W + KC) * 32u;
-            const uint32_t bI = rI + (uint32_t)(slEe * W + KC) * 32u, bD = rD + (uint32_t)(slEe * W + KC) * 32u;
-            const uint32_t bCM = rM + (uint32_t)(cur * W + KC) * 32u;
-            const uint32_t bCI = rI + (uint32_t)(curE * W + KC) * 32u, bCD = rD + (uint32_t)(curE * W + KC) * 32u;
-            uint32_t *gC = cells + off + lane - lo * 32;
+            /* running byte addresses of cell k in the lane's columns; a row's cell k+1 is 32 bytes on */
+            uint32_t pO = rM + (uint32_t)slO * rowB + (uint32_t)(lo * 32), pX = rM + (uint32_t)slX * rowB + (uint32_t)(lo * 32);
+            uint32_t pM = bCM + (uint32_t)(lo * 32), pI = bCI + (uint32_t)(lo * 32), pD = bCD + (uint32_t)(lo * 32);
+            uint32_t *gp = cells + off + lane;
+            keep(pO); keep(pX); keep(pM); keep(pI); keep(pD); keep_ptr(gp);
             const uint32_t um = (uint32_t)m;
-            auto inO = [&](int k) { return k >= hO.x && k <= hO.y; };
-            auto inE = [&](int k) { return k >= hE.x && k <= hE.y; };
-            auto inX = [&](int k) { return k >= hX.x && k <= hX.y; };
-            auto at = [](uint32_t base, int k) { return base + (uint32_t)(k * 32); };
 
-            /* phase A of one cell: sources -> next -> clamp -> (init) -> first 16-base compare */
-            struct Pend { CellO c; int k, ext; uint32_t xr; };
-            auto cell_a = [&](auto chk, const int k, const uint32_t mo_l, const uint32_t mo_r) -> Pend {
-                constexpr bool CHK = decltype(chk)::value;
-                uint32_t ie_l, de_r, mx;
-                if (CHK) {
-                    ie_l = inE(k - 1) ? lds_u8(at(bI, k - 1)) : 0u;
-                    de_r = inE(k + 1) ? lds_u8(at(bD, k + 1)) : 0u;
-                    mx = inX(k) ? lds_u8(at(bX, k)) : 0u;
-                } else {
-                    ie_l = lds_u8(at(bI, k - 1)); de_r = lds_u8(at(bD, k + 1)); mx = lds_u8(at(bX, k));
-                }
-                Pend q; q.k = k;
-                q.c = next_off(mo_l, ie_l, mo_r, de_r, mx, um, (uint32_t)(n + k));
-                if ((uint32_t)(k - klo) > kspan) { q.c.M = 0; q.c.I = 0; q.c.D = 0; }
-                if (CHK) {
-                    if (has_init && k == 0 && q.c.M == 0 && act && !done && (first_eq ? (s == 0) : (s == (uint32_t)x))) {
-                        /* initComponents (wfa.go:155-158); next's Set wins when both write */
-                        q.c.M = 1u; q.c.code = (q.c.code & ~7u) | (first_eq ? T_MATCH : T_MISMATCH);
-                    }
-                }
+            struct Pend { Cell3O c; int ext; uint32_t xr; };
+            /* phase A of one cell: next (wfa.go:572-699) -> first 16-base compare of extend.  CLAMP
+             * rows reach beyond some pair's own diagonals [-(n-1), m-1] (wfa.go:562-563). */
+            auto cell_a = [&](auto clamp, const int k, const uint32_t mo_l, const uint32_t ie_l, const uint32_t mo_r, const uint32_t de_r, const uint32_t mx) -> Pend {
+                Pend q;
+                if (decltype(clamp)::value) {
+                    const bool inb = (uint32_t)(k - klo) <= kspan;
+                    q.c = next_off3(mo_l, ie_l, mo_r, de_r, mx, inb ? um : 0u, inb ? (uint32_t)(n + k) : 0u);
+                } else q.c = next_off3(mo_l, ie_l, mo_r, de_r, mx, um, (uint32_t)(n + k));
                 const int h = (int)q.c.M, v = h - k;
                 const bool ex = q.c.M != 0 && v > 0 && v < n && h < m;                /* extend applies (wfa.go:404) */
                 q.ext = ex ? min(n - v, m - h) : 0;
-                q.xr = lane_chunk(sQ, ex ? v : 0) ^ lane_chunk(sT, ex ? h : 0);
+                /* positions are only meaningful when ex; masked so that the loads stay inside the block */
+                q.xr = lane_chunk(sQ, v & 255) ^ lane_chunk(sT, h);
                 return q;
             };
-            /* phase B: finish extend (wfa.go:411-454), store ring + arena, bookkeeping */
-            auto cell_b = [&](Pend &q) {
-                const int k = q.k;
+            /* phase B: rest of extend (wfa.go:411-454) */
+            auto cell_b = [&](Pend &q, const int k) {
                 if (q.ext) {
                     int l = q.xr ? (__ffs((int)q.xr) - 1) >> 1 : 16;
                     if (q.xr == 0 && q.ext > 16) {
@@ -259,57 +325,73 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
                     }
                     q.c.M += (uint32_t)min(l, q.ext);
                 }
-                sts_u8(at(bCM, k), q.c.M); sts_u8(at(bCI, k), q.c.I); sts_u8(at(bCD, k), q.c.D);
-                gC[k * 32] = q.c.M | q.c.I << 8 | q.c.D << 16 | q.c.code << 24;
-                if (q.c.M) { if (!seen) { seen = true; wlo = k; } whi = k; }
             };
-            using T_ = std::true_type; using F_ = std::false_type;
-            /* interior: every source cell lies inside its row's written range */
-            int ia = INT_MAX, ib = INT_MIN;
-            if (hX.x <= hX.y && hO.x <= hO.y && hE.x <= hE.y && !has_init) {
-                ia = max(max(hX.x, hO.x + 1), max(hE.x + 1, lo));
-                ib = min(min(hX.y, hO.y - 1), min(hE.y - 1, hi));
+            auto row = [&](auto clamp) {
+                int k = lo;
+                uint32_t o_m1 = lds_u8o<-32>(pO), o_0 = lds_u8o<0>(pO), i_m1 = lds_u8o<-32>(pI);
+                for (; k < hi; k += 2) {
+                    const uint32_t o_p1 = lds_u8o<32>(pO), o_p2 = lds_u8o<64>(pO);
+                    const uint32_t i_0 = lds_u8o<0>(pI), i_p1 = lds_u8o<32>(pI);
+                    const uint32_t d_p1 = lds_u8o<32>(pD), d_p2 = lds_u8o<64>(pD);
+                    const uint32_t x_0 = lds_u8o<0>(pX), x_p1 = lds_u8o<32>(pX);
+                    Pend q0 = cell_a(clamp, k, o_m1, i_m1, o_p1, d_p1, x_0);
+                    Pend q1 = cell_a(clamp, k + 1, o_0, i_0, o_p2, d_p2, x_p1);
+                    cell_b(q0, k); cell_b(q1, k + 1);
+                    sts_u8o<0>(pM, q0.c.M); sts_u8o<0>(pI, q0.c.I); sts_u8o<0>(pD, q0.c.D);
+                    sts_u8o<32>(pM, q1.c.M); sts_u8o<32>(pI, q1.c.I); sts_u8o<32>(pD, q1.c.D);
+                    gp[0] = q0.c.M | q0.c.I << 8 | q0.c.D << 16; gp[32] = q1.c.M | q1.c.I << 8 | q1.c.D << 16;
+                    o_m1 = o_p1; o_0 = o_p2; i_m1 = i_p1;
+                    pO += 64; pX += 64; pM += 64; pI += 64; pD += 64; gp += 64;
+                }
+                if (k == hi) {
+                    const uint32_t o_p1 = lds_u8o<32>(pO), d_p1 = lds_u8o<32>(pD), x_0 = lds_u8o<0>(pX);
+                    Pend q0 = cell_a(clamp, k, o_m1, i_m1, o_p1, d_p1, x_0);
+                    cell_b(q0, k);
+                    sts_u8o<0>(pM, q0.c.M); sts_u8o<0>(pI, q0.c.I); sts_u8o<0>(pD, q0.c.D);
+                    gp[0] = q0.c.M | q0.c.I << 8 | q0.c.D << 16;
+                }
+            };
+            if (lo < clamp_lo || hi > clamp_hi) row(std::true_type{}); else row(std::false_type{});
+            if (has_init && act && !done && (first_eq ? (s == 0) : (s == (uint32_t)x)) && lds_u8(bCM) == 0u) {
+                /* initComponents (wfa.go:155-158): cell k = 0, unless next's Set already wrote it
+                 * (wfa_wavefront.go:93); then its extend (the row loop saw an absent cell) */
+                const uint32_t M = lane_extend(sQ, sT, 1u, 0, n, m);
+                sts_u8(bCM, M);
+                uint32_t *g0 = cells + off + lane - lo * 32;
+                *g0 = (*g0 & 0xffffff00u) | M;
             }
-            int k = lo;
-            uint32_t o_m1 = inO(k - 1) ? lds_u8(at(bO, k - 1)) : 0u, o_0 = inO(k) ? lds_u8(at(bO, k)) : 0u;
-            for (; k <= hi && k < ia; k++) {
-                const uint32_t o_p1 = inO(k + 1) ? lds_u8(at(bO, k + 1)) : 0u;
-                Pend q = cell_a(T_{}, k, o_m1, o_p1);
-                cell_b(q);
-                o_m1 = o_0; o_0 = o_p1;
-            }
-            for (; k + 1 <= ib; k += 2) {
-                const uint32_t o_p1 = lds_u8(at(bO, k + 1)), o_p2 = lds_u8(at(bO, k + 2));
-                Pend q0 = cell_a(F_{}, k, o_m1, o_p1);
-                Pend q1 = cell_a(F_{}, k + 1, o_0, o_p2);
-                cell_b(q0); cell_b(q1);
-                o_m1 = o_p1; o_0 = o_p2;
-            }
-            for (; k <= hi; k++) {
-                const uint32_t o_p1 = inO(k + 1) ? lds_u8(at(bO, k + 1)) : 0u;
-                Pend q = cell_a(T_{}, k, o_m1, o_p1);
-                cell_b(q);
-                o_m1 = o_0; o_0 = o_p1;
+            /* M WaveFront.Lo/Hi of this pair = first and last present cell (only the work counter C needs them) */
+            if (act && !done) {
+                int a = lo, b = hi;
+                while (a <= hi && lds_u8(bCM + (uint32_t)(a * 32)) == 0u) a++;
+                while (b > a && lds_u8(bCM + (uint32_t)(b * 32)) == 0u) b--;
+                if (a <= hi) { wlo = a; whi = b; }
             }
         }
+        /* keep "outside a slot's range = absent": clear what the replaced rows held beyond [lo, hi] */
+        if (hP.x <= hP.y && (lo > hi || hP.x < lo || hP.y > hi))
+            for (int k = hP.x; k <= hP.y; k++) if (k < lo || k > hi) sts_u8(bCM + (uint32_t)(k * 32), 0u);
+        if (hE.x <= hE.y && (lo > hi || hE.x < lo || hE.y > hi))
+            for (int k = hE.x; k <= hE.y; k++) if (k < lo || k > hi) { sts_u8(bCI + (uint32_t)(k * 32), 0u); sts_u8(bCD + (uint32_t)(k * 32), 0u); }
+        const bool seen = wlo <= whi;
         const bool any = __any_sync(FULL, seen);
         if (any) {
             top = off;
             if (seen) { c_steps++; c_cells += (uint32_t)(whi - wlo + 1); c_written += (uint32_t)aw; }
             /* end test on diagonal m-n (wfa.go:235-239); the lane reads back its own column */
-            if (seen && Ak >= lo && Ak <= hi) {
-                const uint32_t hM = lds_u8(rM + (uint32_t)(cur * W + KC + Ak) * 32u);
-                if ((int)hM >= m) { done = true; minS = s; my_si = si; klo = 0x3fffffff; }
+            if (seen && Ak >= lo && Ak <= hi) {       /* seen implies a live lane */
+                const uint32_t hM = lds_u8(bCM + (uint32_t)(Ak * 32));
+                if (!done && (int)hM >= m) { done = true; minS = s; my_si = si; }
             }
         }
         __syncwarp();
-        meta[cur] = any ? make_int2(lo, hi) : make_int2(1, 0);            /* same value from every lane */
+        meta[cur] = any ? make_int2(lo, hi) : EMPTY;                      /* same value from every lane; a row nobody has holds zeros only */
         if (lane == 0) hdrs[si] = any ? make_int4(lo, hi, (int)off, aw) : make_int4(1, 0, 0, 0);
         __syncwarp();
         if (__all_sync(FULL, !act || done)) break;
         s += P.g; si++; hdr_limit += 4;
-        cur = cur + 1 == dM ? 0 : cur + 1;
-        curE = curE + 1 == dE ? 0 : curE + 1;
+        cur = cur + 1 == RM ? 0 : cur + 1;
+        curE = curE + 1 == RE ? 0 : curE + 1;
     }
     if (act && !done) status = group_fail ? group_fail : ST_ARENA;
 
@@ -325,6 +407,7 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     __threadfence_block();
     if (status == ST_OK) {
         LaneView A; A.hdr = hdrs; A.cells = cells + lane; A.si_last = my_si;
+        A.n = n; A.m = m; A.xg = P.xg; A.oeg = P.oeg; A.eg = P.eg; A.first_eq = first_eq;
         OpSink sink; sink.buf = scratch; sink.stride = 32;
         sink.cap = top > scratch_w ? (top - scratch_w) / 64u : 0u;
         sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
@@ -343,7 +426,7 @@ lane_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wib = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
-    unsigned char *smem = smem_raw + (size_t)wib * lane_smem_bytes(P.dM, P.dE, P.ring_cap);
+    unsigned char *smem = smem_raw + (size_t)wib * lane_smem_bytes(P.dM, P.dE, P.ring_cap, P.group);
     const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     uint8_t *slot = P.arena + worker * P.slot_bytes;
     for (;;) {
@@ -352,7 +435,7 @@ lane_kernel(const KParams P)
         first = __shfl_sync(0xffffffffu, first, 0);
         if (first >= P.n_work) break;
         const bool have = first + lane < P.n_work;
-        const uint32_t pair = have ? P.work[first + lane] : 0u;
+        const uint32_t pair = have ? (P.work ? P.work[first + lane] : first + lane) : 0u;
         lane_group(P, have, pair, smem, slot, P.slot_bytes);
     }
 }

@@ -57,7 +57,7 @@ struct wfacuda_ctx {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
     double lane_scale = 1.0;       /* the same for the LANE class's group slots */
-    int lane_occ = 0;              /* LANE kernel: resident blocks per SM, 0 = unknown */
+    int lane_occ = 0, lane_occ_sw = 0;   /* LANE kernel: resident blocks per SM for lane_occ_sw words per sequence */
     int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
     int occ_cache[2][2][8] = {};   /* [cta][bits==8][log2(ring_cap/64)+1]: blocks per SM, 0 = unknown */
     uint64_t budget_cache = 0;     /* arena budget; refreshed when the arena has to grow */
@@ -72,6 +72,8 @@ struct wfacuda_batch {
     uint64_t n_pairs = 0;
     std::vector<uint8_t> host_status;       /* EMPTY / TOO_LONG decided on the host */
     std::vector<uint32_t> order_warp, order_cta, order_lane;
+    int identity_cls = -1;                  /* class (0 warp, 1 cta, 2 lane) whose order is 0..n-1: no work list needed */
+    uint32_t lane_maxlen = 1;               /* longest sequence of the LANE class */
     std::vector<PairDesc> descs;
     uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
     void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
@@ -331,26 +333,30 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
 /* Runs one class of pairs to completion, re-queuing pairs that ran out of
  * ring width (WARP kernel -> wider ring or the CTA kernel through *to_cta),
  * arena (4x slot) or ops pool (pool doubled). */
-int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, bool cta, int bits, KParams base,
+int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &order0, bool identity, bool cta, int bits, KParams base,
               std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit)
 {
     double boost = 1.0; int min_cap = 0;
-    for (int attempt = 0; !order.empty(); attempt++) {
+    std::vector<uint32_t> requeued;
+    for (int attempt = 0; ; attempt++) {
+        const std::vector<uint32_t> &order = attempt == 0 ? order0 : requeued;
+        if (order.empty()) break;
+        const bool ident = identity && attempt == 0;      /* pair index == queue position: no work list */
         if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
         LaunchPlan lp;
         int rc = plan_launch(ctx, b, order, cta, bits, boost, min_cap, &lp);
         if (rc) return rc;
         if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.group * lp.workers))) return rc;
-        if ((rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
+        if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
-        CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ident) CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         /* reset queue + retry counters, keep the work counters and the ops cursor */
         Counters *dc = (Counters *)ctx->ctr.p;
         CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
         KParams P = base;
-        P.work = (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
+        P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = lp.ring_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
@@ -427,7 +433,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, b
             } else boost *= 4.0;
             ctx->arena_scale = std::min(64.0, ctx->arena_scale * 2.0);
         }
-        order.swap(again);
+        requeued.swap(again);
     }
     return 0;
 }
@@ -444,7 +450,7 @@ bool lane_class_enabled(const wfacuda_ctx *ctx)
     if (c.flags & (WFACUDA_FLAG_FORCE_CTA | WFACUDA_FLAG_FORCE_8BIT | WFACUDA_FLAG_NO_LANE)) return false;
     if (getenv("WFACUDA_NO_LANE")) return false;
     /* at least two resident blocks per SM */
-    return lane_smem_bytes(ctx->dM, ctx->dE, kLaneW) * WFA_LANE_WARPS * 2 <= ctx->smem_optin;
+    return lane_smem_bytes(ctx->dM, ctx->dE, kLaneW, LANE_SEQ_WORDS) * WFA_LANE_WARPS * 2 <= ctx->smem_optin;
 }
 
 /* arena bytes of one group of 32 pairs as long as (n, m): 128 bytes per (score, diagonal) */
@@ -477,15 +483,24 @@ int grow_ops_pool(wfacuda_ctx *ctx, uint64_t cursor)
 
 /* Runs the LANE class; pairs whose wavefront outgrows the byte ring go to *to_warp, pairs
  * with a non-ACGT byte to *to_8bit, pairs out of arena / ops pool are re-queued here. */
-int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> order, KParams base,
+int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &order0, bool identity, KParams base,
                    std::vector<uint32_t> *to_warp, std::vector<uint32_t> *to_8bit)
 {
     double boost = 1.0;
-    const size_t per_warp = lane_smem_bytes(ctx->dM, ctx->dE, kLaneW), smem = per_warp * WFA_LANE_WARPS;
     const int threads = 32 * WFA_LANE_WARPS;
-    for (int attempt = 0; !order.empty(); attempt++) {
+    std::vector<uint32_t> requeued;
+    for (int attempt = 0; ; attempt++) {
+        const std::vector<uint32_t> &order = attempt == 0 ? order0 : requeued;
+        if (order.empty()) break;
+        const bool ident = identity && attempt == 0;
         if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
-        if (!ctx->lane_occ && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ, lane_kernel, threads, smem) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ = 1; }
+        /* words per sequence in shared memory: the longest of the class + 1 for the funnel shift */
+        const int sw = (int)((b->lane_maxlen + 15) / 16) + 1;
+        const size_t smem = lane_smem_bytes(ctx->dM, ctx->dE, kLaneW, sw) * WFA_LANE_WARPS;
+        if (ctx->lane_occ_sw != sw) {
+            ctx->lane_occ_sw = sw;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ, lane_kernel, threads, smem) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ = 1; }
+        }
         uint64_t need = 0;
         const size_t sample = std::min<size_t>(order.size(), 4096);
         for (size_t i = 0; i < sample; i++) need = std::max(need, estimate_lane(ctx, b->descs[order[i]].n, b->descs[order[i]].m));
@@ -500,16 +515,16 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> ord
         slot = std::min<uint64_t>(slot, 15ull << 30);
         int rc;
         if ((rc = ensure(ctx, ctx->arena, slot * workers))) return rc;
-        if ((rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
+        if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
-        CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ident) CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
         Counters *dc = (Counters *)ctx->ctr.p;
         CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
         KParams P = base;
-        P.work = (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
-        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = 32;
+        P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
+        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = sw;      /* LANE kernel: group = words per sequence */
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         const int blocks = (int)(workers / WFA_LANE_WARPS);
@@ -521,15 +536,8 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> ord
         CU(ctx, cudaMemcpyAsync(&hc, dc, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d blocks x %d thr (%d/SM), smem %zu, group slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", attempt, order.size(), blocks, threads, ctx->lane_occ, smem, slot / 1024.0, ctx->lane_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
-        if (hc.retry_n == 0) {
-            if (boost == 1.0 && !slot_at_max && slot > 65536 && hc.arena_used_max) {
-                const double r = 1.5 * (double)hc.arena_used_max / (double)slot;
-                ctx->lane_scale = std::min(64.0, std::max(1.0 / 64, ctx->lane_scale * std::min(1.0, std::max(r, 0.25))));
-            }
-            break;
-        }
         std::vector<uint64_t> rl(hc.retry_n);
-        CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
+        if (hc.retry_n) CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
         std::vector<uint32_t> again;
         bool ops_full = false, arena_full = false;
         for (uint64_t r : rl) {
@@ -538,6 +546,12 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> ord
             else if (st == ST_NEED8) to_8bit->push_back(pair);
             else { again.push_back(pair); if (st == ST_OPS) ops_full = true; else arena_full = true; }
         }
+        if (!arena_full && boost == 1.0 && !slot_at_max && slot > 65536 && hc.arena_used_max) {
+            /* learn: aim the next batch's group slots at 1.5x the largest use seen */
+            const double r = 1.5 * (double)hc.arena_used_max / (double)slot;
+            ctx->lane_scale = std::min(64.0, std::max(1.0 / 64, ctx->lane_scale * std::min(1.0, std::max(r, 0.25))));
+        }
+        if (hc.retry_n == 0) break;
         ctx->stats.retries += (uint32_t)again.size();
         if (ops_full && (rc = grow_ops_pool(ctx, hc.ops_cursor))) return rc;
         if (arena_full) {
@@ -552,7 +566,7 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, std::vector<uint32_t> ord
             } else boost *= 4.0;
             ctx->lane_scale = std::min(64.0, ctx->lane_scale * 2.0);
         }
-        order.swap(again);
+        requeued.swap(again);
     }
     return 0;
 }
@@ -659,7 +673,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->lane_scale = 1.0; ctx->lane_occ = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->lane_scale = 1.0; ctx->lane_occ = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -763,7 +777,7 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             const int lg = 63 - __builtin_clzll(nm | 1);
             const int bk = 63 - (2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1));
             int cls = force_cta ? 1 : 0;
-            if (lane_ok && d.n <= (uint32_t)LANE_MAX_LEN && d.m <= (uint32_t)LANE_MAX_LEN) cls = 2;
+            if (lane_ok && d.n <= (uint32_t)LANE_MAX_LEN && d.m <= (uint32_t)LANE_MAX_LEN) { cls = 2; b->lane_maxlen = std::max(b->lane_maxlen, std::max(d.n, d.m)); }
             else if (!cls && !narrow_always && nm - 1 > (uint64_t)warp_cap_max) {
                 if (!c.global_alignment) cls = 1;
                 else {
@@ -784,6 +798,7 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             std::vector<uint32_t> &ord = *ords[first_key >> 6];
             ord.resize(n_pairs);
             std::iota(ord.begin(), ord.end(), 0u);
+            b->identity_cls = first_key >> 6;
         } else {
             for (int k2 = 0; k2 < 3; k2++) for (int k = 1; k < 66; k++) counts[k2][k] += counts[k2][k - 1];
             for (int k2 = 0; k2 < 3; k2++) ords[k2]->resize(counts[k2][65]);
@@ -862,19 +877,21 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     /* LANE class first (short global pairs, 2-bit only), then the WARP class incl. what the LANE
      * class handed over (2-bit, then 8-bit), then the CTA class */
     std::vector<uint32_t> to_warp, to_cta, warp8, cta8;
-    if ((rc = run_lane_class(ctx, b, b->order_lane, P, &to_warp, &warp8))) return rc;
+    if ((rc = run_lane_class(ctx, b, b->order_lane, b->identity_cls == 2, P, &to_warp, &warp8))) return rc;
     ctx->stats.pairs_lane = (uint32_t)(b->order_lane.size() - to_warp.size() - warp8.size());
-    std::vector<uint32_t> warp_order = b->order_warp;
-    warp_order.insert(warp_order.end(), to_warp.begin(), to_warp.end());
-    if ((rc = run_class(ctx, b, warp_order, false, force8 ? 8 : 2, P, &to_cta, &warp8))) return rc;
-    if ((rc = run_class(ctx, b, warp8, false, 8, P, &to_cta, nullptr))) return rc;
+    std::vector<uint32_t> warp_extra;                       /* only built when the LANE class handed pairs over */
+    if (!to_warp.empty()) { warp_extra = b->order_warp; warp_extra.insert(warp_extra.end(), to_warp.begin(), to_warp.end()); }
+    const std::vector<uint32_t> &warp_order = to_warp.empty() ? b->order_warp : warp_extra;
+    if ((rc = run_class(ctx, b, warp_order, b->identity_cls == 0 && to_warp.empty(), false, force8 ? 8 : 2, P, &to_cta, &warp8))) return rc;
+    if ((rc = run_class(ctx, b, warp8, false, false, 8, P, &to_cta, nullptr))) return rc;
     const double t_warp = now_ms();
-    std::vector<uint32_t> cta_order = b->order_cta;
-    cta_order.insert(cta_order.end(), to_cta.begin(), to_cta.end());
+    std::vector<uint32_t> cta_extra;
+    if (!to_cta.empty()) { cta_extra = b->order_cta; cta_extra.insert(cta_extra.end(), to_cta.begin(), to_cta.end()); }
+    const std::vector<uint32_t> &cta_order = to_cta.empty() ? b->order_cta : cta_extra;
     ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size());
     ctx->stats.pairs_cta = (uint32_t)cta_order.size();
-    if ((rc = run_class(ctx, b, cta_order, true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
-    if ((rc = run_class(ctx, b, cta8, true, 8, P, nullptr, nullptr))) return rc;
+    if ((rc = run_class(ctx, b, cta_order, b->identity_cls == 1 && to_cta.empty(), true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
+    if ((rc = run_class(ctx, b, cta8, false, true, 8, P, nullptr, nullptr))) return rc;
     ctx->stats.pairs_8bit = force8 ? (uint32_t)n_valid : (uint32_t)(warp8.size() + cta8.size());
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
