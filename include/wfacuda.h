@@ -127,7 +127,9 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg);
  *                        (op<<32|n, already reversed + merged, wfa_cigar.go:32,123,136-169);
  *                        may be NULL with capacity 0 to skip CIGARs
  *   ops_off[n_pairs]     start of pair i's n_ops words in ops (regions never overlap; their
- *                        order in the buffer is unspecified for large, internally chunked batches)
+ *                        order in the buffer is unspecified -- pairs complete in any order on the
+ *                        GPU and their ops stay where they were written; the buffer may hold
+ *                        unused gaps, wfacuda_last_ops_total() is its used length)
  * Returns 0, or a WFACUDA_E_* code.  On WFACUDA_E_OPS_CAPACITY results are
  * valid and wfacuda_last_ops_total() tells the capacity needed. */
 int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
@@ -139,7 +141,8 @@ uint64_t wfacuda_last_ops_total(const wfacuda_ctx *ctx);
 
 /* The same call split in three, so that a caller (or bench.py) can keep a
  * batch resident in HBM: upload = H2D + planning, run = kernels only (inputs
- * and outputs stay in HBM), download = D2H. */
+ * and outputs stay in HBM), download = D2H.  The ops of a run live in the ctx's pool until the
+ * next run on the same ctx: download a batch before running another one there. */
 wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
                                     const uint64_t *q_off, const uint32_t *q_len,
                                     const uint64_t *t_off, const uint32_t *t_len);

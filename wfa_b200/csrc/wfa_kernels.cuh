@@ -61,6 +61,7 @@ struct Result {                /* == wfacuda_result */
 
 struct Counters {              /* device-side work counters, one set per launch */
     unsigned long long cells, cells_written, steps, ops, retry_n, ops_cursor, work_next, arena_used_max;
+    unsigned long long t_first, t_last;   /* globaltimer of the first block start / last block end (LANE kernel, profiling aid) */
 };
 
 struct KParams {
@@ -1016,60 +1017,6 @@ pack_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t
         }
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(pflags) + (sq >> 3), 1u << (((sq >> 1) & 3) * 8));
     }
-}
-
-/* ops reorder: completion-order pool -> index-order buffer */
-__global__ void __launch_bounds__(256)
-gather_ops_kernel(const Result *__restrict__ results, const uint64_t *__restrict__ where,
-                  const uint64_t *__restrict__ dst_off, const uint64_t *__restrict__ pool,
-                  uint64_t *__restrict__ out, uint32_t n_pairs)
-{
-    const uint32_t lane = threadIdx.x & 31;
-    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t p = warp0; p < n_pairs; p += nwarps) {
-        if (results[p].status != ST_OK) continue;
-        const uint32_t cnt = results[p].n_ops;
-        const uint64_t a = where[p], b = dst_off[p];
-        for (uint32_t i = lane; i < cnt; i += 32) out[b + i] = pool[a + i];
-    }
-}
-
-/* exclusive prefix sum of n_ops (index order) in three tiny kernels */
-__global__ void __launch_bounds__(1024)
-scan_block_kernel(const Result *__restrict__ results, uint32_t n, uint64_t *__restrict__ excl, uint64_t *__restrict__ block_sums)
-{
-    __shared__ uint64_t wsum[32];
-    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
-    uint64_t v = (i < n && results[i].status == ST_OK) ? results[i].n_ops : 0;
-    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint64_t inc = v;
-    for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
-    if (lane == 31) wsum[wid] = inc;
-    __syncthreads();
-    if (wid == 0) {
-        uint64_t w = wsum[lane], winc = w;
-        for (int d = 1; d < 32; d <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, winc, d); if ((int)lane >= d) winc += t; }
-        wsum[lane] = winc - w;
-        if (lane == 31) block_sums[blockIdx.x] = winc;
-    }
-    __syncthreads();
-    if (i < n) excl[i] = wsum[wid] + inc - v;
-}
-__global__ void scan_sums_kernel(uint64_t *block_sums, uint32_t nb, uint64_t *total)
-{
-    /* single thread: nb <= a few thousand */
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint64_t acc = 0;
-        for (uint32_t i = 0; i < nb; i++) { uint64_t t = block_sums[i]; block_sums[i] = acc; acc += t; }
-        *total = acc;
-    }
-}
-__global__ void __launch_bounds__(1024)
-scan_add_kernel(uint64_t *__restrict__ excl, const uint64_t *__restrict__ block_sums, uint32_t n)
-{
-    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
-    if (i < n) excl[i] += block_sums[blockIdx.x];
 }
 
 } /* namespace wfak */

@@ -429,6 +429,7 @@ lane_kernel(const KParams P)
     unsigned char *smem = smem_raw + (size_t)wib * lane_smem_bytes(P.dM, P.dE, P.ring_cap, P.group);
     const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     uint8_t *slot = P.arena + worker * P.slot_bytes;
+    if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(&P.ctr->t_first, t); }
     for (;;) {
         uint32_t first = 0;
         if (lane == 0) first = (uint32_t)atomicAdd(&P.ctr->work_next, 32ull);
@@ -438,6 +439,7 @@ lane_kernel(const KParams P)
         const uint32_t pair = have ? (P.work ? P.work[first + lane] : first + lane) : 0u;
         lane_group(P, have, pair, smem, slot, P.slot_bytes);
     }
+    if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(&P.ctr->t_last, t); }
 }
 
 } /* namespace wfak */

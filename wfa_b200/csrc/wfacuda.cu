@@ -10,13 +10,14 @@
  *             class (one block per pair); pairs that ran out of ring width,
  *             arena or ops pool are re-queued with more of it -- still on the
  *             GPU, there is no CPU path
- *   download  prefix-sum n_ops, gather the ops into index order, D2H
+ *   download  D2H of the result records, each pair's position in the ops pool and the pool's used prefix
  */
 #include "../../include/wfacuda.h"
 #include "wfa_kernels.cuh"
 #include "wfa_lane.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,7 @@
 #include <ctime>
 #include <numeric>
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -38,6 +40,7 @@ static_assert(sizeof(RowHdr) == 24, "row header layout");
 namespace {
 
 thread_local std::string g_tls_error;
+double g_dbg_t0 = 0.0;          /* WFACUDA_DEBUG: start of the current wfacuda_align_batch call */
 
 struct DevBuf { void *p = nullptr; size_t cap = 0; };
 
@@ -45,7 +48,12 @@ struct DevBuf { void *p = nullptr; size_t cap = 0; };
 
 struct wfacuda_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     /* the stream work is issued on (normally stream_main) */
+    cudaStream_t stream_main = nullptr;
+    /* High-priority twin: once a batch's big kernel is done, its follow-ups (hand-over of the few
+     * pairs the LANE worker could not hold, retries, D2H) go here so that they do not queue behind
+     * the thousands of pending blocks of other pipeline workers' kernels. */
+    cudaStream_t stream_hi = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     wfacuda_config cfg{};
     uint32_t g = 1; int xg = 0, oeg = 0, eg = 0, dM = 0, dE = 0;
@@ -63,9 +71,19 @@ struct wfacuda_ctx {
     uint64_t budget_cache = 0;     /* arena budget; refreshed when the arena has to grow */
     wfacuda_stats stats{};
     uint64_t last_ops_total = 0;
+    const wfacuda_batch *pool_owner = nullptr;   /* batch whose ops the pool currently holds */
     int last_rc = 0;
     std::string err;
     std::vector<wfacuda_ctx *> subs;   /* pipeline workers of wfacuda_align_batch (same device) */
+    /* Pipeline workers take turns on the H2D copy engine: copies issued from several streams at
+     * once are served round-robin, so every chunk would arrive late and no kernel could start
+     * before most of the batch is across PCIe; one chunk at a time keeps arrival FIFO. */
+    struct Turns {                     /* counting semaphore */
+        std::mutex mu; std::condition_variable cv; int free_slots = 2;
+        void acquire() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return free_slots > 0; }); free_slots--; }
+        void release() { { std::lock_guard<std::mutex> lk(mu); free_slots++; } cv.notify_one(); }
+    } h2d_turns;                       /* owned by the parent ctx: two copies queued keep the engine busy across hand-overs */
+    Turns *h2d_turn = nullptr;         /* set in a worker ctx: the parent's semaphore */
 };
 
 struct wfacuda_batch {
@@ -77,8 +95,8 @@ struct wfacuda_batch {
     std::vector<PairDesc> descs;
     uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
     void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
-    void *d_results = nullptr, *d_where = nullptr, *d_dst = nullptr, *d_ops_sorted = nullptr, *d_bsums = nullptr;
-    size_t sz_raw = 0, sz_packed = 0, sz_descs = 0, sz_flags = 0, sz_results = 0, sz_where = 0, sz_dst = 0, sz_ops_sorted = 0, sz_bsums = 0;
+    void *d_results = nullptr, *d_where = nullptr;
+    size_t sz_raw = 0, sz_packed = 0, sz_descs = 0, sz_flags = 0, sz_results = 0, sz_where = 0;
     uint64_t ops_total = 0, n_invalid = 0;
     bool ran = false;
 };
@@ -225,6 +243,22 @@ int staged_d2h(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes, bool 
     return 0;
 }
 
+/* D2H of a small device region on the ctx's own stream, through the pinned staging buffer.
+ * (A plain cudaMemcpy runs on the legacy default stream; with several pipeline workers it was
+ * seen to wait for the other workers' queued kernels.) */
+int fetch_small(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    size_t done = 0;
+    while (done < bytes) {
+        const size_t chunk = std::min(ctx->pinned_cap, bytes - done);
+        CU(ctx, cudaMemcpyAsync(ctx->pinned[0], (const char *)src + done, chunk, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy((char *)dst + done, ctx->pinned[0], chunk);
+        done += chunk;
+    }
+    return 0;
+}
+
 /* ---- planning ------------------------------------------------------------ */
 
 struct Need { uint64_t arena; int width; };
@@ -349,7 +383,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.group * lp.workers))) return rc;
         if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
-        if (!ident) CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         /* reset queue + retry counters, keep the work counters and the ops cursor */
         Counters *dc = (Counters *)ctx->ctr.p;
         CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
@@ -360,6 +394,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = lp.ring_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+        const double tk0 = now_ms();
         if (cta) { if (bits == 2) align_kernel<2, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
                    else           align_kernel<8, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
         else     { if (bits == 2) align_kernel<2, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
@@ -368,8 +403,8 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         ctx->stats.kernel_launches++; ctx->stats.align_launches++;
         ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, lp.slot_bytes * lp.group * lp.workers);
         Counters hc;
-        CU(ctx, cudaMemcpyAsync(&hc, dc, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   %s kernel: host launch at %.2f, sync returned %.2f ms since call\n", cta ? "cta" : "warp", tk0 - g_dbg_t0, now_ms() - g_dbg_t0);
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch %s bits=%d attempt %d: %zu pairs, %d blocks x %d thr, ring_cap %d, group %d, smem %zu, slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", cta ? "cta" : "warp", bits, attempt, order.size(), lp.blocks, lp.threads, lp.ring_cap, lp.group, lp.smem, lp.slot_bytes / 1024.0, ctx->arena_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
         if (hc.retry_n == 0) {
             /* learn: aim the next batch's slots at 1.5x the largest slot use seen */
@@ -380,7 +415,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
             break;
         }
         std::vector<uint64_t> rl(hc.retry_n);
-        CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
+        { int rc2 = fetch_small(ctx, rl.data(), ctx->retry.p, hc.retry_n * 8); if (rc2) return rc2; }
         std::vector<uint32_t> again, wide;
         bool ops_full = false, arena_full = false;
         for (uint64_t r : rl) {
@@ -517,27 +552,31 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         if ((rc = ensure(ctx, ctx->arena, slot * workers))) return rc;
         if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
-        if (!ident) CU(ctx, cudaMemcpyAsync(ctx->work.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         Counters *dc = (Counters *)ctx->ctr.p;
         CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&dc->t_first, 0xff, 8, ctx->stream));
+        CU(ctx, cudaMemsetAsync(&dc->t_last, 0, 8, ctx->stream));
         KParams P = base;
         P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = sw;      /* LANE kernel: group = words per sequence */
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         const int blocks = (int)(workers / WFA_LANE_WARPS);
+        const double tl0 = now_ms();
         lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P);
         CU(ctx, cudaGetLastError());
+        const double tl1 = now_ms();
         ctx->stats.kernel_launches++; ctx->stats.align_launches++;
         ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, slot * workers);
         Counters hc;
-        CU(ctx, cudaMemcpyAsync(&hc, dc, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   lane kernel: host launch at %.2f (took %.2f), sync returned %.2f ms since call; device span %.3f ms, device end = host %+.3f\n", tl0 - g_dbg_t0, tl1 - tl0, now_ms() - g_dbg_t0, (hc.t_last - hc.t_first) / 1e6, fmod(now_ms(), 1000.0) - (hc.t_last % 1000000000ull) / 1e6);
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d blocks x %d thr (%d/SM), smem %zu, group slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", attempt, order.size(), blocks, threads, ctx->lane_occ, smem, slot / 1024.0, ctx->lane_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
         std::vector<uint64_t> rl(hc.retry_n);
-        if (hc.retry_n) CU(ctx, cudaMemcpy(rl.data(), ctx->retry.p, hc.retry_n * 8, cudaMemcpyDeviceToHost));
+        if (hc.retry_n) { int rc2 = fetch_small(ctx, rl.data(), ctx->retry.p, hc.retry_n * 8); if (rc2) return rc2; }
         std::vector<uint32_t> again;
         bool ops_full = false, arena_full = false;
         for (uint64_t r : rl) {
@@ -607,7 +646,13 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
     if (prop.major != 10) { fail(ctx, WFACUDA_E_CUDA, "device %d is sm_%d%d; libwfacuda is built for sm_100a only", device, prop.major, prop.minor); return bail(); }
     ctx->device = device; ctx->sm_count = prop.multiProcessorCount; ctx->smem_optin = prop.sharedMemPerBlockOptin; ctx->total_mem = prop.totalGlobalMem;
     if (cudaSetDevice(device) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "cudaSetDevice failed"); return bail(); }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "stream creation failed"); return bail(); }
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&ctx->stream_main, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "stream creation failed"); return bail(); }
+        ctx->stream = ctx->stream_main;
+    }
     for (auto &ev : ctx->ev) if (cudaEventCreate(&ev) != cudaSuccess) { fail(ctx, WFACUDA_E_CUDA, "event creation failed"); return bail(); }
     ctx->pinned_cap = 16u << 20;
     for (int i = 0; i < 2; i++) {
@@ -623,6 +668,19 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
         fail(ctx, WFACUDA_E_CUDA, "cudaFuncSetAttribute(max dynamic shared memory) failed: %s", cudaGetErrorString(cudaGetLastError()));
         return bail();
     }
+    /* One shared-memory carveout for every kernel: an SM has to drain before it can switch
+     * carveout, so a small follow-up kernel with the default (small) preference would wait
+     * behind the whole backlog of other pipeline workers' big kernels (measured: 6 ms). */
+    {
+        const int mx = (int)cudaSharedmemCarveoutMaxShared;
+        cudaFuncSetAttribute(align_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(align_kernel<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(align_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(align_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaGetLastError();
+    }
     return ctx;
 }
 
@@ -632,12 +690,14 @@ void wfacuda_destroy(wfacuda_ctx *ctx)
     for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);
     ctx->subs.clear();
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream_main) cudaStreamSynchronize(ctx->stream_main);
+    if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
     for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool}) if (b->p) cudaFree(b->p);
     for (auto &f : ctx->free_dev) cudaFree(f.first);
     for (int i = 0; i < 2; i++) { if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]); if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]); }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream_main) cudaStreamDestroy(ctx->stream_main);
+    if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
     delete ctx;
 }
 
@@ -699,8 +759,7 @@ void wfacuda_batch_free(wfacuda_ctx *ctx, wfacuda_batch *b)
         dev_give(ctx, &b->d_raw, &b->sz_raw); dev_give(ctx, &b->d_packed, &b->sz_packed);
         dev_give(ctx, &b->d_descs, &b->sz_descs); dev_give(ctx, &b->d_flags, &b->sz_flags);
         dev_give(ctx, &b->d_results, &b->sz_results); dev_give(ctx, &b->d_where, &b->sz_where);
-        dev_give(ctx, &b->d_dst, &b->sz_dst); dev_give(ctx, &b->d_ops_sorted, &b->sz_ops_sorted);
-        dev_give(ctx, &b->d_bsums, &b->sz_bsums);
+        if (ctx->pool_owner == b) ctx->pool_owner = nullptr;
     }
     delete b;
 }
@@ -752,7 +811,12 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         if ((rc = dev_take(ctx, &b->d_results, &b->sz_results, n_pairs * sizeof(Result)))) return rc;
         if ((rc = dev_take(ctx, &b->d_where, &b->sz_where, n_pairs * 8))) return rc;
         if (b->raw_bytes) {
-            if ((rc = staged_h2d(ctx, b->d_raw, seq_bytes + base, b->raw_bytes))) return rc;
+            if (ctx->h2d_turn && b->raw_bytes >= 65536 && is_pinned(seq_bytes + base)) {
+                struct Turn { wfacuda_ctx::Turns *t; Turn(wfacuda_ctx::Turns *t_) : t(t_) { t->acquire(); } ~Turn() { t->release(); } } turn(ctx->h2d_turn);
+                CU(ctx, cudaMemcpyAsync(b->d_raw, seq_bytes + base, b->raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+                CU(ctx, cudaStreamSynchronize(ctx->stream));
+                ctx->stats.h2d_bytes += b->raw_bytes;
+            } else if ((rc = staged_h2d(ctx, b->d_raw, seq_bytes + base, b->raw_bytes))) return rc;
             CU(ctx, cudaMemsetAsync((char *)b->d_raw + b->raw_bytes, 0, 64, ctx->stream));
         }
         const double t2 = now_ms();
@@ -838,6 +902,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(ctx, cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
     CU(ctx, cudaMemsetAsync(b->d_flags, 0, b->sz_flags, ctx->stream));
+    if (n) CU(ctx, cudaMemsetAsync(b->d_where, 0, n * 8, ctx->stream));
     /* results start as PENDING, or as the host-side verdict (EMPTY / TOO_LONG) */
     if (b->n_invalid) {
         std::vector<Result> init(n);
@@ -877,7 +942,11 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     /* LANE class first (short global pairs, 2-bit only), then the WARP class incl. what the LANE
      * class handed over (2-bit, then 8-bit), then the CTA class */
     std::vector<uint32_t> to_warp, to_cta, warp8, cta8;
+    /* everything after the first (big) launch of a batch has been waited for by the host, so
+     * moving to the high-priority stream needs no event; restored (and drained) before returning */
+    struct StreamGuard { wfacuda_ctx *c; ~StreamGuard() { if (c->stream != c->stream_main) { cudaStreamSynchronize(c->stream); c->stream = c->stream_main; } } } guard{ctx};
     if ((rc = run_lane_class(ctx, b, b->order_lane, b->identity_cls == 2, P, &to_warp, &warp8))) return rc;
+    if (!b->order_lane.empty()) ctx->stream = ctx->stream_hi;
     ctx->stats.pairs_lane = (uint32_t)(b->order_lane.size() - to_warp.size() - warp8.size());
     std::vector<uint32_t> warp_extra;                       /* only built when the LANE class handed pairs over */
     if (!to_warp.empty()) { warp_extra = b->order_warp; warp_extra.insert(warp_extra.end(), to_warp.begin(), to_warp.end()); }
@@ -895,33 +964,10 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     ctx->stats.pairs_8bit = force8 ? (uint32_t)n_valid : (uint32_t)(warp8.size() + cta8.size());
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
 
-    /* index-order offsets of the ops + total */
-    if (!b->d_dst && (rc = dev_take(ctx, &b->d_dst, &b->sz_dst, n * 8 + 8))) return rc;
-    const uint32_t nb = (uint32_t)((n + 1023) / 1024);
-    if (!b->d_bsums && (rc = dev_take(ctx, &b->d_bsums, &b->sz_bsums, (size_t)nb * 8 + 16))) return rc;
-    uint64_t *d_total = (uint64_t *)b->d_bsums + nb;
-    if (n) {
-        scan_block_kernel<<<nb, 1024, 0, ctx->stream>>>((const Result *)b->d_results, (uint32_t)n, (uint64_t *)b->d_dst, (uint64_t *)b->d_bsums);
-        scan_sums_kernel<<<1, 32, 0, ctx->stream>>>((uint64_t *)b->d_bsums, nb, d_total);
-        scan_add_kernel<<<nb, 1024, 0, ctx->stream>>>((uint64_t *)b->d_dst, (const uint64_t *)b->d_bsums, (uint32_t)n);
-        CU(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches += 3;
-        CU(ctx, cudaMemcpyAsync(&b->ops_total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    } else b->ops_total = 0;
+    /* ops stay where the kernels put them (completion order): pair i's words start at
+     * d_where[i] of the pool, and the pool's used prefix is what download() copies */
     Counters hc{};
-    CU(ctx, cudaMemcpyAsync(&hc, ctx->ctr.p, sizeof hc, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    if (b->ops_total) {
-        if (b->sz_ops_sorted < b->ops_total * 8) {
-            dev_give(ctx, &b->d_ops_sorted, &b->sz_ops_sorted);
-            if ((rc = dev_take(ctx, &b->d_ops_sorted, &b->sz_ops_sorted, b->ops_total * 8))) return rc;
-        }
-        const int gb = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);
-        gather_ops_kernel<<<gb, 256, 0, ctx->stream>>>((const Result *)b->d_results, (const uint64_t *)b->d_where, (const uint64_t *)b->d_dst,
-                                                      (const uint64_t *)ctx->ops_pool.p, (uint64_t *)b->d_ops_sorted, (uint32_t)n);
-        CU(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches++;
-    }
+    if ((rc = fetch_small(ctx, &hc, ctx->ctr.p, sizeof hc))) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->stats.ms_pack, ctx->ev[0], ctx->ev[1]);
@@ -929,6 +975,8 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     cudaEventElapsedTime(&ctx->stats.ms_total_device, ctx->ev[0], ctx->ev[3]);
     ctx->stats.pairs = n_valid; ctx->stats.cells = hc.cells; ctx->stats.cells_written = hc.cells_written;
     ctx->stats.score_steps = hc.steps; ctx->stats.ops = hc.ops; ctx->stats.seq_bases = b->seq_bases;
+    b->ops_total = hc.ops_cursor;
+    ctx->pool_owner = b;
     ctx->last_ops_total = b->ops_total;
     b->ran = true;
     if (dbg) fprintf(stderr, "[wfacuda] run: prep %.2f ms, warp class %.2f ms, rest %.2f ms | device: pack %.2f align %.2f total %.2f\n",
@@ -941,18 +989,19 @@ int wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *r
 {
     if (!ctx || !b) return fail(ctx, WFACUDA_E_INVALID, "NULL ctx or batch");
     if (!b->ran) return fail(ctx, WFACUDA_E_INVALID, "batch has not been run");
+    if (ops && ctx->pool_owner != b) return fail(ctx, WFACUDA_E_INVALID, "another batch ran on this ctx since: its ops replaced this batch's (download right after run)");
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = b->n_pairs;
     const double t0 = now_ms();
     int rc;
     if (n && results) if ((rc = staged_d2h(ctx, results, b->d_results, n * sizeof(Result), true))) return rc;
-    if (n && ops_off) if ((rc = staged_d2h(ctx, ops_off, b->d_dst, n * 8, true))) return rc;
+    if (n && ops_off) if ((rc = staged_d2h(ctx, ops_off, b->d_where, n * 8, true))) return rc;
     if (ops) {
         if (b->ops_total > ops_capacity) {
             cudaStreamSynchronize(ctx->stream);
             return fail(ctx, WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)b->ops_total);
         }
-        if (b->ops_total) if ((rc = staged_d2h(ctx, ops, b->d_ops_sorted, b->ops_total * 8, true))) return rc;
+        if (b->ops_total) if ((rc = staged_d2h(ctx, ops, ctx->ops_pool.p, b->ops_total * 8, true))) return rc;
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));       /* copies into page-locked caller memory were left in flight */
     if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] download: %.2f ms for %.1f MB\n", now_ms() - t0, ctx->stats.d2h_bytes / 1e6);
@@ -1025,14 +1074,17 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         c.arena_budget_bytes = std::max<uint64_t>(share, 64u << 20);
         wfacuda_ctx *sub = wfacuda_create(ctx->device, &c);
         if (!sub) return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: %s", g_tls_error.c_str());
+        sub->h2d_turn = &ctx->h2d_turns;
         ctx->subs.push_back(sub);
     }
+    if (const char *e = getenv("WFACUDA_H2D_TURNS")) ctx->h2d_turns.free_slots = std::max(1, atoi(e));
     std::atomic<uint64_t> next{0}, cursor{0};
     std::atomic<int> first_err{0};
     std::mutex mu;
     wfacuda_stats total{};
     std::string err_text;
     const double t_begin = now_ms();
+    g_dbg_t0 = t_begin;
     std::vector<double> t_up(K, 0.0), t_run(K, 0.0), t_down(K, 0.0);
     auto work = [&](int k) {
         wfacuda_ctx *sub = ctx->subs[k];
@@ -1053,6 +1105,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
                 if (rc == 0 && ops_off) for (uint64_t i = 0; i < cnt; i++) ops_off[a + i] += base;
             }
             t_down[k] += now_ms() - w2;
+            if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   chunk %2llu worker %d: start %.2f uploaded %.2f ran %.2f downloaded %.2f (ms since call)\n", (unsigned long long)c, k, w0 - t_begin, w1 - t_begin, w2 - t_begin, now_ms() - t_begin);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 add_stats(total, sub->stats);
