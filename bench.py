@@ -117,6 +117,16 @@ def run_cpu(args, workload, cfgc):
 
 
 def main():
+    # stdout carries exactly one line, the JSON result: libraries that print there (NCCL's version
+    # banner, ...) are sent to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -146,7 +156,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample,
                                  "note": "C restatement of wfa-go (oracle/); no Go toolchain, reference not buildable"},
                 "e2e": {"value": v, "unit": "alignments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -259,7 +269,7 @@ def main():
             v, sec, cores, cb, sample = run_cpu(a, workload, cfgc)
             line["cpu_baseline"] = {"value": v, "unit": "alignments/s", "cores": cores, "kind": "port", "sample": sample,
                                     "gcups_equiv": cb.cells_equiv() / sec / 1e9}
-        print(json.dumps(line))
+        emit(line)
     algn.close()
     if world > 1:
         dist.destroy_process_group()

@@ -284,7 +284,7 @@ __device__ __forceinline__ uint32_t op_of_type(uint32_t t)
 /* backTrace, wfa.go:703-983, executed by one thread.  Returns ops (reversed
  * order, merged) in sink; fills score/begin/end of res. */
 template <class View>
-__device__ __noinline__ void back_trace(const View &A, const KParams &P, int n, int m,
+__device__ __noinline__ void back_trace(View &A, const KParams &P, int n, int m,
                                         uint32_t s0, int Ak, Result &res, OpSink &sink)
 {
     const bool semi = !P.global_aln;

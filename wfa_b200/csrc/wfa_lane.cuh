@@ -23,7 +23,7 @@
  * "absent" (0), so the diagonal loop reads its five sources without any range test.
  *
  * Backtrace arena (HBM, one slot per warp, reused group after group):
- *   hdr   int4 {lo, hi, off, aw} per score index, shared by the 32 pairs
+ *   (row headers {lo, hi, first word} per score index, shared by the 32 pairs, stay in shared memory)
  *   cell  u32 [aw][32] per score: M | I<<8 | D<<16 (offsets)
  * i.e. 4 bytes per (score, diagonal, pair) instead of the 12 of three raw words.  The 3-bit
  * provenance codes are not stored: `next` picks them as a function of the five source offsets,
@@ -45,10 +45,13 @@ constexpr int LANE_MAX_LEN = 254;           /* offsets up to m+1 must fit a byte
 #define WFA_LANE_WARPS 2
 #endif
 
+constexpr int LANE_HDR_ROWS = 64;            /* scores (in units of g) a group may reach; beyond: WARP worker */
+
 /* dM, dE as in KParams (max(x,o+e)/g+1, e/g+1); W ring columns; SW words per sequence */
 __host__ __device__ inline size_t lane_smem_bytes(int dM, int dE, int W, int SW)
 {
     size_t b = (((size_t)dM * 8) + 15) & ~(size_t)15;                 /* meta int2[] */
+    b += (size_t)LANE_HDR_ROWS * 8;                                    /* row headers int2[] */
     b += 2 * (size_t)SW * 128;                                         /* seqQ, seqT */
     b += ((size_t)(dM - 1) + 2 * (size_t)(dE - 1)) * (size_t)W * 32;   /* rings (in place: one row less than the WARP worker) */
     return (b + 127) & ~(size_t)127;
@@ -135,35 +138,54 @@ __device__ __forceinline__ Cell3O next_off3(uint32_t mo_l, uint32_t ie_l, uint32
     return r;
 }
 
-/* Component.Get on the packed group arena (see the header comment) */
+/* Component.Get on the packed group arena (see the header comment).  The row headers live in
+ * shared memory, and the view remembers the five source words it fetched for the cell the
+ * backtrace stands on: the next cell of the walk and the offsets the reference re-derives
+ * there (wfa.go:766-817) are always among them, so one step of the backtrace costs one round of
+ * five independent global loads instead of six dependent ones. */
 struct LaneView {
-    const int4     *hdr;
+    const int2     *hdr;       /* shared memory: {lo | hi << 16 (both + 0x4000), first word of the row} */
     const uint32_t *cells;     /* already offset by the lane */
     int             si_last;
     int             n, m, xg, oeg, eg;
     bool            first_eq;
+    int             c_si, c_k;                 /* cell whose sources are cached (c_si < 0: none) */
+    uint32_t        c_w[5];                    /* words at (si-oeg,k-1) (si-eg,k-1) (si-oeg,k+1) (si-eg,k+1) (si-xg,k) */
     __device__ __forceinline__ uint32_t word(int si, int k) const
     {
         if (si < 0 || si > si_last) return 0;
-        const int4 h = hdr[si];
-        if (k < h.x || k > h.y) return 0;
-        return cells[(uint32_t)h.z + (uint32_t)(k - h.x) * 32u];
+        const int2 h = hdr[si];
+        const int lo = (h.x & 0xffff) - 0x4000, hi = (int)((uint32_t)h.x >> 16) - 0x4000;
+        if (k < lo || k > hi) return 0;
+        return cells[(uint32_t)h.y + (uint32_t)(k - lo) * 32u];
+    }
+    __device__ __forceinline__ uint32_t cached_word(int si, int k) const
+    {
+        const int dk = k - c_k, ds = c_si - si;
+        if (c_si >= 0) {
+            if (dk == -1) { if (ds == oeg) return c_w[0]; if (ds == eg) return c_w[1]; }
+            else if (dk == 1) { if (ds == oeg) return c_w[2]; if (ds == eg) return c_w[3]; }
+            else if (dk == 0 && ds == xg) return c_w[4];
+        }
+        return word(si, k);
     }
     /* offset << 3, code bits zero: all the backtrace needs of a source cell */
     __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
     {
-        return ((word(si, k) >> (8 * comp)) & 255u) << T_BITS;
+        return ((cached_word(si, k) >> (8 * comp)) & 255u) << T_BITS;
     }
     /* raw word of the cell the backtrace stands on: offset << 3 | provenance code, the code
      * re-derived from the cell's five sources exactly as `next` chose it (wfa.go:579-698), or
      * the init code when `next` wrote nothing there (wfa.go:155-158) */
-    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k) const
+    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k)
     {
-        const uint32_t o = (word(si, k) >> (8 * comp)) & 255u;
+        const uint32_t o = (cached_word(si, k) >> (8 * comp)) & 255u;
         if (o == 0) return 0;
-        const uint32_t wl = word(si - oeg, k - 1), wr = word(si - oeg, k + 1);
-        const uint32_t el = word(si - eg, k - 1), er = word(si - eg, k + 1);
-        const CellO c = next_off(wl & 255u, (el >> 8) & 255u, wr & 255u, (er >> 16) & 255u, word(si - xg, k) & 255u,
+        const uint32_t wl = word(si - oeg, k - 1), el = word(si - eg, k - 1);
+        const uint32_t wr = word(si - oeg, k + 1), er = word(si - eg, k + 1);
+        const uint32_t wx = word(si - xg, k);
+        c_si = si; c_k = k; c_w[0] = wl; c_w[1] = el; c_w[2] = wr; c_w[3] = er; c_w[4] = wx;
+        const CellO c = next_off(wl & 255u, (el >> 8) & 255u, wr & 255u, (er >> 16) & 255u, wx & 255u,
                                  (uint32_t)m, (uint32_t)(n + k));
         uint32_t code;
         if (comp == 1) code = T_INS_OPEN + ((c.code >> 3) & 1u);
@@ -208,7 +230,8 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     const int xg = P.xg, oeg = P.oeg, x = (int)P.x;
 
     int2 *meta = reinterpret_cast<int2 *>(smem);
-    unsigned char *p = smem + ((((size_t)P.dM * 8) + 15) & ~(size_t)15);
+    int2 *hdrs = reinterpret_cast<int2 *>(smem + ((((size_t)P.dM * 8) + 15) & ~(size_t)15));
+    unsigned char *p = reinterpret_cast<unsigned char *>(hdrs + LANE_HDR_ROWS);
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)lane * 4u;
     const uint32_t sT = sQ + (uint32_t)SW * 128u;
     const uint32_t rowB = (uint32_t)W * 32u;
@@ -251,11 +274,10 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     const int clamp_lo = -(__reduce_min_sync(FULL, act ? n : INT_MAX) - 1), clamp_hi = __reduce_min_sync(FULL, act ? m : INT_MAX) - 1;
     const int ulo = -(__reduce_max_sync(FULL, act ? n : 1) - 1), uhi = __reduce_max_sync(FULL, act ? m : 1) - 1;
 
-    int4     *hdrs  = reinterpret_cast<int4 *>(slot);
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
     const uint32_t slot_words = (uint32_t)min((uint64_t)0xfffffff0u, slot_bytes >> 2);
     uint32_t top = slot_words;
-    uint32_t hdr_limit = 2 * 4 + 64 * 32;              /* header words incl. the next one + a minimum of op scratch */
+    const uint32_t hdr_limit = 64 * 32;                /* the slot starts with the op scratch: room for 32 ops per pair at least */
 
     uint32_t s = 0; int si = 0, cur = 0, curE = 0;
     bool done = false; uint32_t minS = 0; int my_si = 0;
@@ -284,7 +306,7 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
         const uint32_t bCM = rM + (uint32_t)cur * rowB, bCI = rI + (uint32_t)curE * rowB, bCD = rD + (uint32_t)curE * rowB;
         if (lo <= hi) {
             aw = hi - lo + 1;
-            if (lo < -KC + 1 || hi > KC - 2) { group_fail = ST_RING; break; }
+            if (lo < -KC + 1 || hi > KC - 2 || si >= LANE_HDR_ROWS) { group_fail = ST_RING; break; }
             const uint32_t need = (uint32_t)aw * 32u;
             if (top < hdr_limit || top - hdr_limit < need) { group_fail = ST_ARENA; break; }
             off = top - need;
@@ -329,26 +351,35 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
             auto row = [&](auto clamp) {
                 int k = lo;
                 uint32_t o_m1 = lds_u8o<-32>(pO), o_0 = lds_u8o<0>(pO), i_m1 = lds_u8o<-32>(pI);
-                for (; k < hi; k += 2) {
-                    const uint32_t o_p1 = lds_u8o<32>(pO), o_p2 = lds_u8o<64>(pO);
-                    const uint32_t i_0 = lds_u8o<0>(pI), i_p1 = lds_u8o<32>(pI);
-                    const uint32_t d_p1 = lds_u8o<32>(pD), d_p2 = lds_u8o<64>(pD);
-                    const uint32_t x_0 = lds_u8o<0>(pX), x_p1 = lds_u8o<32>(pX);
+                auto word_of = [](const Pend &q) { return q.c.M | q.c.I << 8 | q.c.D << 16; };
+                /* four diagonals per pass: their dependency chains interleave (the warps per SM
+                 * are few -- shared memory -- so the instruction-level parallelism has to come from here) */
+                for (; k + 3 <= hi; k += 4) {
+                    const uint32_t o_p1 = lds_u8o<32>(pO), o_p2 = lds_u8o<64>(pO), o_p3 = lds_u8o<96>(pO), o_p4 = lds_u8o<128>(pO);
+                    const uint32_t i_0 = lds_u8o<0>(pI), i_p1 = lds_u8o<32>(pI), i_p2 = lds_u8o<64>(pI), i_p3 = lds_u8o<96>(pI);
+                    const uint32_t d_p1 = lds_u8o<32>(pD), d_p2 = lds_u8o<64>(pD), d_p3 = lds_u8o<96>(pD), d_p4 = lds_u8o<128>(pD);
+                    const uint32_t x_0 = lds_u8o<0>(pX), x_p1 = lds_u8o<32>(pX), x_p2 = lds_u8o<64>(pX), x_p3 = lds_u8o<96>(pX);
                     Pend q0 = cell_a(clamp, k, o_m1, i_m1, o_p1, d_p1, x_0);
                     Pend q1 = cell_a(clamp, k + 1, o_0, i_0, o_p2, d_p2, x_p1);
-                    cell_b(q0, k); cell_b(q1, k + 1);
+                    Pend q2 = cell_a(clamp, k + 2, o_p1, i_p1, o_p3, d_p3, x_p2);
+                    Pend q3 = cell_a(clamp, k + 3, o_p2, i_p2, o_p4, d_p4, x_p3);
+                    cell_b(q0, k); cell_b(q1, k + 1); cell_b(q2, k + 2); cell_b(q3, k + 3);
                     sts_u8o<0>(pM, q0.c.M); sts_u8o<0>(pI, q0.c.I); sts_u8o<0>(pD, q0.c.D);
                     sts_u8o<32>(pM, q1.c.M); sts_u8o<32>(pI, q1.c.I); sts_u8o<32>(pD, q1.c.D);
-                    gp[0] = q0.c.M | q0.c.I << 8 | q0.c.D << 16; gp[32] = q1.c.M | q1.c.I << 8 | q1.c.D << 16;
-                    o_m1 = o_p1; o_0 = o_p2; i_m1 = i_p1;
-                    pO += 64; pX += 64; pM += 64; pI += 64; pD += 64; gp += 64;
+                    sts_u8o<64>(pM, q2.c.M); sts_u8o<64>(pI, q2.c.I); sts_u8o<64>(pD, q2.c.D);
+                    sts_u8o<96>(pM, q3.c.M); sts_u8o<96>(pI, q3.c.I); sts_u8o<96>(pD, q3.c.D);
+                    gp[0] = word_of(q0); gp[32] = word_of(q1); gp[64] = word_of(q2); gp[96] = word_of(q3);
+                    o_m1 = o_p3; o_0 = o_p4; i_m1 = i_p3;
+                    pO += 128; pX += 128; pM += 128; pI += 128; pD += 128; gp += 128;
                 }
-                if (k == hi) {
-                    const uint32_t o_p1 = lds_u8o<32>(pO), d_p1 = lds_u8o<32>(pD), x_0 = lds_u8o<0>(pX);
+                for (; k <= hi; k++) {
+                    const uint32_t o_p1 = lds_u8o<32>(pO), i_0 = lds_u8o<0>(pI), d_p1 = lds_u8o<32>(pD), x_0 = lds_u8o<0>(pX);
                     Pend q0 = cell_a(clamp, k, o_m1, i_m1, o_p1, d_p1, x_0);
                     cell_b(q0, k);
                     sts_u8o<0>(pM, q0.c.M); sts_u8o<0>(pI, q0.c.I); sts_u8o<0>(pD, q0.c.D);
-                    gp[0] = q0.c.M | q0.c.I << 8 | q0.c.D << 16;
+                    gp[0] = word_of(q0);
+                    o_m1 = o_0; o_0 = o_p1; i_m1 = i_0;
+                    pO += 32; pX += 32; pM += 32; pI += 32; pD += 32; gp += 32;
                 }
             };
             if (lo < clamp_lo || hi > clamp_hi) row(std::true_type{}); else row(std::false_type{});
@@ -386,17 +417,18 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
         }
         __syncwarp();
         meta[cur] = any ? make_int2(lo, hi) : EMPTY;                      /* same value from every lane; a row nobody has holds zeros only */
-        if (lane == 0) hdrs[si] = any ? make_int4(lo, hi, (int)off, aw) : make_int4(1, 0, 0, 0);
+        if (lane == 0 && si < LANE_HDR_ROWS)
+            hdrs[si] = any ? make_int2((lo + 0x4000) | (hi + 0x4000) << 16, (int)off) : make_int2(0x4001 | 0x4000 << 16, 0);
         __syncwarp();
         if (__all_sync(FULL, !act || done)) break;
-        s += P.g; si++; hdr_limit += 4;
+        s += P.g; si++;
         cur = cur + 1 == RM ? 0 : cur + 1;
         curE = curE + 1 == RE ? 0 : curE + 1;
     }
     if (act && !done) status = group_fail ? group_fail : ST_ARENA;
 
     /* ---------------- backtrace (wfa.go:703-983), lane-parallel, then the group's results */
-    const uint32_t scratch_w = ((((uint32_t)(si + 1) * 16u) + 7u) / 8u) * 2u;
+    const uint32_t scratch_w = 0;
     uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w) + lane;
     Result res;
     res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
@@ -406,7 +438,8 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     __syncwarp();
     __threadfence_block();
     if (status == ST_OK) {
-        LaneView A; A.hdr = hdrs; A.cells = cells + lane; A.si_last = my_si;
+        LaneView A; A.hdr = hdrs; A.cells = cells + lane; A.si_last = my_si; A.c_si = -1; A.c_k = 0;
+        A.c_w[0] = A.c_w[1] = A.c_w[2] = A.c_w[3] = A.c_w[4] = 0;
         A.n = n; A.m = m; A.xg = P.xg; A.oeg = P.oeg; A.eg = P.eg; A.first_eq = first_eq;
         OpSink sink; sink.buf = scratch; sink.stride = 32;
         sink.cap = top > scratch_w ? (top - scratch_w) / 64u : 0u;

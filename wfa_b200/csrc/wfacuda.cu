@@ -79,10 +79,10 @@ struct wfacuda_ctx {
      * once are served round-robin, so every chunk would arrive late and no kernel could start
      * before most of the batch is across PCIe; one chunk at a time keeps arrival FIFO. */
     struct Turns {                     /* counting semaphore */
-        std::mutex mu; std::condition_variable cv; int free_slots = 2;
+        std::mutex mu; std::condition_variable cv; int free_slots = 1;
         void acquire() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return free_slots > 0; }); free_slots--; }
         void release() { { std::lock_guard<std::mutex> lk(mu); free_slots++; } cv.notify_one(); }
-    } h2d_turns;                       /* owned by the parent ctx: two copies queued keep the engine busy across hand-overs */
+    } h2d_turns;                       /* owned by the parent ctx; one copy at a time measured best (WFACUDA_H2D_TURNS) */
     Turns *h2d_turn = nullptr;         /* set in a worker ctx: the parent's semaphore */
 };
 
@@ -1041,22 +1041,27 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     if (!ctx) return fail(nullptr, WFACUDA_E_INVALID, "ctx is NULL");
     if (n_pairs && !results) return fail(ctx, WFACUDA_E_INVALID, "results is NULL");
     if (n_pairs && (!seq_bytes || !q_off || !q_len || !t_off || !t_len)) return fail(ctx, WFACUDA_E_INVALID, "NULL input array");
-    const uint64_t kMinChunk = 65536;
+    const uint64_t kMinChunk = 32768;
     if (n_pairs < 2 * kMinChunk || getenv("WFACUDA_NO_PIPELINE")) {
         int rc = align_batch_single(ctx, n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
         if (rc == 0 || rc == WFACUDA_E_OPS_CAPACITY) return rc;
         return rc;
     }
-    /* chunk size: >= kMinChunk pairs (fills the persistent grid several times), <= ~192 MB of sequence */
+    /* chunk size: about 16 MB of sequence (0.3 ms of PCIe), at least kMinChunk pairs */
     uint64_t sample_bytes = 0;
     const uint64_t sample_n = std::min<uint64_t>(n_pairs, 4096);
     for (uint64_t i = 0; i < sample_n; i++) sample_bytes += (uint64_t)q_len[i * (n_pairs / sample_n)] + t_len[i * (n_pairs / sample_n)];
     const double mean_bytes = std::max(1.0, (double)sample_bytes / (double)sample_n);
-    uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)(24e6 / mean_bytes)));
+    /* pageable caller memory is staged by the workers themselves (host memcpy, memory-bound):
+     * fewer, larger chunks there */
+    const bool src_pinned = is_pinned(seq_bytes);
+    uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 16e6 : 24e6) / mean_bytes)));
     if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     const uint64_t n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
     const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-    unsigned kmax = std::min<unsigned>(8, hw / 2);
+    /* one worker per chunk in flight: enough of them that uploads (PCIe-bound, taken in turns)
+     * never wait for a worker that is still computing or downloading */
+    unsigned kmax = src_pinned ? std::min<unsigned>(16, std::max(2u, hw - 2)) : std::min<unsigned>(8, hw / 2);
     if (const char *e = getenv("WFACUDA_PIPE_WORKERS")) kmax = std::max(1, atoi(e));
     const int K = (int)std::min<uint64_t>(kmax, n_chunks);
     if ((int)ctx->subs.size() < K && ctx->arena.p) {
