@@ -977,35 +977,38 @@ align_kernel(const KParams P)
 }
 
 /* 2-bit packing of every sequence of the batch + detection of non-ACGT bytes.
- * One warp per sequence (2*n_pairs sequences), lanes stride over 16-base
- * words: 4 aligned 32-bit loads in, one 32-bit word out. */
+ * One warp per pair: lanes 0-15 stride over the 16-base words of the query, lanes 16-31 over
+ * those of the target; 5 aligned 32-bit loads in (neighbouring lanes read neighbouring bytes),
+ * one 32-bit word out. */
 __global__ void __launch_bounds__(256)
 pack_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t *__restrict__ raw,
             uint32_t *__restrict__ packed, uint8_t *__restrict__ pflags)
 {
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
     const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t sq = warp0; sq < 2ull * n_pairs; sq += nwarps) {
-        const PairDesc pd = pairs[sq >> 1];
-        const bool is_t = sq & 1;
-        const uint64_t boff = is_t ? pd.t_byte : pd.q_byte;
-        const uint32_t len = is_t ? pd.m : pd.n;
-        uint32_t *out = packed + (is_t ? pd.t_word : pd.q_word);
+    for (uint64_t pr = warp0; pr < n_pairs; pr += nwarps) {
+        const PairDesc pd = pairs[pr];
+        const uint64_t boff = half ? pd.t_byte : pd.q_byte;
+        const uint32_t len = half ? pd.m : pd.n;
+        uint32_t *out = packed + (half ? pd.t_word : pd.q_word);
         const uint32_t nwords = (len + 15) >> 4;
         const uint32_t *src = raw + (boff >> 2);
         const uint32_t sh = (uint32_t)(boff & 3) * 8;
         bool bad = false;
-        for (uint32_t w = lane; w < nwords; w += 32) {
+        for (uint32_t w = l16; w < nwords; w += 16) {
             uint32_t in[5];
 #pragma unroll
             for (int j = 0; j < 5; j++) in[j] = __ldg(src + 4 * w + j);
+            const int left = (int)len - (int)(16 * w);                     /* bases from this word on */
             uint32_t o = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 uint32_t x = __funnelshift_r(in[j], in[j + 1], sh);       /* bases 16w+4j .. +3 */
-                const int rem = (int)len - (int)(16 * w + 4 * j);          /* valid bytes in x */
-                if (rem < 4) x = rem <= 0 ? 0x41414141u : ((x & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem)));
+                if (left < 16) {                                           /* last word: bytes past the end read as 'A' */
+                    const int rem = left - 4 * j;
+                    if (rem < 4) x = rem <= 0 ? 0x41414141u : ((x & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem)));
+                }
                 const uint32_t c = (x >> 1) & 0x03030303u;
                 /* valid iff every byte equals the letter its code maps back to (A,C,T,G) */
                 const uint32_t sel = (c & 3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
@@ -1015,7 +1018,7 @@ pack_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t
             }
             out[w] = o;
         }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(pflags) + (sq >> 3), 1u << (((sq >> 1) & 3) * 8));
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(pflags) + (pr >> 2), 1u << ((pr & 3) * 8));
     }
 }
 

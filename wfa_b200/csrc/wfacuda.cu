@@ -913,7 +913,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     } else if (n) CU(ctx, cudaMemsetAsync(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
     const uint64_t n_valid = b->order_warp.size() + b->order_cta.size() + b->order_lane.size();
     if (n_valid) {
-        const int pack_blocks = (int)std::min<uint64_t>((2 * n_valid + 7) / 8, (uint64_t)ctx->sm_count * 16);
+        const int pack_blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);      /* one warp per pair */
         pack_kernel<<<pack_blocks, 256, 0, ctx->stream>>>((const PairDesc *)b->d_descs, (uint32_t)n, (const uint32_t *)b->d_raw,
                                                          (uint32_t *)b->d_packed, (uint8_t *)b->d_flags);
         CU(ctx, cudaGetLastError());
