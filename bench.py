@@ -92,6 +92,22 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(kernel, workload, n_pairs):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_roofline.json, written by scripts/make_profiles.py); only quoted when this run
+    launches the kernel on the same workload and batch size as the capture."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline.json")))
+    except Exception:
+        return None, None
+    size = {"cfg2": ("cfg2_150bp_e5_global", 1_000_000), "cfg3": ("cfg3_1kbp_e10_global_adaptive", 100_000)}
+    for key, v in d.get("kernels", {}).items():
+        cfg, name = key.split(":", 1)
+        if size.get(cfg) == (workload, n_pairs) and kernel.split("<")[0] in name:
+            return int(v["dram_bytes"]), d.get("source")
+    return None, None
+
+
 def algorithmic_bytes(stats, batch):
     """B = 12*C + ceil((n+m)/4) + 8*R + 64 per pair (2-bit sequences)."""
     return 12 * stats["cells"] + (stats["seq_bases"] + 3) // 4 + 8 * stats["ops"] + 64 * stats["pairs"]
@@ -166,6 +182,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no GPU visible; the wfacuda arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -237,6 +254,8 @@ def main():
         k_sec = (ms_align / args.steps) / 1e3
         achieved = B / k_sec / 1e9
         int_ops = 32 * stats["cells"] + 10 * stats["cells"] + 8 * stats["cells"]      # O = 32C + 10V + 8W with V,W ~ C
+        kname = max((stats["pairs_lane"], "lane_kernel"), (stats["pairs_warp"], "align_kernel<warp>"), (stats["pairs_cta"], "align_kernel<cta>"))[1]
+        traffic, traffic_src = ncu_traffic(kname, workload, n_pairs)
         line = {
             "metric": "alignments_per_sec", "value": pairs_all / sec_step, "unit": "alignments/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_step * 1e3,
@@ -252,11 +271,19 @@ def main():
                     "host_buffers": "page-locked (wfacuda_host_alloc)", "pageable_value": pairs_all / wall_pageable},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": max((stats["pairs_lane"], "lane_kernel"), (stats["pairs_warp"], "align_kernel<warp>"), (stats["pairs_cta"], "align_kernel<cta>"))[1],
+            "roofline": {"bound": "hbm", "kernel": kname,
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(B),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(B),
                          "kernel_ms": ms_align / args.steps,
                          "cells_per_s": stats["cells"] / k_sec, "int32_ops_per_s_est": int_ops / k_sec},
+            # the second bound SURVEY 8(d) names: INT32 issue.  achieved = algorithmic integer ops
+            # (O = 32 C + 10 V + 8 W, V and W taken as C) per second of the align phase; peak = one
+            # 32-lane integer instruction per scheduler and clock at the SM clock sampled under load
+            "roofline_int32": {"bound": "int32-issue", "achieved": int_ops / k_sec / 1e12,
+                               "peak": sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "Tops/s",
+                               "frac": (int_ops / k_sec) / (sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                               "algorithmic_ops_per_launch": int(int_ops),
+                               "note": "executed warp instructions and issue-slot utilisation of the same kernel: profiles/r1_ncu_summary.md"},
             "device_ms_per_step": ms_dev / args.steps,
             "work": {"cells": int(stats["cells"]), "cells_written": int(stats["cells_written"]), "score_steps": int(stats["score_steps"]),
                      "ops": int(stats["ops"]), "retries": int(stats["retries"]), "pairs_lane": int(stats["pairs_lane"]), "pairs_warp": int(stats["pairs_warp"]),

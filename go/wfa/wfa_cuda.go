@@ -98,9 +98,19 @@ func (algn *Aligner) AlignBatch(qs, ts [][]byte) ([]*AlignmentResult, []error) {
 	for i := range qs {
 		total += len(qs[i]) + len(ts[i])
 	}
-	// One C-allocated byte pool + offset arrays: no Go pointer is retained by C
-	// after the call returns (cgo pointer rule); the library copies to pinned staging.
-	pool := make([]byte, 0, total+16)
+	// The byte pool lives in page-locked memory from the library (wfacuda_host_alloc): the DMA
+	// engine reads it directly instead of the library staging it through its own pinned buffers,
+	// and it is C memory, so no Go pointer is retained by C (cgo pointer rule).
+	poolPtr := C.wfacuda_host_alloc(C.size_t(total + 16))
+	if poolPtr == nil {
+		err := fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(nil)))
+		for i := range errs {
+			errs[i] = err
+		}
+		return results, errs
+	}
+	defer C.wfacuda_host_free(poolPtr)
+	pool := unsafe.Slice((*byte)(poolPtr), total+16)[:0]
 	qOff, tOff := make([]C.uint64_t, n), make([]C.uint64_t, n)
 	qLen, tLen := make([]C.uint32_t, n), make([]C.uint32_t, n)
 	for i := range qs {
@@ -134,7 +144,7 @@ func (algn *Aligner) AlignBatch(qs, ts [][]byte) ([]*AlignmentResult, []error) {
 		switch res[i].status {
 		case C.WFACUDA_OK:
 			r := NewAlignmentResult(algn.opt.GlobalAlignment) // pool, wfa_cigar.go:67-72
-			a := uint64(off[i])
+			a := uint64(off[i]) // pairs complete in any order on the GPU: off[i] is where pair i's ops landed
 			r.Ops = append(r.Ops[:0], ops[a:a+uint64(res[i].n_ops)]...) // already reversed + merged
 			r.Score = uint32(res[i].score)
 			r.TBegin, r.TEnd = int(res[i].tbegin), int(res[i].tend)

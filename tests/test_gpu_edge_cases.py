@@ -163,3 +163,34 @@ def test_config3_properties_at_scale(built_lib):
     sub_gpu = (res[:10_000], api.ops_in_index_order(res[:10_000], ops, off[:10_000]),
                np.concatenate([[0], np.cumsum(res["n_ops"][:10_000].astype(np.uint64))])[:-1].astype(np.uint64))
     parity.assert_same(sub, sub_gpu, ref, name + " prefix")
+
+
+def test_page_locked_buffers_and_ops_placement(built_lib):
+    """wfacuda_host_alloc: inputs in page-locked memory take the direct-DMA path (chunked pipeline
+    included) and give the same results as ordinary arrays; ops_off regions are disjoint, inside
+    the used prefix of the buffer, and hold each pair's ops whatever order pairs completed in."""
+    batch = datagen.generate(150_000, 150, 0.05, config=2)                  # > 2 chunks: pipelined path
+    a = parity.make_aligner()
+    try:
+        host = [api.pinned_copy(x) for x in (batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)]
+        r1, o1, off1 = a.align_arrays(*host, copy=True)
+        st = a.stats()
+        r2, o2, off2 = a.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len, copy=True)
+    finally:
+        a.close()
+    assert st["pairs_lane"] > 0 and st["h2d_bytes"] >= batch.seq_bytes.nbytes
+    for f in parity.FIELDS:
+        assert np.array_equal(r1[f], r2[f]), f
+    assert np.array_equal(parity.ops_in_index_order(r1, o1, off1), parity.ops_in_index_order(r2, o2, off2))
+    n_ops = r1["n_ops"].astype(np.int64)
+    order = np.argsort(off1, kind="stable")
+    ends = off1[order].astype(np.int64) + n_ops[order]
+    assert (ends[:-1] <= off1[order][1:].astype(np.int64)).all() and ends.max() <= len(o1)
+    sample = batch_slice(batch, 0, 3000)
+    ref = parity.oracle_batch(sample)
+    parity.assert_same(sample, (r1[:3000], o1, off1[:3000]), ref, "pinned e2e vs oracle")
+
+
+def batch_slice(batch, a, b):
+    pairs = [batch.pair(i) for i in range(a, b)]
+    return datagen.Batch.from_pairs(pairs)
