@@ -148,8 +148,10 @@ int ensure(wfacuda_ctx *ctx, DevBuf &b, size_t bytes)
     if (b.p) cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
     bytes = (bytes + 255) & ~(size_t)255;
+    const double t0 = now_ms();
     CU(ctx, cudaMalloc(&b.p, bytes));
     b.cap = bytes;
+    if (getenv("WFACUDA_DEBUG_ALLOC")) fprintf(stderr, "[wfacuda] ensure: cudaMalloc(%.1f MB) took %.2f ms\n", bytes / 1e6, now_ms() - t0);
     return 0;
 }
 
@@ -166,7 +168,9 @@ int dev_take(wfacuda_ctx *ctx, void **p, size_t *sz, size_t bytes)
         ctx->free_dev.erase(ctx->free_dev.begin() + best);
         return 0;
     }
+    const double t0 = now_ms();
     cudaError_t e = cudaMalloc(p, bytes);
+    if (getenv("WFACUDA_DEBUG_ALLOC")) fprintf(stderr, "[wfacuda] dev_take: cudaMalloc(%.1f MB) took %.2f ms (cache holds %zu)\n", bytes / 1e6, now_ms() - t0, ctx->free_dev.size());
     if (e != cudaSuccess) {
         /* drop the cache and retry once */
         for (auto &f : ctx->free_dev) cudaFree(f.first);
