@@ -68,6 +68,7 @@ struct KParams {
     const PairDesc *pairs;
     const uint32_t *work;      /* pair indices, decreasing cost */
     uint32_t        n_work;
+    uint32_t        pair_base; /* LANE kernels without a work list: item i is pair pair_base + i */
     const uint32_t *packed;    /* 2-bit pool */
     const uint32_t *raw;       /* byte pool viewed as words (base is 16-byte aligned) */
     const uint8_t  *pflags;    /* bit0: pair has a non-ACGT byte -> 8-bit path */
@@ -278,14 +279,14 @@ struct OpSink {
 __device__ __forceinline__ uint32_t op_of_type(uint32_t t)
 {
     /* wfaOps = ". I I D D X M H" (wfa_backtrace_types.go:37) */
-    return (uint32_t)(".IIDDXMH"[t & 7]);
+    return __byte_perm(0x4449492eu, 0x484d5844u, t & 7u) & 0xffu;     /* one PRMT instead of an indexed constant load */
 }
 
 /* backTrace, wfa.go:703-983, executed by one thread.  Returns ops (reversed
  * order, merged) in sink; fills score/begin/end of res. */
-template <class View>
-__device__ __noinline__ void back_trace(View &A, const KParams &P, int n, int m,
-                                        uint32_t s0, int Ak, Result &res, OpSink &sink)
+template <class View, class Sink>
+__device__ __forceinline__ void back_trace_inl(View &A, const KParams &P, int n, int m,
+                                               uint32_t s0, int Ak, Result &res, Sink &sink)
 {
     const bool semi = !P.global_aln;
     /* scores are carried as indices s/g: the reference's uint32 s-x etc. (wfa.go:760-762)
@@ -377,6 +378,14 @@ __device__ __noinline__ void back_trace(View &A, const KParams &P, int n, int m,
     if (h > 1) sink.add('I', (uint32_t)(h - 1));
     res.tbegin = tBegin; res.qbegin = qBegin;     /* :979 */
     sink.flush();
+}
+
+/* out-of-line copy for the WARP / CTA workers (their kernels are register-bound in the forward pass) */
+template <class View>
+__device__ __noinline__ void back_trace(View &A, const KParams &P, int n, int m,
+                                        uint32_t s0, int Ak, Result &res, OpSink &sink)
+{
+    back_trace_inl(A, P, n, m, s0, Ak, res, sink);
 }
 
 /* ------------------------------------------------------------------ explicit shared-memory access
@@ -805,10 +814,20 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
 /* ---------------- result of up to 32 pairs (lane j owns pair j): one ops-pool reservation per
  * group, process() (wfa_cigar.go:136-214) in one pass per lane, result records and work
  * counters.  `scratch` holds the lane's reversed, run-merged ops, `stride` words apart. */
+/* Work counters of a worker that handles many groups: added to the launch's Counters once, when
+ * the worker is done, instead of with same-address atomics per group. */
+struct WorkAcc { unsigned long long cells, written, steps, ops, arena_max; };
+
+struct ScratchOps {                /* j-th op as the backtrace produced it (reversed order) */
+    const uint64_t *scratch; uint32_t stride;
+    __device__ __forceinline__ uint64_t operator()(uint32_t j) const { return scratch[(size_t)j * stride]; }
+};
+
+template <class GetOp>
 __device__ __forceinline__ void group_emit(const KParams &P, const bool have, const uint32_t pair, int status, Result &res,
-                                           uint32_t n_ops, const uint64_t *scratch, const uint32_t stride,
+                                           uint32_t n_ops, const GetOp get_op,
                                            const unsigned long long arena_used, const unsigned long long c_cells,
-                                           const unsigned long long c_written, const unsigned long long c_steps)
+                                           const unsigned long long c_written, const unsigned long long c_steps, WorkAcc *acc = nullptr)
 {
     const int lane = threadIdx.x & 31;
     /* one pool reservation per group: exclusive scan of n_ops over the lanes */
@@ -827,7 +846,7 @@ __device__ __forceinline__ void group_emit(const KParams &P, const bool have, co
             unsigned a0 = 0, m0 = 0, g0 = 0, r0 = 0, a1 = 0, m1 = 0, g1 = 0, r1 = 0;
             bool seenM = false;
             for (uint32_t i = 0; i < n_ops; i++) {
-                const uint64_t op = scratch[(size_t)(n_ops - 1 - i) * stride];
+                const uint64_t op = get_op(n_ops - 1 - i);
                 if (P.ops_pool) P.ops_pool[base + i] = op;
                 const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
                 if (o == 'M' && !seenM) { seenM = true; a0 = alen; m0 = matches; g0 = gaps; r0 = regions; }
@@ -838,7 +857,7 @@ __device__ __forceinline__ void group_emit(const KParams &P, const bool have, co
             }
             if (seenM) { res.align_len = a1 - a0; res.matches = m1 - m0; res.gaps = g1 - g0; res.gap_regions = r1 - r0; }
             else if (n_ops) {                                      /* no M: begin = end = 0 (:170-186) */
-                const uint64_t op = scratch[(size_t)(n_ops - 1) * stride];
+                const uint64_t op = get_op(n_ops - 1);
                 const unsigned cnt = (unsigned)(op & 0xffffffffu), o = (unsigned)(op >> 32);
                 res.align_len = cnt; res.matches = 0;
                 res.gaps = (o == 'I' || o == 'D') ? cnt : 0; res.gap_regions = (o == 'I' || o == 'D') ? 1 : 0;
@@ -852,21 +871,24 @@ __device__ __forceinline__ void group_emit(const KParams &P, const bool have, co
         if (status != ST_OK) {
             const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
             P.retry[r] = (uint64_t)status << 32 | pair;
-        } else {
-            atomicMax(&P.ctr->arena_used_max, arena_used);
         }
         P.results[pair] = res;
     }
-    /* work counters: one atomic per group */
+    /* work counters: one set of atomics per group (a million same-address atomics per launch
+     * serialise in L2), or none at all when the worker accumulates them */
     unsigned long long c0 = (have && status == ST_OK) ? c_cells : 0, c1 = (have && status == ST_OK) ? c_written : 0;
     unsigned long long c2 = (have && status == ST_OK) ? c_steps : 0, c3 = (have && status == ST_OK) ? n_ops : 0;
+    unsigned long long c4 = (have && status == ST_OK) ? arena_used : 0;
     for (int d = 16; d > 0; d >>= 1) {
         c0 += __shfl_xor_sync(0xffffffffu, c0, d); c1 += __shfl_xor_sync(0xffffffffu, c1, d);
         c2 += __shfl_xor_sync(0xffffffffu, c2, d); c3 += __shfl_xor_sync(0xffffffffu, c3, d);
+        c4 = max(c4, __shfl_xor_sync(0xffffffffu, c4, d));
     }
-    if (lane == 0) {
+    if (acc) { acc->cells += c0; acc->written += c1; acc->steps += c2; acc->ops += c3; acc->arena_max = max(acc->arena_max, c4); }
+    else if (lane == 0) {
         atomicAdd(&P.ctr->cells, c0); atomicAdd(&P.ctr->cells_written, c1);
         atomicAdd(&P.ctr->steps, c2); atomicAdd(&P.ctr->ops, c3);
+        if (c4) atomicMax(&P.ctr->arena_used_max, c4);
     }
     __syncwarp();
 }
@@ -899,7 +921,7 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
         if (sink.overflow) { status = ST_ARENA; n_ops = 0; }
     }
     __syncwarp();
-    group_emit(P, have, pair, status, res, n_ops, scratch, 1u,
+    group_emit(P, have, pair, status, res, n_ops, ScratchOps{scratch, 1u},
                (unsigned long long)((slot_words - top + scratch_w) * 4 + 8ull * n_ops), f.c_cells, f.c_written, f.c_steps);
 }
 

@@ -46,12 +46,57 @@ constexpr int LANE_MAX_LEN = 254;           /* offsets up to m+1 must fit a byte
 #endif
 
 constexpr int LANE_HDR_ROWS = 64;            /* scores (in units of g) a group may reach; beyond: WARP worker */
+/* A group's slot starts with what the forward kernel leaves for the finish kernel (words):
+ *   [0, 128)    row headers int2[LANE_HDR_ROWS]: {lo | hi << 16 (both + 0x4000), first word of the row}
+ *   [128, 384)  per-pair records, word j of lane l at 128 + 32 j + l:
+ *               0 status | first_eq << 8 | final score index << 16, 1 final score, 2 C, 3 cells written, 4 score steps, 5 top
+ *   [384, ...)  op scratch of the backtrace, then free space, then the rows (growing down from the end) */
+constexpr uint32_t LANE_REC_W = 128, LANE_SCRATCH_W = 384;
+constexpr int LANE_FINISH_WARPS = 4;
+constexpr uint32_t LANE_SOPS = 32;           /* ops per pair kept in shared memory by the finish kernel (16 bits each); more go to the slot */
+
+/* Op sink of the finish kernel: the first LANE_SOPS run-merged ops of a pair stay in shared
+ * memory as letter index << 13 | count (counts <= n + m < 8192 in the LANE class), the rest go
+ * to the group's slot like OpSink's. */
+struct LaneSink {
+    uint16_t *sbuf;                /* shared memory, [op][lane], already offset by the lane */
+    uint64_t *buf; uint32_t cap, n; uint32_t cur_op, cur_n; bool overflow;
+    __device__ __forceinline__ void add(uint32_t op, uint32_t cnt)
+    {
+        if (op == cur_op) { cur_n += cnt; return; }
+        flush();
+        cur_op = op; cur_n = cnt;
+    }
+    __device__ __forceinline__ void flush()
+    {
+        if (cur_op == 0) return;
+        if (n < LANE_SOPS) {
+            /* 'D' 44, 'H' 48, 'I' 49, 'M' 4d, 'X' 58 -> 0..4 */
+            const uint32_t c = cur_op == 'M' ? 3u : (cur_op == 'X' ? 4u : (cur_op == 'I' ? 2u : (cur_op == 'H' ? 1u : 0u)));
+            sbuf[n * 32u] = (uint16_t)(c << 13 | cur_n);
+        } else if (n - LANE_SOPS < cap) buf[(size_t)(n - LANE_SOPS) * 32u] = (uint64_t)cur_op << 32 | cur_n;
+        else overflow = true;
+        n++;
+        cur_op = 0;
+    }
+};
+struct LaneOps {
+    const uint16_t *sbuf; const uint64_t *buf;
+    __device__ __forceinline__ uint64_t operator()(uint32_t j) const
+    {
+        if (j < LANE_SOPS) {
+            const uint32_t w = sbuf[j * 32u];
+            const uint32_t letter = __byte_perm(0x4d494844u, 0x00000058u, w >> 13) & 0xffu;
+            return (uint64_t)letter << 32 | (w & 0x1fffu);
+        }
+        return buf[(size_t)(j - LANE_SOPS) * 32u];
+    }
+};
 
 /* dM, dE as in KParams (max(x,o+e)/g+1, e/g+1); W ring columns; SW words per sequence */
 __host__ __device__ inline size_t lane_smem_bytes(int dM, int dE, int W, int SW)
 {
     size_t b = (((size_t)dM * 8) + 15) & ~(size_t)15;                 /* meta int2[] */
-    b += (size_t)LANE_HDR_ROWS * 8;                                    /* row headers int2[] */
     b += 2 * (size_t)SW * 128;                                         /* seqQ, seqT */
     b += ((size_t)(dM - 1) + 2 * (size_t)(dE - 1)) * (size_t)W * 32;   /* rings (in place: one row less than the WARP worker) */
     return (b + 127) & ~(size_t)127;
@@ -217,9 +262,10 @@ __device__ __forceinline__ uint32_t lane_extend(uint32_t sQ, uint32_t sT, uint32
     return M + (uint32_t)min(l, ext);
 }
 
-/* Forward pass + backtrace of one group of up to 32 pairs. */
-__device__ __noinline__ void lane_group(const KParams &P, const bool have, const uint32_t pair, unsigned char *smem,
-                                        uint8_t *slot, const uint64_t slot_bytes)
+/* Forward pass of one group of up to 32 pairs: rows, row headers and the per-pair records go
+ * to the group's slot; lane_finish_kernel runs the backtraces. */
+__device__ __forceinline__ void lane_forward(const KParams &P, const bool have, const uint32_t pair, unsigned char *smem,
+                                          uint8_t *slot, const uint64_t slot_bytes)
 {
     const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -230,8 +276,8 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     const int xg = P.xg, oeg = P.oeg, x = (int)P.x;
 
     int2 *meta = reinterpret_cast<int2 *>(smem);
-    int2 *hdrs = reinterpret_cast<int2 *>(smem + ((((size_t)P.dM * 8) + 15) & ~(size_t)15));
-    unsigned char *p = reinterpret_cast<unsigned char *>(hdrs + LANE_HDR_ROWS);
+    int2 *hdrs = reinterpret_cast<int2 *>(slot);                       /* global: read by the finish kernel */
+    unsigned char *p = smem + ((((size_t)P.dM * 8) + 15) & ~(size_t)15);
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)lane * 4u;
     const uint32_t sT = sQ + (uint32_t)SW * 128u;
     const uint32_t rowB = (uint32_t)W * 32u;
@@ -277,7 +323,7 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
     const uint32_t slot_words = (uint32_t)min((uint64_t)0xfffffff0u, slot_bytes >> 2);
     uint32_t top = slot_words;
-    const uint32_t hdr_limit = 64 * 32;                /* the slot starts with the op scratch: room for 32 ops per pair at least */
+    const uint32_t hdr_limit = LANE_SCRATCH_W + 64 * 32;   /* headers, records, then the op scratch: room for 32 ops per pair at least */
 
     uint32_t s = 0; int si = 0, cur = 0, curE = 0;
     bool done = false; uint32_t minS = 0; int my_si = 0;
@@ -427,8 +473,34 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     }
     if (act && !done) status = group_fail ? group_fail : ST_ARENA;
 
-    /* ---------------- backtrace (wfa.go:703-983), lane-parallel, then the group's results */
-    const uint32_t scratch_w = 0;
+    /* what the finish kernel needs of this pair */
+    uint32_t *rec = cells + LANE_REC_W + lane;
+    rec[0] = (uint32_t)status | (first_eq ? 0x100u : 0u) | (uint32_t)my_si << 16;
+    rec[32] = minS; rec[64] = c_cells; rec[96] = c_written; rec[128] = c_steps; rec[160] = top;
+}
+
+/* Backtraces (wfa.go:703-983) of one group, lane-parallel, then the group's results. */
+__device__ __forceinline__ void lane_finish(const KParams &P, const bool have, const uint32_t pair, int2 *hdrs, uint16_t *sops,
+                                            uint8_t *slot, const uint64_t slot_bytes, WorkAcc *acc)
+{
+    const uint32_t FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
+    const uint32_t slot_words = (uint32_t)min((uint64_t)0xfffffff0u, slot_bytes >> 2);
+    {
+        const int4 *g = reinterpret_cast<const int4 *>(slot);           /* 64 headers = 32 x 16 bytes */
+        reinterpret_cast<int4 *>(hdrs)[lane] = g[lane];
+    }
+    const uint32_t *rec = cells + LANE_REC_W + lane;
+    const uint32_t r0 = rec[0], minS = rec[32], c_cells = rec[64], c_written = rec[96], c_steps = rec[128], top = rec[160];
+    int status = (int)(r0 & 255u);
+    const bool first_eq = (r0 & 0x100u) != 0u;
+    const int my_si = (int)(r0 >> 16);
+    int n = 0, m = 0;
+    if (status == ST_OK) { const PairDesc pd = P.pairs[pair]; n = (int)pd.n; m = (int)pd.m; }
+    const int Ak = m - n;
+
+    const uint32_t scratch_w = LANE_SCRATCH_W;
     uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w) + lane;
     Result res;
     res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
@@ -436,22 +508,21 @@ __device__ __noinline__ void lane_group(const KParams &P, const bool have, const
     res.status = (uint8_t)status; res.pad_[0] = res.pad_[1] = res.pad_[2] = 0;
     uint32_t n_ops = 0;
     __syncwarp();
-    __threadfence_block();
     if (status == ST_OK) {
         LaneView A; A.hdr = hdrs; A.cells = cells + lane; A.si_last = my_si; A.c_si = -1; A.c_k = 0;
         A.c_w[0] = A.c_w[1] = A.c_w[2] = A.c_w[3] = A.c_w[4] = 0;
         A.n = n; A.m = m; A.xg = P.xg; A.oeg = P.oeg; A.eg = P.eg; A.first_eq = first_eq;
-        OpSink sink; sink.buf = scratch; sink.stride = 32;
+        LaneSink sink; sink.sbuf = sops + lane; sink.buf = scratch;
         sink.cap = top > scratch_w ? (top - scratch_w) / 64u : 0u;
         sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
-        back_trace(A, P, n, m, minS, Ak, res, sink);
+        back_trace_inl(A, P, n, m, minS, Ak, res, sink);
         n_ops = sink.n;
         if (sink.overflow) { status = ST_ARENA; n_ops = 0; }
     }
     __syncwarp();
     const uint32_t max_ops = __reduce_max_sync(FULL, n_ops);
-    group_emit(P, have, pair, status, res, n_ops, scratch, 32u,
-               (unsigned long long)(slot_words - top + scratch_w) * 4ull + 256ull * max_ops, c_cells, c_written, c_steps);
+    group_emit(P, have, pair, status, res, n_ops, LaneOps{sops + lane, scratch},
+               (unsigned long long)(slot_words - top + scratch_w) * 4ull + 256ull * (max_ops > LANE_SOPS ? max_ops - LANE_SOPS : 0u), c_cells, c_written, c_steps, acc);
 }
 
 __global__ void __launch_bounds__(32 * WFA_LANE_WARPS)
@@ -460,8 +531,6 @@ lane_kernel(const KParams P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wib = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     unsigned char *smem = smem_raw + (size_t)wib * lane_smem_bytes(P.dM, P.dE, P.ring_cap, P.group);
-    const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    uint8_t *slot = P.arena + worker * P.slot_bytes;
     if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(&P.ctr->t_first, t); }
     for (;;) {
         uint32_t first = 0;
@@ -469,8 +538,33 @@ lane_kernel(const KParams P)
         first = __shfl_sync(0xffffffffu, first, 0);
         if (first >= P.n_work) break;
         const bool have = first + lane < P.n_work;
-        const uint32_t pair = have ? (P.work ? P.work[first + lane] : first + lane) : 0u;
-        lane_group(P, have, pair, smem, slot, P.slot_bytes);
+        const uint32_t pair = have ? (P.work ? P.work[first + lane] : P.pair_base + first + lane) : 0u;
+        lane_forward(P, have, pair, smem, P.arena + (uint64_t)(first >> 5) * P.slot_bytes, P.slot_bytes);   /* one slot per group */
+    }
+    if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(&P.ctr->t_last, t); }
+}
+
+/* One warp per group, many warps per SM: the backtrace is a chain of dependent arena reads, so
+ * it runs here at full occupancy instead of inside the shared-memory-limited forward kernel. */
+__global__ void __launch_bounds__(32 * LANE_FINISH_WARPS, 10)
+lane_finish_kernel(const KParams P)
+{
+    __shared__ __align__(16) int2 hdr_s[LANE_FINISH_WARPS][LANE_HDR_ROWS];
+    __shared__ uint16_t ops_s[LANE_FINISH_WARPS][LANE_SOPS * 32];
+    const int wib = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const uint32_t n_groups = (P.n_work + 31u) >> 5;
+    WorkAcc acc; acc.cells = acc.written = acc.steps = acc.ops = acc.arena_max = 0;
+    for (uint32_t g = blockIdx.x * LANE_FINISH_WARPS + wib; g < n_groups; g += gridDim.x * LANE_FINISH_WARPS) {
+        const uint32_t first = g << 5;
+        const bool have = first + lane < P.n_work;
+        const uint32_t pair = have ? (P.work ? P.work[first + lane] : P.pair_base + first + lane) : 0u;
+        __syncwarp();
+        lane_finish(P, have, pair, hdr_s[wib], ops_s[wib], P.arena + (uint64_t)g * P.slot_bytes, P.slot_bytes, &acc);
+    }
+    if (lane == 0) {
+        atomicAdd(&P.ctr->cells, acc.cells); atomicAdd(&P.ctr->cells_written, acc.written);
+        atomicAdd(&P.ctr->steps, acc.steps); atomicAdd(&P.ctr->ops, acc.ops);
+        if (acc.arena_max) atomicMax(&P.ctr->arena_used_max, acc.arena_max);
     }
     if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(&P.ctr->t_last, t); }
 }

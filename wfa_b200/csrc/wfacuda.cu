@@ -544,37 +544,47 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         const size_t sample = std::min<size_t>(order.size(), 4096);
         for (size_t i = 0; i < sample; i++) need = std::max(need, estimate_lane(ctx, b->descs[order[i]].n, b->descs[order[i]].m));
         uint64_t slot = ((uint64_t)((double)std::max<uint64_t>(need, 65536) * boost) + 255) & ~255ull;
+        /* one slot per GROUP (the finish kernel reads what the forward kernel left); when the
+         * arena budget does not hold all groups the class runs in rounds of as many groups as fit */
         const uint64_t groups = (order.size() + 31) / 32;
-        uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ) * WFA_LANE_WARPS;
-        workers = std::min<uint64_t>(workers, ((groups + WFA_LANE_WARPS - 1) / WFA_LANE_WARPS) * WFA_LANE_WARPS);
         const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
         bool slot_at_max = false;
-        if (slot * workers > budget) workers = std::max<uint64_t>(WFA_LANE_WARPS, (budget / slot) / WFA_LANE_WARPS * WFA_LANE_WARPS);
-        if (slot * workers > budget) { slot = (budget / workers) & ~255ull; slot_at_max = true; }
+        uint64_t round_groups = std::min<uint64_t>(groups, std::max<uint64_t>(1, budget / slot));
+        if (slot > budget) { slot = budget & ~255ull; slot_at_max = true; }
         slot = std::min<uint64_t>(slot, 15ull << 30);
+        uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ) * WFA_LANE_WARPS;
         int rc;
-        if ((rc = ensure(ctx, ctx->arena, slot * workers))) return rc;
+        if ((rc = ensure(ctx, ctx->arena, slot * round_groups))) return rc;
         if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         Counters *dc = (Counters *)ctx->ctr.p;
         CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->t_first, 0xff, 8, ctx->stream));
         CU(ctx, cudaMemsetAsync(&dc->t_last, 0, 8, ctx->stream));
-        KParams P = base;
-        P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
-        P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = sw;      /* LANE kernel: group = words per sequence */
-        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
-        P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
-        const int blocks = (int)(workers / WFA_LANE_WARPS);
         const double tl0 = now_ms();
-        lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P);
-        CU(ctx, cudaGetLastError());
+        int blocks = 0;
+        for (uint64_t g0 = 0; g0 < groups; g0 += round_groups) {
+            const uint64_t g1 = std::min(groups, g0 + round_groups);
+            const uint64_t p0 = g0 * 32, p1 = std::min<uint64_t>(order.size(), g1 * 32);
+            CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
+            KParams P = base;
+            P.work = ident ? nullptr : (const uint32_t *)ctx->work.p + p0; P.pair_base = (uint32_t)p0; P.n_work = (uint32_t)(p1 - p0);
+            P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = sw;      /* LANE kernel: group = words per sequence */
+            P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
+            P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+            const uint64_t w = std::min<uint64_t>(workers, ((g1 - g0 + WFA_LANE_WARPS - 1) / WFA_LANE_WARPS) * WFA_LANE_WARPS);
+            blocks = (int)(w / WFA_LANE_WARPS);
+            lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P);
+            CU(ctx, cudaGetLastError());
+            const int fblocks = (int)std::min<uint64_t>((g1 - g0 + LANE_FINISH_WARPS - 1) / LANE_FINISH_WARPS, (uint64_t)ctx->sm_count * 16);
+            lane_finish_kernel<<<fblocks, 32 * LANE_FINISH_WARPS, 0, ctx->stream>>>(P);
+            CU(ctx, cudaGetLastError());
+            ctx->stats.kernel_launches += 2; ctx->stats.align_launches++;
+        }
         const double tl1 = now_ms();
-        ctx->stats.kernel_launches++; ctx->stats.align_launches++;
-        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, slot * workers);
+        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, slot * round_groups);
         Counters hc;
         { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   lane kernel: host launch at %.2f (took %.2f), sync returned %.2f ms since call; device span %.3f ms, device end = host %+.3f\n", tl0 - g_dbg_t0, tl1 - tl0, now_ms() - g_dbg_t0, (hc.t_last - hc.t_first) / 1e6, fmod(now_ms(), 1000.0) - (hc.t_last % 1000000000ull) / 1e6);
@@ -598,7 +608,7 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         ctx->stats.retries += (uint32_t)again.size();
         if (ops_full && (rc = grow_ops_pool(ctx, hc.ops_cursor))) return rc;
         if (arena_full) {
-            if (slot_at_max && workers <= (uint64_t)WFA_LANE_WARPS) {
+            if (slot_at_max) {
                 /* the whole budget is not enough for one group: let the WARP class place them */
                 std::vector<uint32_t> keep;
                 for (uint64_t r : rl) {
