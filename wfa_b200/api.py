@@ -331,7 +331,16 @@ class Aligner:
         seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
         q_off = np.ascontiguousarray(q_off, np.uint64); t_off = np.ascontiguousarray(t_off, np.uint64)
         q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
-        cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64 if want_ops else 0
+        # ops capacity: the buffers kept from the previous call when there are any (the library
+        # reports E_OPS_CAPACITY with the exact need otherwise), else 1/4 op per base -- summing
+        # two million-entry length arrays in every call costs more than a tenth of config 2's call
+        bufs = getattr(self, "_bufs", None)
+        if not want_ops:
+            cap = 0
+        elif bufs is not None and len(bufs[0]) >= n:
+            cap = len(bufs[2])
+        else:
+            cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64
         while True:
             results, ops_off, ops = self._out_buffers(n, cap)
             rc = self._L.wfacuda_align_batch(self._ctx, n, seq_bytes.ctypes.data, q_off.ctypes.data, q_len.ctypes.data,

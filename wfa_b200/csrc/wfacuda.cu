@@ -84,6 +84,16 @@ struct wfacuda_ctx {
         void release() { { std::lock_guard<std::mutex> lk(mu); free_slots++; } cv.notify_one(); }
     } h2d_turns;                       /* owned by the parent ctx; one copy at a time measured best (WFACUDA_H2D_TURNS) */
     Turns *h2d_turn = nullptr;         /* set in a worker ctx: the parent's semaphore */
+    /* The pipeline workers' sequence uploads all go through ONE stream of the parent ctx: copies
+     * queued on one stream run back to back in FIFO order with no host round trip between them
+     * (the semaphore above left ~50 us of PCIe idle per chunk: sync wake-up, hand-over, launch);
+     * the worker's own stream waits for its copy through an event. */
+    cudaStream_t h2d_fifo = nullptr;   /* parent: the shared upload stream */
+    std::mutex h2d_mu;                 /* parent: serialises the enqueue + event record */
+    wfacuda_ctx *h2d_parent = nullptr; /* worker: whose h2d_fifo to use */
+    cudaEvent_t ev_h2d = nullptr;      /* worker: completion of its chunk's sequence upload */
+    PairDesc *pin_descs = nullptr; size_t pin_descs_cap = 0;   /* worker: page-locked descriptors, DMA'd without a staging copy */
+    const wfacuda_batch *pin_descs_owner = nullptr;
 };
 
 struct wfacuda_batch {
@@ -92,7 +102,8 @@ struct wfacuda_batch {
     std::vector<uint32_t> order_warp, order_cta, order_lane;
     int identity_cls = -1;                  /* class (0 warp, 1 cta, 2 lane) whose order is 0..n-1: no work list needed */
     uint32_t lane_maxlen = 1;               /* longest sequence of the LANE class */
-    std::vector<PairDesc> descs;
+    PairDesc *descs = nullptr;              /* descs_own's storage, or the ctx's page-locked descriptor buffer (pipeline workers) */
+    std::vector<PairDesc> descs_own;
     uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
     void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
     void *d_results = nullptr, *d_where = nullptr;
@@ -121,6 +132,31 @@ int fail(wfacuda_ctx *ctx, int code, const char *fmt, ...)
     } while (0)
 
 double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
+
+
+/* Device fills run as kernels, not cudaMemsetAsync: a memset may be executed by a copy engine,
+ * where it queues behind every upload the pipeline workers have in flight. */
+__global__ void fill_kernel(uint4 *p16, size_t n16, unsigned char *p1, size_t n1, unsigned int byte)
+{
+    const unsigned int w = byte * 0x01010101u;
+    const uint4 v = make_uint4(w, w, w, w);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p16[i] = v;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n1; i += (size_t)gridDim.x * blockDim.x) p1[i] = (unsigned char)byte;
+}
+cudaError_t dev_fill(void *p, int byte, size_t bytes, cudaStream_t stream)
+{
+    if (!bytes) return cudaSuccess;
+    unsigned char *c = (unsigned char *)p;
+    size_t head = (16 - ((uintptr_t)c & 15)) & 15; if (head > bytes) head = bytes;
+    /* bytes before the first 16-byte boundary and after the last one go through the byte loop */
+    const size_t n16 = (bytes - head) / 16, tail = bytes - head - n16 * 16;
+    if (head) fill_kernel<<<1, 32, 0, stream>>>(nullptr, 0, c, head, (unsigned int)(byte & 255));
+    if (n16 || tail) {
+        const int blocks = (int)std::min<size_t>(std::max<size_t>((n16 + 255) / 256, 1), 1184);
+        fill_kernel<<<blocks, 256, 0, stream>>>((uint4 *)(c + head), n16, c + head + n16 * 16, tail, (unsigned int)(byte & 255));
+    }
+    return cudaGetLastError();
+}
 
 uint32_t gcd_u32(uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; }
 
@@ -390,9 +426,9 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         /* reset queue + retry counters, keep the work counters and the ops cursor */
         Counters *dc = (Counters *)ctx->ctr.p;
-        CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->retry_n, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->work_next, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->arena_used_max, 0, 8, ctx->stream));
         KParams P = base;
         P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
@@ -559,16 +595,16 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         Counters *dc = (Counters *)ctx->ctr.p;
-        CU(ctx, cudaMemsetAsync(&dc->retry_n, 0, 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(&dc->arena_used_max, 0, 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(&dc->t_first, 0xff, 8, ctx->stream));
-        CU(ctx, cudaMemsetAsync(&dc->t_last, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->retry_n, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->arena_used_max, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->t_first, 0xff, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->t_last, 0, 8, ctx->stream));
         const double tl0 = now_ms();
         int blocks = 0;
         for (uint64_t g0 = 0; g0 < groups; g0 += round_groups) {
             const uint64_t g1 = std::min(groups, g0 + round_groups);
             const uint64_t p0 = g0 * 32, p1 = std::min<uint64_t>(order.size(), g1 * 32);
-            CU(ctx, cudaMemsetAsync(&dc->work_next, 0, 8, ctx->stream));
+            CU(ctx, dev_fill(&dc->work_next, 0, 8, ctx->stream));
             KParams P = base;
             P.work = ident ? nullptr : (const uint32_t *)ctx->work.p + p0; P.pair_base = (uint32_t)p0; P.n_work = (uint32_t)(p1 - p0);
             P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = sw;      /* LANE kernel: group = words per sequence */
@@ -710,6 +746,9 @@ void wfacuda_destroy(wfacuda_ctx *ctx)
     for (auto &f : ctx->free_dev) cudaFree(f.first);
     for (int i = 0; i < 2; i++) { if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]); if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]); }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
+    if (ctx->pin_descs) cudaFreeHost(ctx->pin_descs);
+    if (ctx->h2d_fifo) { cudaStreamSynchronize(ctx->h2d_fifo); cudaStreamDestroy(ctx->h2d_fifo); }
     if (ctx->stream_main) cudaStreamDestroy(ctx->stream_main);
     if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
     delete ctx;
@@ -774,6 +813,7 @@ void wfacuda_batch_free(wfacuda_ctx *ctx, wfacuda_batch *b)
         dev_give(ctx, &b->d_descs, &b->sz_descs); dev_give(ctx, &b->d_flags, &b->sz_flags);
         dev_give(ctx, &b->d_results, &b->sz_results); dev_give(ctx, &b->d_where, &b->sz_where);
         if (ctx->pool_owner == b) ctx->pool_owner = nullptr;
+        if (ctx->pin_descs_owner == b) ctx->pin_descs_owner = nullptr;
     }
     delete b;
 }
@@ -789,8 +829,22 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
     wfacuda_batch *b = new wfacuda_batch();
     b->n_pairs = n_pairs;
     b->host_status.assign(n_pairs, ST_PENDING);
-    b->descs.resize(n_pairs);
     const bool dbg = getenv("WFACUDA_DEBUG") != nullptr;
+    /* pipeline worker with page-locked caller memory: sequence bytes and descriptors go through
+     * the parent's FIFO upload stream */
+    const bool fifo = ctx->h2d_parent && ctx->h2d_parent->h2d_fifo && n_pairs && is_pinned(seq_bytes) &&
+                      ctx->pin_descs_owner == nullptr && !getenv("WFACUDA_NO_FIFO");
+    if (fifo) {
+        if (ctx->pin_descs_cap < n_pairs) {
+            if (ctx->pin_descs) cudaFreeHost(ctx->pin_descs);
+            ctx->pin_descs = nullptr; ctx->pin_descs_cap = 0;
+            if (cudaHostAlloc((void **)&ctx->pin_descs, (n_pairs + n_pairs / 8) * sizeof(PairDesc), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError(); fail(ctx, WFACUDA_E_NOMEM, "page-locked descriptor buffer allocation failed"); delete b; return nullptr;
+            }
+            ctx->pin_descs_cap = n_pairs + n_pairs / 8;
+        }
+        b->descs = ctx->pin_descs; ctx->pin_descs_owner = b;
+    } else { b->descs_own.resize(n_pairs); b->descs = b->descs_own.data(); }
     auto body = [&]() -> int {
         const double t0 = now_ms();
         ctx->stats = wfacuda_stats{};
@@ -824,17 +878,27 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         if ((rc = dev_take(ctx, &b->d_flags, &b->sz_flags, n_pairs + 16))) return rc;
         if ((rc = dev_take(ctx, &b->d_results, &b->sz_results, n_pairs * sizeof(Result)))) return rc;
         if ((rc = dev_take(ctx, &b->d_where, &b->sz_where, n_pairs * 8))) return rc;
-        if (b->raw_bytes) {
+        if (fifo) {
+            /* descriptors first, then the sequence bytes, queued together: the copy engine serves
+             * copies in the order they were issued, whatever stream they are on */
+            wfacuda_ctx *par = ctx->h2d_parent;
+            ctx->h2d_turn->acquire();            /* bounded queue depth: released when this chunk's copies are done */
+            std::lock_guard<std::mutex> lk(par->h2d_mu);
+            CU(ctx, cudaMemcpyAsync(b->d_descs, b->descs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
+            if (b->raw_bytes) CU(ctx, cudaMemcpyAsync(b->d_raw, seq_bytes + base, b->raw_bytes, cudaMemcpyHostToDevice, par->h2d_fifo));
+            CU(ctx, cudaEventRecord(ctx->ev_h2d, par->h2d_fifo));
+            ctx->stats.h2d_bytes += b->raw_bytes + n_pairs * sizeof(PairDesc);
+        } else if (b->raw_bytes) {
             if (ctx->h2d_turn && b->raw_bytes >= 65536 && is_pinned(seq_bytes + base)) {
                 struct Turn { wfacuda_ctx::Turns *t; Turn(wfacuda_ctx::Turns *t_) : t(t_) { t->acquire(); } ~Turn() { t->release(); } } turn(ctx->h2d_turn);
                 CU(ctx, cudaMemcpyAsync(b->d_raw, seq_bytes + base, b->raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
                 CU(ctx, cudaStreamSynchronize(ctx->stream));
                 ctx->stats.h2d_bytes += b->raw_bytes;
             } else if ((rc = staged_h2d(ctx, b->d_raw, seq_bytes + base, b->raw_bytes))) return rc;
-            CU(ctx, cudaMemsetAsync((char *)b->d_raw + b->raw_bytes, 0, 64, ctx->stream));
         }
+        if (b->raw_bytes) CU(ctx, dev_fill((char *)b->d_raw + b->raw_bytes, 0, 64, ctx->stream));
         const double t2 = now_ms();
-        if (n_pairs) if ((rc = staged_h2d(ctx, b->d_descs, b->descs.data(), n_pairs * sizeof(PairDesc)))) return rc;
+        if (n_pairs && !fifo) if ((rc = staged_h2d(ctx, b->d_descs, b->descs, n_pairs * sizeof(PairDesc)))) return rc;
         const double t3 = now_ms();
         /* cost bins: longest first (counting sort on half-octave buckets of n+m).  A pair goes to
          * the CTA class when its wavefront cannot fit the widest shared-memory ring: width is
@@ -887,6 +951,10 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             }
         }
         const double t4 = now_ms();
+        /* FIFO uploads: host-side wait for this chunk's copies (kernels queued behind a device-side
+         * event wait were seen to hold up the other workers' streams -- streams share hardware
+         * queues); the copies queued behind these are not affected by when this thread wakes up */
+        if (fifo) { const cudaError_t e = cudaEventSynchronize(ctx->ev_h2d); ctx->h2d_turn->release(); CU(ctx, e); }
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (dbg) fprintf(stderr, "[wfacuda] upload: validate+descs %.2f ms, alloc+seq h2d %.2f, descs h2d %.2f, binning %.2f, sync %.2f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now_ms() - t4);
         return 0;
@@ -914,9 +982,9 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     int rc;
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    CU(ctx, cudaMemsetAsync(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
-    CU(ctx, cudaMemsetAsync(b->d_flags, 0, b->sz_flags, ctx->stream));
-    if (n) CU(ctx, cudaMemsetAsync(b->d_where, 0, n * 8, ctx->stream));
+    CU(ctx, dev_fill(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
+    CU(ctx, dev_fill(b->d_flags, 0, b->sz_flags, ctx->stream));
+    if (n) CU(ctx, dev_fill(b->d_where, 0, n * 8, ctx->stream));
     /* results start as PENDING, or as the host-side verdict (EMPTY / TOO_LONG) */
     if (b->n_invalid) {
         std::vector<Result> init(n);
@@ -924,7 +992,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
         for (uint64_t i = 0; i < n; i++) init[i].status = b->host_status[i];
         if ((rc = staged_h2d(ctx, b->d_results, init.data(), n * sizeof(Result)))) return rc;
         CU(ctx, cudaStreamSynchronize(ctx->stream));     /* init goes out of scope */
-    } else if (n) CU(ctx, cudaMemsetAsync(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
+    } else if (n) CU(ctx, dev_fill(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
     const uint64_t n_valid = b->order_warp.size() + b->order_cta.size() + b->order_lane.size();
     if (n_valid) {
         const int pack_blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);      /* one warp per pair */
@@ -1094,8 +1162,14 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         wfacuda_ctx *sub = wfacuda_create(ctx->device, &c);
         if (!sub) return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: %s", g_tls_error.c_str());
         sub->h2d_turn = &ctx->h2d_turns;
+        sub->h2d_parent = ctx;
+        if (cudaEventCreateWithFlags(&sub->ev_h2d, cudaEventDisableTiming) != cudaSuccess) { wfacuda_destroy(sub); return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: event creation failed"); }
         ctx->subs.push_back(sub);
     }
+    if (!ctx->h2d_fifo && cudaStreamCreateWithFlags(&ctx->h2d_fifo, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->h2d_fifo = nullptr; }
+    /* uploads in flight: with the shared FIFO stream two keep the copy engine fed back to back
+     * (the next copy is already queued when one completes) without letting chunks arrive late */
+    ctx->h2d_turns.free_slots = ctx->h2d_fifo && !getenv("WFACUDA_NO_FIFO") ? 2 : 1;
     if (const char *e = getenv("WFACUDA_H2D_TURNS")) ctx->h2d_turns.free_slots = std::max(1, atoi(e));
     std::atomic<uint64_t> next{0}, cursor{0};
     std::atomic<int> first_err{0};
