@@ -115,6 +115,18 @@ def test_tiny_arena_budget_requeues_then_reports_resources(built_lib):
     assert np.array_equal(res["score"][:-1], ref[0]["score"][:-1])
 
 
+def test_lane_class_in_rounds_when_arena_is_small(built_lib):
+    """The LANE class keeps one arena slot per group of 32 pairs until its finish kernel has
+    run; a budget that holds only a few dozen slots makes it work through the batch in rounds
+    (forward + finish kernel per round), with the same results."""
+    batch = datagen.generate(6000, 150, 0.05, config=2)
+    gpu, ref, stats = parity.check(batch, what="lane rounds", gpu_kw=dict(arena_budget_bytes=4 << 20))
+    assert stats["pairs_lane"] > 5900 and stats["align_launches"] >= 3, stats
+    assert stats["cells"] == ref[3]["cells"]
+    full = parity.check(batch, what="lane one round")[2]
+    assert full["align_launches"] < stats["align_launches"]
+
+
 def _cigar_properties(batch, res, ops, off, penalties=(4, 6, 2)):
     """Size-independent checks: every CIGAR consumes exactly its query and target, and in
     global mode its gap-affine cost is the reported score."""

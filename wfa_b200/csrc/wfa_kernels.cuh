@@ -86,6 +86,7 @@ struct KParams {
     int32_t  dM, dE;           /* ring depths: max(xg,oeg)+1, eg+1 */
     int32_t  ring_cap;         /* diagonals per ring row (WARP kernel) */
     int32_t  group;            /* WARP kernel: pairs per group (1..32), slot_bytes = group * sub-slot */
+    int32_t  seq_cap;          /* WARP kernel: 32-bit words of shared memory per warp for the pair's 2-bit sequences (0: read them from global) */
     uint8_t  global_aln, adaptive, semi_literal, pad8_;
     int32_t  min_wf_len, max_dist_diff;
 };
@@ -95,26 +96,31 @@ struct KParams {
  * (byte>>1)&3 (A=0 C=1 T=2 G=3), only used when every byte of the pair is one
  * of "ACGT" so that code equality == byte equality (wfa.go:408-454 compares
  * raw bytes).  8-bit mode reads the caller's bytes unchanged. */
-template <int BITS> struct SeqView {
+template <int BITS, bool SM = false> struct SeqView {
     const uint32_t *w;   /* word holding symbol 0 (aligned down) */
     uint32_t        mis; /* symbols before symbol 0 inside that word (8-bit mode only) */
+    uint32_t        sa;  /* SM: shared-window byte address of word 0 (the WARP worker's copy of a short sequence) */
     static constexpr int PER_WORD = 32 / BITS;
+    __device__ __forceinline__ uint32_t word(uint32_t wi) const {
+        if (SM) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa + wi * 4u)); return v; }
+        return __ldg(w + wi);
+    }
     __device__ __forceinline__ uint32_t sym(int i) const {
         uint32_t j = (uint32_t)i + mis;
-        return (__ldg(w + j / PER_WORD) >> ((j % PER_WORD) * BITS)) & ((1u << BITS) - 1u);
+        return (word(j / PER_WORD) >> ((j % PER_WORD) * BITS)) & ((1u << BITS) - 1u);
     }
     /* PER_WORD symbols starting at symbol i, symbol i in the low bits */
     __device__ __forceinline__ uint32_t chunk(int i) const {
         uint32_t j = (uint32_t)i + mis, wi = j / PER_WORD;
-        return __funnelshift_r(__ldg(w + wi), __ldg(w + wi + 1), (j % PER_WORD) * BITS);
+        return __funnelshift_r(word(wi), word(wi + 1), (j % PER_WORD) * BITS);
     }
 };
 
 /* Longest common prefix of q[v:] and t[h:], at most maxl symbols: exactly what
  * the reference's 8-byte block loop + byte loop compute (wfa.go:411-454),
  * here 16 bases (or 4 bytes) per XOR + find-first-set step. */
-template <int BITS>
-__device__ __forceinline__ int lcp(const SeqView<BITS> &Q, const SeqView<BITS> &T, int v, int h, int maxl)
+template <int BITS, bool SM>
+__device__ __forceinline__ int lcp(const SeqView<BITS, SM> &Q, const SeqView<BITS, SM> &T, int v, int h, int maxl)
 {
     constexpr int PW = 32 / BITS;
     int l = 0;
@@ -414,10 +420,10 @@ template <typename T> __device__ __forceinline__ void keep_ptr(T *&p) { asm vola
  *   bslot u64[2]             broadcast scratch
  *   ring  u32[dM][cap][3]    WARP only: ring of rows, cell-major {M, I, D} triples
  */
-template <bool CTA> __host__ __device__ inline size_t worker_smem_bytes(int dM, int dE, int cap)
+template <bool CTA> __host__ __device__ inline size_t worker_smem_bytes(int dM, int dE, int cap, int seq_cap = 0)
 {
     size_t b = (size_t)dM * 16 + (size_t)dM * 8 + 128 * sizeof(int) + 16;
-    if (!CTA) b += (size_t)dM * (size_t)cap * 12;
+    if (!CTA) b += (size_t)dM * (size_t)cap * 12 + (size_t)seq_cap * 4;      /* ring, then the pair's sequences */
     return (b + 15) & ~(size_t)15;
 }
 
@@ -431,7 +437,7 @@ struct FwdOut {
     unsigned long long c_cells, c_written, c_steps;
 };
 
-template <int BITS, bool CTA>
+template <int BITS, bool CTA, bool SSEQ = false>
 __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned char *smem, uint8_t *slot, const uint64_t slot_bytes)
 {
     using G = Grp<CTA>;
@@ -440,7 +446,8 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
     const int dM = P.dM, cap = P.ring_cap;
 
-    SeqView<BITS> Q, T;
+    SeqView<BITS, SSEQ> Q, T;
+    Q.sa = T.sa = 0;
     if (BITS == 2) { Q.w = P.packed + pd.q_word; Q.mis = 0; T.w = P.packed + pd.t_word; T.mis = 0; }
     else { Q.w = P.raw + (pd.q_byte >> 2); Q.mis = (uint32_t)(pd.q_byte & 3); T.w = P.raw + (pd.t_byte >> 2); T.mis = (uint32_t)(pd.t_byte & 3); }
 
@@ -456,6 +463,17 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
     constexpr int KS = CTA ? 1 : 3;                                     /* words between neighbouring diagonals */
     uint32_t ring_sa = (uint32_t)__cvta_generic_to_shared(ring);
     keep(ring_sa);
+    if (SSEQ) {
+        /* short pair: its 2-bit words live in the warp's shared memory for the whole forward
+         * pass (extend reads two words per sequence and step); one spare word each for the
+         * funnel shift */
+        const uint32_t wq = ((uint32_t)n + 15u) >> 4, wt = ((uint32_t)m + 15u) >> 4;
+        uint32_t *sq = ring + (size_t)dM * cap * 3, *st = sq + wq + 1;
+        for (uint32_t i = tid; i <= wq; i += 32) sq[i] = i < wq ? __ldg(Q.w + i) : 0u;
+        for (uint32_t i = tid; i <= wt; i += 32) st[i] = i < wt ? __ldg(T.w + i) : 0u;
+        Q.sa = (uint32_t)__cvta_generic_to_shared(sq); T.sa = (uint32_t)__cvta_generic_to_shared(st);
+        __syncwarp();
+    }
 
     RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);                /* grows up, index s/g */
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);              /* rows grow down from the end */
@@ -485,9 +503,8 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
         /* source rows s-x, s-o-e, s-e: ring slots kept incrementally (no division) */
         int slX = cur - xg, slO = cur - oeg, slE = cur - eg;
         slX += slX < 0 ? dM : 0; slO += slO < 0 ? dM : 0; slE += slE < 0 ? dM : 0;
-        const int4 hX = si >= xg ? meta[slX] : EMPTY;
-        const int4 hO = si >= oeg ? meta[slO] : EMPTY;
-        const int4 hE = si >= eg ? meta[slE] : EMPTY;
+        /* slots this pair has not written yet still hold EMPTY from the start of the pair */
+        const int4 hX = meta[slX], hO = meta[slO], hE = meta[slE];
         /* loop range (wfa.go:557-563); a superset is harmless, the clamp is not */
         int lo = INT_MAX, hi = INT_MIN;
         if (hX.y <= hX.z) { lo = min(lo, hX.y); hi = max(hi, hX.z); }
@@ -500,6 +517,11 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
         bool exists = false;
         int wlo = INT_MAX, whi = INT_MIN, endhit = 0;
         int aw = 0; Off off = 0;
+        /* WARP worker, row of at most 64 diagonals (the usual wf-adaptive row): the lane's one or
+         * two cells stay in registers, so that Lo/Hi, the end test and reduce need no second look
+         * at the row */
+        uint32_t myM0 = 0, myM1 = 0;
+        const bool narrow = !CTA && lo <= hi && hi - lo < 64;
         if (lo <= hi) {
             aw = hi - lo + 1;
             if (!CTA && aw > cap) { status = ST_RING; break; }
@@ -520,7 +542,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                     /* extend (wfa.go:394-455) */
                     int h = (int)(c.M >> T_BITS), v = h - k;
                     if (v > 0 && v < n && h < m) {
-                        const int l = lcp<BITS>(Q, T, v, h, min(n - v, m - h));
+                        const int l = lcp(Q, T, v, h, min(n - v, m - h));
                         c.M += (uint32_t)l << T_BITS;
                         h += l;
                     }
@@ -581,7 +603,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                             if (ext[u]) {
                                 int l;
                                 if (xr[u]) l = (__ffs((int)xr[u]) - 1) / BITS;
-                                else l = PW + (ext[u] > PW ? lcp<BITS>(Q, T, h - k + PW, h + PW, ext[u] - PW) : 0);
+                                else l = PW + (ext[u] > PW ? lcp(Q, T, h - k + PW, h + PW, ext[u] - PW) : 0);
                                 l = min(l, ext[u]);
                                 c[u].M += (uint32_t)l << T_BITS;
                                 h += l;
@@ -603,7 +625,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                 uint32_t *gC = cells + off + 3 * (k - lo);
                 int rO = k - 1 - hO.y, rE = k - 1 - hE.y, rX = k - hX.y;      /* unsigned range tests: r < cnt */
                 keep(pO); keep(pE); keep(pX); keep(pC); keep_ptr(gC); keep(rO); keep(rE); keep(rX);
-                for (; k <= hi; k += 32) {
+                for (int pass = 0; k <= hi; k += 32, pass++) {
                     uint32_t mo_l = 0, ie_l = 0, mo_r = 0, de_r = 0, mx = 0;
                     if ((uint32_t)rO < cntO) mo_l = lds32<-12>(pO);
                     if ((uint32_t)(rO + 2) < cntO) mo_r = lds32<12>(pO);
@@ -612,12 +634,20 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                     if ((uint32_t)rX < cntX) mx = lds32<0>(pX);
                     Cell3 c = next_cell(mo_l, ie_l, mo_r, de_r, mx, k, n, m);
                     finish_cell(c, k);
+                    if (pass == 0) myM0 = c.M; else if (pass == 1) myM1 = c.M;
                     sts32<0>(pC, c.M); sts32<4>(pC, c.I); sts32<8>(pC, c.D);
                     gC[0] = c.M; gC[1] = c.I; gC[2] = c.D;
                     pO += 384; pE += 384; pX += 384; pC += 384; gC += 96; rO += 32; rE += 32; rX += 32;
                 }
             }
-            G::reduce3(wlo, whi, endhit, red);
+            if (narrow) {
+                /* lane j holds diagonals lo + j and lo + 32 + j: first / last present cell from two ballots */
+                const unsigned long long pres = (unsigned long long)__ballot_sync(0xffffffffu, myM0 != 0) |
+                                                (unsigned long long)__ballot_sync(0xffffffffu, myM1 != 0) << 32;
+                endhit = __any_sync(0xffffffffu, endhit != 0);
+                if (pres) { wlo = lo + __ffsll((long long)pres) - 1; whi = lo + 63 - __clzll((long long)pres); }
+                else { wlo = INT_MAX; whi = INT_MIN; }
+            } else G::reduce3(wlo, whi, endhit, red);
             exists = wlo <= whi;
         }
 
@@ -641,6 +671,23 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
         bool finished = endhit != 0;
         if (!finished && P.adaptive && whi - wlo + 1 >= P.min_wf_len) {
             /* reduce (wfa.go:461-540) as three group reductions; see DESIGN.md 4.3 */
+            if (narrow) {
+                /* the same three reductions on the lanes' own cells: min distance by redux, the
+                 * first / last near diagonal and the last valid one below it from ballots */
+                const int d0 = dist_of(myM0, lo + tid, n, m), d1 = dist_of(myM1, lo + 32 + tid, n, m);   /* no cell: -1 */
+                const int mind = __reduce_min_sync(0xffffffffu, min(d0 >= 0 ? d0 : INT_MAX, d1 >= 0 ? d1 : INT_MAX));
+                const unsigned long long valid = (unsigned long long)__ballot_sync(0xffffffffu, d0 >= 0) |
+                                                 (unsigned long long)__ballot_sync(0xffffffffu, d1 >= 0) << 32;
+                const unsigned long long far = (unsigned long long)__ballot_sync(0xffffffffu, d0 >= 0 && d0 - mind > maxdiff) |
+                                               (unsigned long long)__ballot_sync(0xffffffffu, d1 >= 0 && d1 - mind > maxdiff) << 32;
+                if (far) {
+                    const unsigned long long near = valid & ~far;           /* never empty: the closest cell is near */
+                    const int fb = __ffsll((long long)near) - 1, Lb = 63 - __clzll((long long)near);
+                    const unsigned long long below = valid & ((1ull << fb) - 1ull);
+                    if (below) elo = lo + (63 - __clzll((long long)below)) + 1;
+                    ehi = lo + Lb;
+                }
+            } else {
             int mind = INT_MAX, dummy1 = INT_MIN, dummy2 = 0;
             for (int k = wlo + tid; k <= whi; k += gsz) {
                 const int d = dist_of(rowM[KS * (k - lo)], k, n, m);
@@ -660,6 +707,7 @@ __device__ FwdOut forward_pair(const KParams &P, const uint32_t pair, unsigned c
                 G::reduce3(d0, lf, d2, red);
                 if (lf != INT_MIN) elo = lf + 1;
                 ehi = L;
+            }
             }
         }
         bool hit = false; int hitK = Ak;
@@ -942,7 +990,7 @@ align_kernel(const KParams P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wpb = CTA ? 1 : (int)(blockDim.x >> 5);
     const int wib = CTA ? 0 : (int)(threadIdx.x >> 5);
-    const size_t wbytes = worker_smem_bytes<CTA>(P.dM, P.dE, P.ring_cap);
+    const size_t wbytes = worker_smem_bytes<CTA>(P.dM, P.dE, P.ring_cap, P.seq_cap);
     unsigned char *smem = smem_raw + (size_t)wib * wbytes;
     const uint64_t worker = (uint64_t)blockIdx.x * wpb + wib;
     uint8_t *slot = P.arena + worker * P.slot_bytes;
@@ -990,7 +1038,10 @@ align_kernel(const KParams P)
                     }
                     continue;
                 }
-                const FwdOut f = forward_pair<BITS, CTA>(P, pair, smem, slot + (uint64_t)j * sub_bytes, sub_bytes);
+                FwdOut f;
+                if (BITS == 2 && !CTA && ((P.pairs[pair].n + 15u) >> 4) + ((P.pairs[pair].m + 15u) >> 4) + 2u <= (uint32_t)P.seq_cap)
+                    f = forward_pair<BITS, CTA, BITS == 2 && !CTA>(P, pair, smem, slot + (uint64_t)j * sub_bytes, sub_bytes);
+                else f = forward_pair<BITS, CTA, false>(P, pair, smem, slot + (uint64_t)j * sub_bytes, sub_bytes);
                 if (lane == (int)j) { mine = f; have = true; my_pair = pair; }
             }
             finish_group(P, have, my_pair, mine, slot + (uint64_t)lane * sub_bytes, sub_bytes);

@@ -329,7 +329,7 @@ Need estimate(const wfacuda_ctx *ctx, uint32_t n, uint32_t m)
 }
 
 struct LaunchPlan {
-    bool cta; int threads; int blocks; int ring_cap; size_t smem; uint64_t slot_bytes; uint64_t workers; bool slot_at_max;
+    bool cta; int threads; int blocks; int ring_cap; int seq_cap; size_t smem; uint64_t slot_bytes; uint64_t workers; bool slot_at_max;
     int group;               /* WARP class: pairs per warp group; slot_bytes is per pair, a warp owns group * slot_bytes */
 };
 
@@ -349,14 +349,18 @@ uint64_t arena_budget(wfacuda_ctx *ctx, bool refresh = true)
 int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint32_t> &order, bool cta, int bits,
                 double boost, int min_ring_cap, LaunchPlan *lp)
 {
-    uint64_t need_max = 0; int width_max = 1;
+    uint64_t need_max = 0; int width_max = 1; uint32_t seq_words_max = 0;
     /* the list is sorted longest first; a prefix sample bounds the estimate cheaply */
     const size_t sample = std::min<size_t>(order.size(), 4096);
     for (size_t i = 0; i < sample; i++) {
         const PairDesc &d = b->descs[order[i]];
         const Need nd = estimate(ctx, d.n, d.m);
         need_max = std::max(need_max, nd.arena); width_max = std::max(width_max, nd.width);
+        seq_words_max = std::max(seq_words_max, ((d.n + 15) >> 4) + ((d.m + 15) >> 4) + 2);
     }
+    /* WARP worker, 2-bit: pairs of up to ~2 kbp keep their packed sequences in shared memory
+     * (the kernel checks every pair against this capacity and reads longer ones from global) */
+    lp->seq_cap = (!cta && bits == 2 && seq_words_max <= 264 && !getenv("WFACUDA_NO_SEQ_SMEM")) ? (int)((seq_words_max + 3) & ~3u) : 0;
     need_max = (uint64_t)((double)need_max * boost);
     lp->cta = cta; lp->slot_at_max = false;
     /* the device is only asked for its free memory when the arena may have to grow */
@@ -375,12 +379,13 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
         int cap = 64;
         while (cap < (int)(width_max * 0.33) + 8 && cap < 512) cap *= 2;
         cap = std::max(cap, std::max(min_ring_cap, ctx->ring_cap_learned));
-        size_t per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap);
-        while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap); }
+        size_t per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap, lp->seq_cap);
+        while (per_warp * wpb > ctx->smem_optin && cap > 32) { cap /= 2; per_warp = worker_smem_bytes<false>(ctx->dM, ctx->dE, cap, lp->seq_cap); }
         if (per_warp * wpb > ctx->smem_optin) return fail(ctx, WFACUDA_E_INVALID, "penalties need a deeper shared-memory ring than fits");
         lp->ring_cap = cap; lp->threads = wpb * 32; lp->smem = per_warp * wpb;
         int ci = 1; for (int c = 64; c < cap && ci < 7; c *= 2) ci++;
-        int &oc = ctx->occ_cache[0][bits == 8][cap < 64 ? 0 : ci];
+        int oc_seq = 0;
+        int &oc = lp->seq_cap ? oc_seq : ctx->occ_cache[0][bits == 8][cap < 64 ? 0 : ci];
         if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, bits == 2 ? align_kernel<2, false> : align_kernel<8, false>, lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
         blocks_per_sm = oc;
         blocks_per_sm = std::max(1, blocks_per_sm);
@@ -433,7 +438,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
-        P.ring_cap = lp.ring_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+        P.ring_cap = lp.ring_cap; P.seq_cap = lp.seq_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         const double tk0 = now_ms();
         if (cta) { if (bits == 2) align_kernel<2, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
                    else           align_kernel<8, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
