@@ -62,6 +62,29 @@ struct Result {                /* == wfacuda_result */
 struct Counters {              /* device-side work counters, one set per launch */
     unsigned long long cells, cells_written, steps, ops, retry_n, ops_cursor, work_next, arena_used_max;
     unsigned long long t_first, t_last;   /* globaltimer of the first block start / last block end (LANE kernel, profiling aid) */
+    unsigned long long lane_count[8];     /* LANE class: [j] pairs entering stage j, [4 + j] group queue of stage j */
+    unsigned int lane_hist[64];           /* LANE class: sampled histogram of the final score index (next batch's stage boundaries) */
+};
+
+/* LANE class (wfa_lane.cuh).  Without heuristic the loop range of `next` depends only on which
+ * scores exist, so the rows of every group have the same geometry: one table per launch. */
+constexpr int LANE_MAX_STAGES = 4;
+struct LaneGeom {
+    int8_t   lo[64], hi[64];            /* loop range of the row of score index si; lo > hi: no such row */
+    uint16_t off[64];                   /* first cell of the row inside its stage's group slot, in units of 32 words */
+    int32_t  n_rows;                    /* rows in the table; a pair still running after row n_rows - 1 goes to the WARP worker */
+    int32_t  n_stages;
+    int32_t  stage_end[LANE_MAX_STAGES];/* last row of stage j; stage_end[n_stages - 1] = n_rows - 1 */
+    uint32_t slot_words[LANE_MAX_STAGES];
+    uint32_t scratch_words;             /* op scratch (backtrace overflow) at the start of every slot */
+    uint32_t state_words;               /* words of a pair's saved state (ring bytes + 3 counters) */
+};
+struct LaneAux {
+    uint32_t *rec;                      /* [ticket][LANE_REC_WORDS]: what the finish kernel needs of a pair */
+    uint32_t *state;                    /* [ticket][state_words]: rings of a pair that moves on to the next stage */
+    uint32_t *list[LANE_MAX_STAGES];    /* tickets entering stage j >= 1 */
+    uint8_t  *arena[LANE_MAX_STAGES];   /* group slots of stage j */
+    uint32_t  cap[LANE_MAX_STAGES];     /* groups the arena of stage j holds */
 };
 
 struct KParams {
@@ -89,6 +112,8 @@ struct KParams {
     int32_t  seq_cap;          /* WARP kernel: 32-bit words of shared memory per warp for the pair's 2-bit sequences (0: read them from global) */
     uint8_t  global_aln, adaptive, semi_literal, pad8_;
     int32_t  min_wf_len, max_dist_diff;
+    LaneGeom lg;               /* LANE kernels only */
+    LaneAux  la;
 };
 
 /* ------------------------------------------------------------------ sequences

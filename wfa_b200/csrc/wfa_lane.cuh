@@ -46,12 +46,6 @@ constexpr int LANE_MAX_LEN = 254;           /* offsets up to m+1 must fit a byte
 #endif
 
 constexpr int LANE_HDR_ROWS = 64;            /* scores (in units of g) a group may reach; beyond: WARP worker */
-/* A group's slot starts with what the forward kernel leaves for the finish kernel (words):
- *   [0, 128)    row headers int2[LANE_HDR_ROWS]: {lo | hi << 16 (both + 0x4000), first word of the row}
- *   [128, 384)  per-pair records, word j of lane l at 128 + 32 j + l:
- *               0 status | first_eq << 8 | final score index << 16, 1 final score, 2 C, 3 cells written, 4 score steps, 5 top
- *   [384, ...)  op scratch of the backtrace, then free space, then the rows (growing down from the end) */
-constexpr uint32_t LANE_REC_W = 128, LANE_SCRATCH_W = 384;
 constexpr int LANE_FINISH_WARPS = 4;
 constexpr uint32_t LANE_SOPS = 32;           /* ops per pair kept in shared memory by the finish kernel (16 bits each); more go to the slot */
 
@@ -96,8 +90,7 @@ struct LaneOps {
 /* dM, dE as in KParams (max(x,o+e)/g+1, e/g+1); W ring columns; SW words per sequence */
 __host__ __device__ inline size_t lane_smem_bytes(int dM, int dE, int W, int SW)
 {
-    size_t b = (((size_t)dM * 8) + 15) & ~(size_t)15;                 /* meta int2[] */
-    b += 2 * (size_t)SW * 128;                                         /* seqQ, seqT */
+    size_t b = 2 * (size_t)SW * 128;                                   /* seqQ, seqT */
     b += ((size_t)(dM - 1) + 2 * (size_t)(dE - 1)) * (size_t)W * 32;   /* rings (in place: one row less than the WARP worker) */
     return (b + 127) & ~(size_t)127;
 }
@@ -183,63 +176,6 @@ __device__ __forceinline__ Cell3O next_off3(uint32_t mo_l, uint32_t ie_l, uint32
     return r;
 }
 
-/* Component.Get on the packed group arena (see the header comment).  The row headers live in
- * shared memory, and the view remembers the five source words it fetched for the cell the
- * backtrace stands on: the next cell of the walk and the offsets the reference re-derives
- * there (wfa.go:766-817) are always among them, so one step of the backtrace costs one round of
- * five independent global loads instead of six dependent ones. */
-struct LaneView {
-    const int2     *hdr;       /* shared memory: {lo | hi << 16 (both + 0x4000), first word of the row} */
-    const uint32_t *cells;     /* already offset by the lane */
-    int             si_last;
-    int             n, m, xg, oeg, eg;
-    bool            first_eq;
-    int             c_si, c_k;                 /* cell whose sources are cached (c_si < 0: none) */
-    uint32_t        c_w[5];                    /* words at (si-oeg,k-1) (si-eg,k-1) (si-oeg,k+1) (si-eg,k+1) (si-xg,k) */
-    __device__ __forceinline__ uint32_t word(int si, int k) const
-    {
-        if (si < 0 || si > si_last) return 0;
-        const int2 h = hdr[si];
-        const int lo = (h.x & 0xffff) - 0x4000, hi = (int)((uint32_t)h.x >> 16) - 0x4000;
-        if (k < lo || k > hi) return 0;
-        return cells[(uint32_t)h.y + (uint32_t)(k - lo) * 32u];
-    }
-    __device__ __forceinline__ uint32_t cached_word(int si, int k) const
-    {
-        const int dk = k - c_k, ds = c_si - si;
-        if (c_si >= 0) {
-            if (dk == -1) { if (ds == oeg) return c_w[0]; if (ds == eg) return c_w[1]; }
-            else if (dk == 1) { if (ds == oeg) return c_w[2]; if (ds == eg) return c_w[3]; }
-            else if (dk == 0 && ds == xg) return c_w[4];
-        }
-        return word(si, k);
-    }
-    /* offset << 3, code bits zero: all the backtrace needs of a source cell */
-    __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
-    {
-        return ((cached_word(si, k) >> (8 * comp)) & 255u) << T_BITS;
-    }
-    /* raw word of the cell the backtrace stands on: offset << 3 | provenance code, the code
-     * re-derived from the cell's five sources exactly as `next` chose it (wfa.go:579-698), or
-     * the init code when `next` wrote nothing there (wfa.go:155-158) */
-    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k)
-    {
-        const uint32_t o = (cached_word(si, k) >> (8 * comp)) & 255u;
-        if (o == 0) return 0;
-        const uint32_t wl = word(si - oeg, k - 1), el = word(si - eg, k - 1);
-        const uint32_t wr = word(si - oeg, k + 1), er = word(si - eg, k + 1);
-        const uint32_t wx = word(si - xg, k);
-        c_si = si; c_k = k; c_w[0] = wl; c_w[1] = el; c_w[2] = wr; c_w[3] = er; c_w[4] = wx;
-        const CellO c = next_off(wl & 255u, (el >> 8) & 255u, wr & 255u, (er >> 16) & 255u, wx & 255u,
-                                 (uint32_t)m, (uint32_t)(n + k));
-        uint32_t code;
-        if (comp == 1) code = T_INS_OPEN + ((c.code >> 3) & 1u);
-        else if (comp == 2) code = T_DEL_OPEN + ((c.code >> 4) & 1u);
-        else code = c.M ? (c.code & 7u) : (first_eq ? T_MATCH : T_MISMATCH);
-        return o << T_BITS | code;
-    }
-};
-
 /* 16 bases starting at base `pos` of a lane's sequence in shared memory (base pos in the low bits) */
 __device__ __forceinline__ uint32_t lane_chunk(uint32_t seq_sa, int pos)
 {
@@ -262,33 +198,41 @@ __device__ __forceinline__ uint32_t lane_extend(uint32_t sQ, uint32_t sT, uint32
     return M + (uint32_t)min(l, ext);
 }
 
-/* Forward pass of one group of up to 32 pairs: rows, row headers and the per-pair records go
- * to the group's slot; lane_finish_kernel runs the backtraces. */
-__device__ __forceinline__ void lane_forward(const KParams &P, const bool have, const uint32_t pair, unsigned char *smem,
-                                          uint8_t *slot, const uint64_t slot_bytes)
+/* One stage of the forward pass of one group of up to 32 pairs: the rows of score indices
+ * [si0, si1] go to the group's slot of this stage.  A pair that reaches the end cell leaves its
+ * record for the finish kernel; a pair still running at the end of the stage saves its rings and
+ * is queued for the next stage, where it is grouped with other pairs that are still running --
+ * lanes of a warp work in lockstep, so a group costs as many rows as its slowest pair needs, and
+ * regrouping the survivors keeps finished lanes from idling through the long tail. */
+constexpr uint32_t LANE_REC_WORDS = 12;      /* 0 status | first_eq << 8 | final score index << 16 | stages << 24, 1 final score,
+                                              * 2 C, 3 cells written, 4 score steps, 5.. group << 5 | lane of every stage */
+
+__device__ __forceinline__ void lane_stage(const KParams &P, const int stg, const bool have, const uint32_t ticket, const uint32_t pair,
+                                           unsigned char *smem, uint32_t *cells, const uint32_t group)
 {
     const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     /* rings are written in place: the row of score s replaces the oldest row still needed,
      * M[s - max(x,o+e)] resp. I/D[s - e]; sources ahead of the write position are read first and
-     * the ones behind it are carried in registers */
+     * the ones behind it are carried in registers.  A row's range contains the range of the row
+     * it replaces (the geometry only grows), so what lies outside a row's range stays 0 = absent. */
     const int RM = P.dM - 1, RE = P.dE - 1, W = P.ring_cap, KC = W >> 1, SW = P.group;
     const int xg = P.xg, oeg = P.oeg, x = (int)P.x;
+    const LaneGeom &G = P.lg;
 
-    int2 *meta = reinterpret_cast<int2 *>(smem);
-    int2 *hdrs = reinterpret_cast<int2 *>(slot);                       /* global: read by the finish kernel */
-    unsigned char *p = smem + ((((size_t)P.dM * 8) + 15) & ~(size_t)15);
+    unsigned char *p = smem;
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)lane * 4u;
     const uint32_t sT = sQ + (uint32_t)SW * 128u;
     const uint32_t rowB = (uint32_t)W * 32u;
-    const uint32_t rM = sQ - (uint32_t)lane * 4u + 2u * (uint32_t)SW * 128u + (uint32_t)lane + (uint32_t)KC * 32u;   /* column of this lane, diagonal 0 */
+    const uint32_t ringL = sQ - (uint32_t)lane * 4u + 2u * (uint32_t)SW * 128u + (uint32_t)lane;          /* this lane's byte of column 0, ring row 0 */
+    const uint32_t rM = ringL + (uint32_t)KC * 32u;                                                        /* diagonal 0 */
     const uint32_t rI = rM + (uint32_t)RM * rowB, rD = rI + (uint32_t)RE * rowB;
 
     int status = have ? ST_OK : ST_PENDING;
     PairDesc pd; pd.q_byte = pd.t_byte = pd.q_word = pd.t_word = 0; pd.n = pd.m = 0;
     if (have) {
         pd = P.pairs[pair];
-        if (P.pflags[pair] & 1) status = ST_NEED8;
+        if (stg == 0 && (P.pflags[pair] & 1)) status = ST_NEED8;
     }
     const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
     const bool act = status == ST_OK;
@@ -298,16 +242,18 @@ __device__ __forceinline__ void lane_forward(const KParams &P, const bool have, 
         const uint32_t *gq = P.packed + pd.q_word, *gt = P.packed + pd.t_word;
         const int wq = act ? (n + 15) >> 4 : 0, wt = act ? (m + 15) >> 4 : 0;
 #pragma unroll 1
-        for (int w = 0; w < SW; w++) {
-            sts_u32(sQ + (uint32_t)w * 128u, w < wq ? __ldg(gq + w) : 0u);
-            sts_u32(sT + (uint32_t)w * 128u, w < wt ? __ldg(gt + w) : 0u);
+        for (int w0 = 0; w0 < SW; w0 += 4) {
+            uint32_t a[4], c[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { a[j] = w0 + j < wq ? __ldg(gq + w0 + j) : 0u; c[j] = w0 + j < wt ? __ldg(gt + w0 + j) : 0u; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) if (w0 + j < SW) { sts_u32(sQ + (uint32_t)(w0 + j) * 128u, a[j]); sts_u32(sT + (uint32_t)(w0 + j) * 128u, c[j]); }
         }
         const uint32_t ring0 = sQ + 2u * (uint32_t)SW * 128u;           /* rings are a multiple of 128 bytes per 4 columns */
         const int ring_words = (RM + 2 * RE) * W * 8;
 #pragma unroll 1
         for (int w = 0; w < ring_words; w += 32) sts_u32(ring0 + (uint32_t)w * 4u, 0u);
     }
-    for (int i = lane; i < RM; i += 32) meta[i] = make_int2(1, 0);
     __syncwarp();
     const bool first_eq = ((lds_u32(sQ) ^ lds_u32(sT)) & 3u) == 0u;       /* q[0] == t[0], wfa.go:155-158 */
     /* a lane works on diagonals [klo, klo + kspan] = [-(n-1), m-1] (wfa.go:562-563); an idle or
@@ -318,44 +264,52 @@ __device__ __forceinline__ void lane_forward(const KParams &P, const bool have, 
      * masked at all: what they compute is never read (their counters, end test and results are
      * guarded, their arena column past the final score is not visited by the backtrace). */
     const int clamp_lo = -(__reduce_min_sync(FULL, act ? n : INT_MAX) - 1), clamp_hi = __reduce_min_sync(FULL, act ? m : INT_MAX) - 1;
-    const int ulo = -(__reduce_max_sync(FULL, act ? n : 1) - 1), uhi = __reduce_max_sync(FULL, act ? m : 1) - 1;
 
-    uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
-    const uint32_t slot_words = (uint32_t)min((uint64_t)0xfffffff0u, slot_bytes >> 2);
-    uint32_t top = slot_words;
-    const uint32_t hdr_limit = LANE_SCRATCH_W + 64 * 32;   /* headers, records, then the op scratch: room for 32 ops per pair at least */
-
-    uint32_t s = 0; int si = 0, cur = 0, curE = 0;
+    const int si0 = stg == 0 ? 0 : G.stage_end[stg - 1] + 1, si1 = G.stage_end[stg];
+    const int ring_rows = RM + 2 * RE, wpr = W >> 2;                     /* saved state: ring_rows x wpr words of 4 columns each */
     bool done = false; uint32_t minS = 0; int my_si = 0;
     uint32_t c_cells = 0, c_written = 0, c_steps = 0;
-    int group_fail = 0;
-    const int2 EMPTY = make_int2(1, 0);
+    /* ring columns (in words of 4) that hold anything after row sb: those of the last row that exists up to sb */
+    auto ring_span = [&](int sb, int &c0, int &c1) {
+        while (sb > 0 && G.lo[sb] > G.hi[sb]) sb--;
+        c0 = (G.lo[sb] + KC) >> 2; c1 = (G.hi[sb] + KC) >> 2;
+    };
+    if (stg > 0 && act) {
+        /* rings as the previous stage left them; only the columns its last row could reach.  A
+         * ring row is wpr = 16 words of four columns: its four 16-byte quarters are requested
+         * together (each lane reads its own pair's record, so every load is a DRAM round trip) */
+        const uint4 *st = reinterpret_cast<const uint4 *>(P.la.state + (size_t)ticket * G.state_words);
+        int cw0, cw1; ring_span(si0 - 1, cw0, cw1);
+        const int q0 = cw0 >> 2, q1 = cw1 >> 2, qpr = wpr >> 2;
+#pragma unroll 1
+        for (int r = 0; r < ring_rows; r++) {
+            uint4 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = (q >= q0 && q <= q1 && q < qpr) ? st[r * qpr + q] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) if (w4[j]) {
+                    const uint32_t a = ringL + (uint32_t)r * rowB + (uint32_t)(q * 4 + j) * 128u;
+                    sts_u8o<0>(a, w4[j] & 255u); sts_u8o<32>(a, (w4[j] >> 8) & 255u); sts_u8o<64>(a, (w4[j] >> 16) & 255u); sts_u8o<96>(a, w4[j] >> 24);
+                }
+            }
+        }
+        const uint4 cn = st[ring_rows * qpr];
+        c_cells = cn.x; c_written = cn.y; c_steps = cn.z;
+    }
 
+    uint32_t s = (uint32_t)si0 * P.g; int si = si0, cur = si0 % RM, curE = si0 % RE;
     if (__any_sync(FULL, act)) for (;;) {
-        int slX = cur - xg, slO = cur - oeg;
-        slX += slX < 0 ? RM : 0; slO += slO < 0 ? RM : 0;
-        const int2 hX = meta[slX], hO = meta[slO];
-        int slE = cur - P.eg; slE += slE < 0 ? RM : 0;
-        const int2 hE = meta[slE];                     /* also the range held by the I/D slot about to be replaced */
-        const int2 hP = meta[cur];                     /* range held by the M slot about to be replaced */
-        /* union loop range (wfa.go:557-563), clamped with the longest sequences of the group */
-        int lo = INT_MAX, hi = INT_MIN;
-        if (hX.x <= hX.y) { lo = min(lo, hX.x); hi = max(hi, hX.y); }
-        if (hO.x <= hO.y) { lo = min(lo, hO.x); hi = max(hi, hO.y); }
-        if (hE.x <= hE.y) { lo = min(lo, hE.x); hi = max(hi, hE.y); }
-        if (lo <= hi) { lo = max(lo - 1, ulo); hi = min(hi + 1, uhi); }
-        const bool has_init = (s == 0) || (s == (uint32_t)x);          /* global: the one cell k = 0 */
-        if (has_init) { lo = min(lo, 0); hi = max(hi, 0); }
-
-        int wlo = INT_MAX, whi = INT_MIN;
-        int aw = 0; uint32_t off = 0;
-        const uint32_t bCM = rM + (uint32_t)cur * rowB, bCI = rI + (uint32_t)curE * rowB, bCD = rD + (uint32_t)curE * rowB;
+        const int lo = G.lo[si], hi = G.hi[si];
         if (lo <= hi) {
-            aw = hi - lo + 1;
-            if (lo < -KC + 1 || hi > KC - 2 || si >= LANE_HDR_ROWS) { group_fail = ST_RING; break; }
-            const uint32_t need = (uint32_t)aw * 32u;
-            if (top < hdr_limit || top - hdr_limit < need) { group_fail = ST_ARENA; break; }
-            off = top - need;
+            int slX = cur - xg, slO = cur - oeg;
+            slX += slX < 0 ? RM : 0; slO += slO < 0 ? RM : 0;
+            const bool has_init = (s == 0) || (s == (uint32_t)x);          /* global: the one cell k = 0 */
+            const int aw = hi - lo + 1;
+            const uint32_t off = (uint32_t)G.off[si] * 32u;
+            const uint32_t bCM = rM + (uint32_t)cur * rowB, bCI = rI + (uint32_t)curE * rowB, bCD = rD + (uint32_t)curE * rowB;
             /* running byte addresses of cell k in the lane's columns; a row's cell k+1 is 32 bytes on */
             uint32_t pO = rM + (uint32_t)slO * rowB + (uint32_t)(lo * 32), pX = rM + (uint32_t)slX * rowB + (uint32_t)(lo * 32);
             uint32_t pM = bCM + (uint32_t)(lo * 32), pI = bCI + (uint32_t)(lo * 32), pD = bCD + (uint32_t)(lo * 32);
@@ -437,129 +391,225 @@ __device__ __forceinline__ void lane_forward(const KParams &P, const bool have, 
                 uint32_t *g0 = cells + off + lane - lo * 32;
                 *g0 = (*g0 & 0xffffff00u) | M;
             }
-            /* M WaveFront.Lo/Hi of this pair = first and last present cell (only the work counter C needs them) */
             if (act && !done) {
+                /* M WaveFront.Lo/Hi of this pair = first and last present cell (only the work counter C needs them) */
                 int a = lo, b = hi;
                 while (a <= hi && lds_u8(bCM + (uint32_t)(a * 32)) == 0u) a++;
                 while (b > a && lds_u8(bCM + (uint32_t)(b * 32)) == 0u) b--;
-                if (a <= hi) { wlo = a; whi = b; }
+                if (a <= hi) {
+                    c_steps++; c_cells += (uint32_t)(b - a + 1); c_written += (uint32_t)aw;
+                    /* end test on diagonal m-n (wfa.go:235-239); the lane reads back its own column */
+                    if (Ak >= lo && Ak <= hi) {
+                        const uint32_t hM = lds_u8(bCM + (uint32_t)(Ak * 32));
+                        if ((int)hM >= m) { done = true; minS = s; my_si = si; }
+                    }
+                }
             }
         }
-        /* keep "outside a slot's range = absent": clear what the replaced rows held beyond [lo, hi] */
-        if (hP.x <= hP.y && (lo > hi || hP.x < lo || hP.y > hi))
-            for (int k = hP.x; k <= hP.y; k++) if (k < lo || k > hi) sts_u8(bCM + (uint32_t)(k * 32), 0u);
-        if (hE.x <= hE.y && (lo > hi || hE.x < lo || hE.y > hi))
-            for (int k = hE.x; k <= hE.y; k++) if (k < lo || k > hi) { sts_u8(bCI + (uint32_t)(k * 32), 0u); sts_u8(bCD + (uint32_t)(k * 32), 0u); }
-        const bool seen = wlo <= whi;
-        const bool any = __any_sync(FULL, seen);
-        if (any) {
-            top = off;
-            if (seen) { c_steps++; c_cells += (uint32_t)(whi - wlo + 1); c_written += (uint32_t)aw; }
-            /* end test on diagonal m-n (wfa.go:235-239); the lane reads back its own column */
-            if (seen && Ak >= lo && Ak <= hi) {       /* seen implies a live lane */
-                const uint32_t hM = lds_u8(bCM + (uint32_t)(Ak * 32));
-                if (!done && (int)hM >= m) { done = true; minS = s; my_si = si; }
-            }
-        }
-        __syncwarp();
-        meta[cur] = any ? make_int2(lo, hi) : EMPTY;                      /* same value from every lane; a row nobody has holds zeros only */
-        if (lane == 0 && si < LANE_HDR_ROWS)
-            hdrs[si] = any ? make_int2((lo + 0x4000) | (hi + 0x4000) << 16, (int)off) : make_int2(0x4001 | 0x4000 << 16, 0);
-        __syncwarp();
-        if (__all_sync(FULL, !act || done)) break;
+        if (si == si1 || __all_sync(FULL, !act || done)) break;
         s += P.g; si++;
         cur = cur + 1 == RM ? 0 : cur + 1;
         curE = curE + 1 == RE ? 0 : curE + 1;
     }
-    if (act && !done) status = group_fail ? group_fail : ST_ARENA;
+    const bool last_stage = stg + 1 >= G.n_stages;
+    bool cont = act && !done;                                              /* still running at the end of the stage */
+    if (cont && last_stage) { status = ST_RING; cont = false; }          /* beyond the byte rings' reach: WARP worker */
 
-    /* what the finish kernel needs of this pair */
-    uint32_t *rec = cells + LANE_REC_W + lane;
-    rec[0] = (uint32_t)status | (first_eq ? 0x100u : 0u) | (uint32_t)my_si << 16;
-    rec[32] = minS; rec[64] = c_cells; rec[96] = c_written; rec[128] = c_steps; rec[160] = top;
+    if (!last_stage) {
+        const unsigned cm = __ballot_sync(FULL, cont);
+        if (cm) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&P.ctr->lane_count[stg + 1], (unsigned long long)__popc(cm));
+            base = __shfl_sync(FULL, base, 0);
+            if (cont) {
+                const unsigned long long pos = base + (unsigned)__popc(cm & ((1u << lane) - 1u));
+                if (pos < (unsigned long long)P.la.cap[stg + 1] * 32ull) {
+                    P.la.list[stg + 1][pos] = ticket;
+                    uint4 *st = reinterpret_cast<uint4 *>(P.la.state + (size_t)ticket * G.state_words);
+                    int cw0, cw1; ring_span(si1, cw0, cw1);
+                    const int q0 = cw0 >> 2, q1 = cw1 >> 2, qpr = wpr >> 2;
+#pragma unroll 1
+                    for (int r = 0; r < ring_rows; r++)
+#pragma unroll 1
+                        for (int q = q0; q <= q1; q++) {
+                            uint32_t w4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const uint32_t a = ringL + (uint32_t)r * rowB + (uint32_t)(q * 4 + j) * 128u;
+                                w4[j] = lds_u8o<0>(a) | lds_u8o<32>(a) << 8 | lds_u8o<64>(a) << 16 | lds_u8o<96>(a) << 24;
+                            }
+                            st[r * qpr + q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
+                    st[ring_rows * qpr] = make_uint4(c_cells, c_written, c_steps, 0u);
+                } else { status = ST_ARENA; cont = false; }                /* the next stage's arena is full: the host re-queues the pair */
+            }
+        }
+    }
+    if (have) {
+        uint32_t *rec = P.la.rec + (size_t)ticket * LANE_REC_WORDS;
+        rec[5 + stg] = group << 5 | (uint32_t)lane;
+        if (!cont) {
+            rec[0] = (uint32_t)status | (first_eq ? 0x100u : 0u) | (uint32_t)my_si << 16 | (uint32_t)(stg + 1) << 24;
+            rec[1] = minS; rec[2] = c_cells; rec[3] = c_written; rec[4] = c_steps;
+        }
+    }
 }
 
-/* Backtraces (wfa.go:703-983) of one group, lane-parallel, then the group's results. */
-__device__ __forceinline__ void lane_finish(const KParams &P, const bool have, const uint32_t pair, int2 *hdrs, uint16_t *sops,
-                                            uint8_t *slot, const uint64_t slot_bytes, WorkAcc *acc)
+/* Component.Get on the staged group arenas.  The rows of score index si of every group of a
+ * stage have the same geometry (LaneGeom, copied to shared memory); the pair's own column in
+ * each stage is `seg[stage]` = its group's slot + its lane.  Like before, the view remembers
+ * the five source words it fetched for the cell the backtrace stands on: the next cell of the
+ * walk and the offsets the reference re-derives there (wfa.go:766-817) are always among them,
+ * so one step of the backtrace costs one round of five independent global loads. */
+struct LaneGeomS { int8_t lo[64], hi[64]; uint16_t off[64]; };
+struct LaneView {
+    const LaneGeomS *G;        /* shared memory */
+    const uint32_t *const *seg;/* shared memory: seg[stage * 32] = this lane's column in the slot of its group of that stage */
+    int             e0, e1, e2;/* last row of stages 0..2 (INT_MAX where there is no later stage) */
+    int             si_last;
+    int             n, m, xg, oeg, eg;
+    bool            first_eq;
+    int             c_si, c_k;                 /* cell whose sources are cached (c_si < 0: none) */
+    uint32_t        c_w[5];                    /* words at (si-oeg,k-1) (si-eg,k-1) (si-oeg,k+1) (si-eg,k+1) (si-xg,k) */
+    __device__ __forceinline__ uint32_t word(int si, int k) const
+    {
+        if (si < 0 || si > si_last) return 0;
+        const int lo = G->lo[si], hi = G->hi[si];
+        if (k < lo || k > hi) return 0;
+        const int j = (si > e0) + (si > e1) + (si > e2);
+        return seg[j * 32][((uint32_t)G->off[si] + (uint32_t)(k - lo)) * 32u];
+    }
+    __device__ __forceinline__ uint32_t cached_word(int si, int k) const
+    {
+        const int dk = k - c_k, ds = c_si - si;
+        if (c_si >= 0) {
+            if (dk == -1) { if (ds == oeg) return c_w[0]; if (ds == eg) return c_w[1]; }
+            else if (dk == 1) { if (ds == oeg) return c_w[2]; if (ds == eg) return c_w[3]; }
+            else if (dk == 0 && ds == xg) return c_w[4];
+        }
+        return word(si, k);
+    }
+    /* offset << 3, code bits zero: all the backtrace needs of a source cell */
+    __device__ __forceinline__ uint32_t get(int comp, int si, int k) const
+    {
+        return ((cached_word(si, k) >> (8 * comp)) & 255u) << T_BITS;
+    }
+    /* raw word of the cell the backtrace stands on: offset << 3 | provenance code, the code
+     * re-derived from the cell's five sources exactly as `next` chose it (wfa.go:579-698), or
+     * the init code when `next` wrote nothing there (wfa.go:155-158) */
+    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k)
+    {
+        const uint32_t o = (cached_word(si, k) >> (8 * comp)) & 255u;
+        if (o == 0) return 0;
+        const uint32_t wl = word(si - oeg, k - 1), el = word(si - eg, k - 1);
+        const uint32_t wr = word(si - oeg, k + 1), er = word(si - eg, k + 1);
+        const uint32_t wx = word(si - xg, k);
+        c_si = si; c_k = k; c_w[0] = wl; c_w[1] = el; c_w[2] = wr; c_w[3] = er; c_w[4] = wx;
+        const CellO c = next_off(wl & 255u, (el >> 8) & 255u, wr & 255u, (er >> 16) & 255u, wx & 255u,
+                                 (uint32_t)m, (uint32_t)(n + k));
+        uint32_t code;
+        if (comp == 1) code = T_INS_OPEN + ((c.code >> 3) & 1u);
+        else if (comp == 2) code = T_DEL_OPEN + ((c.code >> 4) & 1u);
+        else code = c.M ? (c.code & 7u) : (first_eq ? T_MATCH : T_MISMATCH);
+        return o << T_BITS | code;
+    }
+};
+
+/* Backtraces (wfa.go:703-983) of 32 pairs, lane-parallel, then their results. */
+__device__ __forceinline__ void lane_finish(const KParams &P, const bool have, const uint32_t ticket, const uint32_t pair,
+                                            const LaneGeomS *Gs, const uint32_t **seg, uint16_t *sops, const bool sample, WorkAcc *acc)
 {
     const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
-    const uint32_t slot_words = (uint32_t)min((uint64_t)0xfffffff0u, slot_bytes >> 2);
-    {
-        const int4 *g = reinterpret_cast<const int4 *>(slot);           /* 64 headers = 32 x 16 bytes */
-        reinterpret_cast<int4 *>(hdrs)[lane] = g[lane];
+    const LaneGeom &G = P.lg;
+    int status = ST_PENDING; bool first_eq = false; int my_si = 0, nseg = 0;
+    uint32_t minS = 0, c_cells = 0, c_written = 0, c_steps = 0;
+    uint32_t *slot_last = nullptr; uint32_t lane_last = 0;
+    if (have) {
+        const uint32_t *rec = P.la.rec + (size_t)ticket * LANE_REC_WORDS;
+        const uint32_t r0 = rec[0];
+        status = (int)(r0 & 255u); first_eq = (r0 & 0x100u) != 0u; my_si = (int)((r0 >> 16) & 255u); nseg = (int)(r0 >> 24);
+        minS = rec[1]; c_cells = rec[2]; c_written = rec[3]; c_steps = rec[4];
+        for (int j = 0; j < nseg; j++) {
+            const uint32_t sg = rec[5 + j];
+            uint32_t *slot = reinterpret_cast<uint32_t *>(P.la.arena[j]) + (size_t)(sg >> 5) * G.slot_words[j];
+            seg[j * 32 + lane] = slot + (sg & 31u);
+            slot_last = slot; lane_last = sg & 31u;
+        }
     }
-    const uint32_t *rec = cells + LANE_REC_W + lane;
-    const uint32_t r0 = rec[0], minS = rec[32], c_cells = rec[64], c_written = rec[96], c_steps = rec[128], top = rec[160];
-    int status = (int)(r0 & 255u);
-    const bool first_eq = (r0 & 0x100u) != 0u;
-    const int my_si = (int)(r0 >> 16);
     int n = 0, m = 0;
     if (status == ST_OK) { const PairDesc pd = P.pairs[pair]; n = (int)pd.n; m = (int)pd.m; }
     const int Ak = m - n;
 
-    const uint32_t scratch_w = LANE_SCRATCH_W;
-    uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w) + lane;
     Result res;
     res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
     res.align_len = res.matches = res.gaps = res.gap_regions = 0; res.n_ops = 0;
     res.status = (uint8_t)status; res.pad_[0] = res.pad_[1] = res.pad_[2] = 0;
     uint32_t n_ops = 0;
+    /* ops beyond the shared-memory tier: the pair's column of the op scratch of its last slot */
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(slot_last) + lane_last;
     __syncwarp();
     if (status == ST_OK) {
-        LaneView A; A.hdr = hdrs; A.cells = cells + lane; A.si_last = my_si; A.c_si = -1; A.c_k = 0;
+        LaneView A; A.G = Gs; A.seg = seg + lane; A.si_last = my_si; A.c_si = -1; A.c_k = 0;
+        A.e0 = G.n_stages > 1 ? G.stage_end[0] : INT_MAX; A.e1 = G.n_stages > 2 ? G.stage_end[1] : INT_MAX; A.e2 = G.n_stages > 3 ? G.stage_end[2] : INT_MAX;
         A.c_w[0] = A.c_w[1] = A.c_w[2] = A.c_w[3] = A.c_w[4] = 0;
         A.n = n; A.m = m; A.xg = P.xg; A.oeg = P.oeg; A.eg = P.eg; A.first_eq = first_eq;
         LaneSink sink; sink.sbuf = sops + lane; sink.buf = scratch;
-        sink.cap = top > scratch_w ? (top - scratch_w) / 64u : 0u;
+        sink.cap = G.scratch_words / 64u;
         sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false;
         back_trace_inl(A, P, n, m, minS, Ak, res, sink);
         n_ops = sink.n;
         if (sink.overflow) { status = ST_ARENA; n_ops = 0; }
+        else if (sample) atomicAdd(&P.ctr->lane_hist[my_si & 63], 1u);
     }
     __syncwarp();
-    const uint32_t max_ops = __reduce_max_sync(FULL, n_ops);
     group_emit(P, have, pair, status, res, n_ops, LaneOps{sops + lane, scratch},
-               (unsigned long long)(slot_words - top + scratch_w) * 4ull + 256ull * (max_ops > LANE_SOPS ? max_ops - LANE_SOPS : 0u), c_cells, c_written, c_steps, acc);
+               (unsigned long long)G.slot_words[0] * 4ull, c_cells, c_written, c_steps, acc);
 }
 
 __global__ void __launch_bounds__(32 * WFA_LANE_WARPS)
-lane_kernel(const KParams P)
+lane_kernel(const KParams P, const int stg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wib = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
     unsigned char *smem = smem_raw + (size_t)wib * lane_smem_bytes(P.dM, P.dE, P.ring_cap, P.group);
-    if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(&P.ctr->t_first, t); }
+    if (stg == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin(&P.ctr->t_first, t); }
+    /* pairs entering this stage: the whole work list, or what the previous stage queued */
+    uint32_t n_in = P.n_work;
+    if (stg > 0) n_in = (uint32_t)min(P.ctr->lane_count[stg], (unsigned long long)P.la.cap[stg] * 32ull);
     for (;;) {
         uint32_t first = 0;
-        if (lane == 0) first = (uint32_t)atomicAdd(&P.ctr->work_next, 32ull);
+        if (lane == 0) first = (uint32_t)atomicAdd(&P.ctr->lane_count[4 + stg], 32ull);
         first = __shfl_sync(0xffffffffu, first, 0);
-        if (first >= P.n_work) break;
-        const bool have = first + lane < P.n_work;
-        const uint32_t pair = have ? (P.work ? P.work[first + lane] : P.pair_base + first + lane) : 0u;
-        lane_forward(P, have, pair, smem, P.arena + (uint64_t)(first >> 5) * P.slot_bytes, P.slot_bytes);   /* one slot per group */
+        if (first >= n_in) break;
+        const bool have = first + lane < n_in;
+        const uint32_t ticket = have ? (stg == 0 ? first + lane : P.la.list[stg][first + lane]) : 0u;
+        const uint32_t pair = have ? (P.work ? P.work[ticket] : P.pair_base + ticket) : 0u;
+        const uint32_t group = first >> 5;                                   /* one slot per group and stage */
+        lane_stage(P, stg, have, ticket, pair, smem, reinterpret_cast<uint32_t *>(P.la.arena[stg]) + (size_t)group * P.lg.slot_words[stg], group);
     }
     if (lane == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax(&P.ctr->t_last, t); }
 }
 
-/* One warp per group, many warps per SM: the backtrace is a chain of dependent arena reads, so
- * it runs here at full occupancy instead of inside the shared-memory-limited forward kernel. */
-__global__ void __launch_bounds__(32 * LANE_FINISH_WARPS, 10)
+/* One warp per 32 pairs, many warps per SM: the backtrace is a chain of dependent arena reads, so
+ * it runs here at high occupancy instead of inside the shared-memory-limited forward kernel. */
+__global__ void __launch_bounds__(32 * LANE_FINISH_WARPS, 8)
 lane_finish_kernel(const KParams P)
 {
-    __shared__ __align__(16) int2 hdr_s[LANE_FINISH_WARPS][LANE_HDR_ROWS];
+    __shared__ LaneGeomS geom_s;
+    __shared__ const uint32_t *seg_s[LANE_FINISH_WARPS][LANE_MAX_STAGES * 32];
     __shared__ uint16_t ops_s[LANE_FINISH_WARPS][LANE_SOPS * 32];
     const int wib = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) { geom_s.lo[i] = P.lg.lo[i]; geom_s.hi[i] = P.lg.hi[i]; geom_s.off[i] = P.lg.off[i]; }
+    __syncthreads();
     const uint32_t n_groups = (P.n_work + 31u) >> 5;
     WorkAcc acc; acc.cells = acc.written = acc.steps = acc.ops = acc.arena_max = 0;
     for (uint32_t g = blockIdx.x * LANE_FINISH_WARPS + wib; g < n_groups; g += gridDim.x * LANE_FINISH_WARPS) {
-        const uint32_t first = g << 5;
-        const bool have = first + lane < P.n_work;
-        const uint32_t pair = have ? (P.work ? P.work[first + lane] : P.pair_base + first + lane) : 0u;
+        const uint32_t ticket = (g << 5) + lane;
+        const bool have = ticket < P.n_work;
+        const uint32_t pair = have ? (P.work ? P.work[ticket] : P.pair_base + ticket) : 0u;
         __syncwarp();
-        lane_finish(P, have, pair, hdr_s[wib], ops_s[wib], P.arena + (uint64_t)g * P.slot_bytes, P.slot_bytes, &acc);
+        lane_finish(P, have, ticket, pair, &geom_s, seg_s[wib], ops_s[wib], (g & 15u) == 0u, &acc);
     }
     if (lane == 0) {
         atomicAdd(&P.ctr->cells, acc.cells); atomicAdd(&P.ctr->cells_written, acc.written);

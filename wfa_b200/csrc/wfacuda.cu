@@ -64,7 +64,10 @@ struct wfacuda_ctx {
     void *pinned[2] = {nullptr, nullptr}; size_t pinned_cap = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
-    double lane_scale = 1.0;       /* the same for the LANE class's group slots */
+    /* LANE class: sampled histogram of the score index at which the previous batch's pairs
+     * finished, and the stage boundaries taken from it */
+    uint64_t lane_hist[64] = {}; uint64_t lane_hist_n = 0;
+    int lane_bounds[3] = {0, 0, 0}; int lane_n_bounds = 0;
     int lane_occ = 0, lane_occ_sw = 0;   /* LANE kernel: resident blocks per SM for lane_occ_sw words per sequence */
     int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
     int occ_cache[2][2][8] = {};   /* [cta][bits==8][log2(ring_cap/64)+1]: blocks per SM, 0 = unknown */
@@ -533,20 +536,6 @@ bool lane_class_enabled(const wfacuda_ctx *ctx)
     return lane_smem_bytes(ctx->dM, ctx->dE, kLaneW, LANE_SEQ_WORDS) * WFA_LANE_WARPS * 2 <= ctx->smem_optin;
 }
 
-/* arena bytes of one group of 32 pairs as long as (n, m): 128 bytes per (score, diagonal) */
-uint64_t estimate_lane(const wfacuda_ctx *ctx, uint32_t n, uint32_t m)
-{
-    const wfacuda_config &c = ctx->cfg;
-    const double L = std::min(n, m), diag = (double)n + m - 1;
-    const double oe = (double)c.gap_open + c.gap_ext;
-    const double per_edit = (c.mismatch + 2.0 * oe) / 3.0;
-    const double score = 0.10 * L * per_edit + oe + std::abs((double)m - n) * c.gap_ext + 4.0 * c.mismatch;
-    const double rows = score / ctx->g + 2;
-    const double width_final = std::min(std::min(diag, 2.0 * score / c.gap_ext + 3), (double)kLaneW);
-    double bytes = rows * ((0.55 * width_final + 3) * 128.0 + 16.0) + 256.0 * ((n + m) / 8.0 + 16.0) + 64 * 32 * 4 + 4096;
-    return (uint64_t)(bytes * 1.3 * ctx->lane_scale);
-}
-
 int grow_ops_pool(wfacuda_ctx *ctx, uint64_t cursor)
 {
     /* grow the completion-order pool; what successful pairs wrote stays valid */
@@ -561,19 +550,69 @@ int grow_ops_pool(wfacuda_ctx *ctx, uint64_t cursor)
     return 0;
 }
 
+/* Row geometry of a LANE launch (LaneGeom): the loop range of `next` (wfa.go:557-563) for every
+ * score index, as the kernel's rings see it -- the union over both ways a pair can start
+ * (M[0][0] or M[x][0], wfa.go:155-158), clamped with the longest sequence of the class; the
+ * per-pair clamp to [-(n-1), m-1] stays in the kernel.  Rows are cut into stages at
+ * `bounds` (score indices, ascending), each stage with its own group slots. */
+void lane_geometry(const wfacuda_ctx *ctx, uint32_t maxlen, const std::vector<int> &bounds, uint32_t scratch_ops, LaneGeom *G)
+{
+    memset(G, 0, sizeof *G);
+    const int KC = kLaneW / 2, L = (int)std::max<uint32_t>(maxlen, 1);
+    /* which cells `next` can write at all: I[s][k] needs M[s-o-e][k-1] or I[s-e][k-1], D[s][k] needs
+     * M[s-o-e][k+1] or D[s-e][k+1], M[s][k] needs M[s-x][k], I[s][k] or D[s][k] (wfa.go:579-698),
+     * plus the init cell k = 0 at s = 0 and s = x.  Intervals; the row range is kept monotone
+     * (hull with the previous rows) so that a ring row always covers the row it replaces. */
+    struct Iv { int lo, hi; bool ok() const { return lo <= hi; } };
+    const Iv none{1, 0};
+    auto hull = [](Iv a, Iv b) { if (!a.ok()) return b; if (!b.ok()) return a; return Iv{std::min(a.lo, b.lo), std::max(a.hi, b.hi)}; };
+    auto shift = [](Iv a, int d) { return a.ok() ? Iv{a.lo + d, a.hi + d} : a; };
+    Iv Mv[64], Iw[64], Dv[64], run = none;
+    int n_rows = 0;
+    for (int si = 0; si < 64; si++) {
+        auto at = [&](Iv *v, int src) { return src >= 0 ? v[src] : none; };
+        Iw[si] = shift(hull(at(Mv, si - ctx->oeg), at(Iw, si - ctx->eg)), +1);
+        Dv[si] = shift(hull(at(Mv, si - ctx->oeg), at(Dv, si - ctx->eg)), -1);
+        Mv[si] = hull(hull(at(Mv, si - ctx->xg), Iw[si]), Dv[si]);
+        if (si == 0 || si == ctx->xg) Mv[si] = hull(Mv[si], Iv{0, 0});
+        for (Iv *v : {&Mv[si], &Iw[si], &Dv[si]}) if (v->ok()) { v->lo = std::max(v->lo, -(L - 1)); v->hi = std::min(v->hi, L - 1); if (!v->ok()) *v = none; }
+        Iv row = Mv[si];
+        if (row.ok()) { row = hull(row, run); run = row; }
+        if (row.ok() && (row.lo < -KC + 1 || row.hi > KC - 2)) break;     /* beyond the byte rings: WARP worker */
+        G->lo[si] = (int8_t)(row.ok() ? row.lo : 1); G->hi[si] = (int8_t)(row.ok() ? row.hi : 0);
+        n_rows = si + 1;
+    }
+    G->n_rows = n_rows;
+    int ns = 0;
+    for (int bd : bounds) if (ns < LANE_MAX_STAGES - 1 && bd >= 0 && bd < n_rows - 1 && (ns == 0 || bd > G->stage_end[ns - 1])) G->stage_end[ns++] = bd;
+    G->stage_end[ns++] = n_rows - 1;
+    G->n_stages = ns;
+    G->scratch_words = scratch_ops * 64u;                                   /* 8-byte ops, 32 lanes */
+    const int ring_rows = (ctx->dM - 1) + 2 * (ctx->dE - 1);
+    G->state_words = (uint32_t)(ring_rows * (kLaneW / 4) + 4);               /* 16-byte units: ring quarters, then the counters */
+    int si = 0;
+    for (int j = 0; j < ns; j++) {
+        uint32_t run = G->scratch_words / 32u;
+        for (; si <= G->stage_end[j]; si++)
+            if (G->lo[si] <= G->hi[si]) { G->off[si] = (uint16_t)run; run += (uint32_t)(G->hi[si] - G->lo[si] + 1); }
+        G->slot_words[j] = run * 32u;
+    }
+}
+
 /* Runs the LANE class; pairs whose wavefront outgrows the byte ring go to *to_warp, pairs
- * with a non-ACGT byte to *to_8bit, pairs out of arena / ops pool are re-queued here. */
+ * with a non-ACGT byte to *to_8bit, pairs out of op scratch / ops pool / stage room are
+ * re-queued here (single stage, larger scratch). */
 int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &order0, bool identity, KParams base,
                    std::vector<uint32_t> *to_warp, std::vector<uint32_t> *to_8bit)
 {
-    double boost = 1.0;
+    uint32_t scratch_ops = 32;
     const int threads = 32 * WFA_LANE_WARPS;
     std::vector<uint32_t> requeued;
     for (int attempt = 0; ; attempt++) {
         const std::vector<uint32_t> &order = attempt == 0 ? order0 : requeued;
         if (order.empty()) break;
         const bool ident = identity && attempt == 0;
-        if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
+        if (attempt > 8) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
         /* words per sequence in shared memory: the longest of the class + 1 for the funnel shift */
         const int sw = (int)((b->lane_maxlen + 15) / 16) + 1;
         const size_t smem = lane_smem_bytes(ctx->dM, ctx->dE, kLaneW, sw) * WFA_LANE_WARPS;
@@ -581,21 +620,47 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             ctx->lane_occ_sw = sw;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ, lane_kernel, threads, smem) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ = 1; }
         }
-        uint64_t need = 0;
-        const size_t sample = std::min<size_t>(order.size(), 4096);
-        for (size_t i = 0; i < sample; i++) need = std::max(need, estimate_lane(ctx, b->descs[order[i]].n, b->descs[order[i]].m));
-        uint64_t slot = ((uint64_t)((double)std::max<uint64_t>(need, 65536) * boost) + 255) & ~255ull;
-        /* one slot per GROUP (the finish kernel reads what the forward kernel left); when the
-         * arena budget does not hold all groups the class runs in rounds of as many groups as fit */
+        /* stages: where the previous batch's pairs finished (score-index quantiles); the first
+         * batch of a ctx, retries and tiny launches run in one stage */
+        std::vector<int> bounds;
         const uint64_t groups = (order.size() + 31) / 32;
-        const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
-        bool slot_at_max = false;
-        uint64_t round_groups = std::min<uint64_t>(groups, std::max<uint64_t>(1, budget / slot));
-        if (slot > budget) { slot = budget & ~255ull; slot_at_max = true; }
-        slot = std::min<uint64_t>(slot, 15ull << 30);
-        uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ) * WFA_LANE_WARPS;
+        const bool staged = attempt == 0 && ctx->lane_hist_n >= 256 && groups >= 64 && !getenv("WFACUDA_NO_STAGES");
+        if (staged) bounds.assign(ctx->lane_bounds, ctx->lane_bounds + ctx->lane_n_bounds);
+        KParams P = base;
+        lane_geometry(ctx, b->lane_maxlen, bounds, scratch_ops, &P.lg);
+        const LaneGeom &G = P.lg;
+        /* groups per stage: all of them enter stage 0; later stages are sized from the histogram
+         * (a pair that finds its next stage full is re-queued) */
+        double frac[LANE_MAX_STAGES] = {1.0, 1.0, 1.0, 1.0};
+        for (int j = 1; j < G.n_stages; j++) {
+            uint64_t later = 0;
+            for (int si = G.stage_end[j - 1] + 1; si < 64; si++) later += ctx->lane_hist[si];
+            frac[j] = std::min(1.0, 1.25 * (double)later / (double)std::max<uint64_t>(ctx->lane_hist_n, 1) + 0.02);
+        }
+        /* device memory per group of the round: its slots, the pairs' records, saved states and queue entries */
+        double per_group = 32.0 * (LANE_REC_WORDS * 4 + (G.n_stages > 1 ? G.state_words * 4 + 4 * (G.n_stages - 1) : 0));
+        for (int j = 0; j < G.n_stages; j++) per_group += frac[j] * G.slot_words[j] * 4.0;
+        const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0);
+        const uint64_t round_groups = std::min<uint64_t>(groups, std::max<uint64_t>(1, (uint64_t)((double)budget / per_group)));
+        if ((double)budget < per_group) {
+            /* not even one group fits: the WARP class places these pairs */
+            for (uint32_t pi : order) to_warp->push_back(pi);
+            break;
+        }
+        uint64_t cap[LANE_MAX_STAGES], arena_off[LANE_MAX_STAGES], total = 0;
+        for (int j = 0; j < G.n_stages; j++) {
+            cap[j] = j == 0 ? round_groups : std::min<uint64_t>(round_groups, (uint64_t)(frac[j] * (double)round_groups) + 8);
+            arena_off[j] = total; total += (cap[j] * G.slot_words[j] * 4 + 255) & ~255ull;
+        }
+        const uint64_t round_pairs = round_groups * 32;
+        const uint64_t rec_off = total; total += (round_pairs * LANE_REC_WORDS * 4 + 255) & ~255ull;
+        uint64_t state_off = total, list_off[LANE_MAX_STAGES] = {0, 0, 0, 0};
+        if (G.n_stages > 1) {
+            total += (round_pairs * G.state_words * 4 + 255) & ~255ull;
+            for (int j = 1; j < G.n_stages; j++) { list_off[j] = total; total += (cap[j] * 32 * 4 + 255) & ~255ull; }
+        }
         int rc;
-        if ((rc = ensure(ctx, ctx->arena, slot * round_groups))) return rc;
+        if ((rc = ensure(ctx, ctx->arena, total))) return rc;
         if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
         if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
@@ -604,62 +669,81 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         CU(ctx, dev_fill(&dc->arena_used_max, 0, 8, ctx->stream));
         CU(ctx, dev_fill(&dc->t_first, 0xff, 8, ctx->stream));
         CU(ctx, dev_fill(&dc->t_last, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(dc->lane_hist, 0, sizeof dc->lane_hist, ctx->stream));
+        uint8_t *abase = (uint8_t *)ctx->arena.p;
+        for (int j = 0; j < G.n_stages; j++) {
+            P.la.arena[j] = abase + arena_off[j]; P.la.cap[j] = (uint32_t)cap[j];
+            P.la.list[j] = j ? (uint32_t *)(abase + list_off[j]) : nullptr;
+        }
+        P.la.rec = (uint32_t *)(abase + rec_off); P.la.state = (uint32_t *)(abase + state_off);
+        P.arena = abase; P.slot_bytes = (uint64_t)G.slot_words[0] * 4; P.group = sw;      /* LANE kernel: group = words per sequence */
+        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
+        P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+        const uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ) * WFA_LANE_WARPS;
         const double tl0 = now_ms();
         int blocks = 0;
         for (uint64_t g0 = 0; g0 < groups; g0 += round_groups) {
             const uint64_t g1 = std::min(groups, g0 + round_groups);
             const uint64_t p0 = g0 * 32, p1 = std::min<uint64_t>(order.size(), g1 * 32);
-            CU(ctx, dev_fill(&dc->work_next, 0, 8, ctx->stream));
-            KParams P = base;
+            CU(ctx, dev_fill(dc->lane_count, 0, sizeof dc->lane_count, ctx->stream));
             P.work = ident ? nullptr : (const uint32_t *)ctx->work.p + p0; P.pair_base = (uint32_t)p0; P.n_work = (uint32_t)(p1 - p0);
-            P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = sw;      /* LANE kernel: group = words per sequence */
-            P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
-            P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
-            const uint64_t w = std::min<uint64_t>(workers, ((g1 - g0 + WFA_LANE_WARPS - 1) / WFA_LANE_WARPS) * WFA_LANE_WARPS);
-            blocks = (int)(w / WFA_LANE_WARPS);
-            lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P);
-            CU(ctx, cudaGetLastError());
+            for (int j = 0; j < G.n_stages; j++) {
+                const uint64_t gj = j == 0 ? g1 - g0 : std::min<uint64_t>(cap[j], g1 - g0);
+                const uint64_t w = std::min<uint64_t>(workers, ((gj + WFA_LANE_WARPS - 1) / WFA_LANE_WARPS) * WFA_LANE_WARPS);
+                blocks = (int)(w / WFA_LANE_WARPS);
+                lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P, j);
+                CU(ctx, cudaGetLastError());
+            }
             const int fblocks = (int)std::min<uint64_t>((g1 - g0 + LANE_FINISH_WARPS - 1) / LANE_FINISH_WARPS, (uint64_t)ctx->sm_count * 16);
             lane_finish_kernel<<<fblocks, 32 * LANE_FINISH_WARPS, 0, ctx->stream>>>(P);
             CU(ctx, cudaGetLastError());
-            ctx->stats.kernel_launches += 2; ctx->stats.align_launches++;
+            ctx->stats.kernel_launches += G.n_stages + 1; ctx->stats.align_launches++;
         }
         const double tl1 = now_ms();
-        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, slot * round_groups);
+        ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, total);
         Counters hc;
         { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
-        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   lane kernel: host launch at %.2f (took %.2f), sync returned %.2f ms since call; device span %.3f ms, device end = host %+.3f\n", tl0 - g_dbg_t0, tl1 - tl0, now_ms() - g_dbg_t0, (hc.t_last - hc.t_first) / 1e6, fmod(now_ms(), 1000.0) - (hc.t_last % 1000000000ull) / 1e6);
-        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d blocks x %d thr (%d/SM), smem %zu, group slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", attempt, order.size(), blocks, threads, ctx->lane_occ, smem, slot / 1024.0, ctx->lane_scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   lane kernels: host launch at %.2f (took %.2f), sync returned %.2f ms since call; device span %.3f ms\n", tl0 - g_dbg_t0, tl1 - tl0, now_ms() - g_dbg_t0, (hc.t_last - hc.t_first) / 1e6);
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d stages (ends %d %d %d %d; entered %llu %llu %llu), rows %d, slot0 %.1f KB, %.1f MB device, retry %llu\n", attempt, order.size(), G.n_stages, G.stage_end[0], G.stage_end[1], G.stage_end[2], G.stage_end[3], (unsigned long long)hc.lane_count[1], (unsigned long long)hc.lane_count[2], (unsigned long long)hc.lane_count[3], G.n_rows, G.slot_words[0] / 256.0, total / 1e6, (unsigned long long)hc.retry_n);
+        /* learn the next batch's stage boundaries: the score indices by which 30 %, 75 % and
+         * 92 % of the sampled pairs had finished (first attempt of a batch only) */
+        if (attempt == 0) {
+            uint64_t tot = 0;
+            for (int i = 0; i < 64; i++) tot += hc.lane_hist[i];
+            if (tot >= 256) {
+                for (int i = 0; i < 64; i++) ctx->lane_hist[i] = hc.lane_hist[i];
+                ctx->lane_hist_n = tot;
+                const double qs[3] = {0.30, 0.75, 0.92};
+                ctx->lane_n_bounds = 0;
+                uint64_t cum = 0; int qi = 0;
+                for (int i = 0; i < 64 && qi < 3; i++) {
+                    cum += hc.lane_hist[i];
+                    while (qi < 3 && (double)cum >= qs[qi] * (double)tot) {
+                        if (ctx->lane_n_bounds == 0 || ctx->lane_bounds[ctx->lane_n_bounds - 1] < i) ctx->lane_bounds[ctx->lane_n_bounds++] = i;
+                        qi++;
+                    }
+                }
+            }
+        }
         std::vector<uint64_t> rl(hc.retry_n);
         if (hc.retry_n) { int rc2 = fetch_small(ctx, rl.data(), ctx->retry.p, hc.retry_n * 8); if (rc2) return rc2; }
         std::vector<uint32_t> again;
-        bool ops_full = false, arena_full = false;
+        bool ops_full = false;
         for (uint64_t r : rl) {
             const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
             if (st == ST_RING) to_warp->push_back(pair);
             else if (st == ST_NEED8) to_8bit->push_back(pair);
-            else { again.push_back(pair); if (st == ST_OPS) ops_full = true; else arena_full = true; }
-        }
-        if (!arena_full && boost == 1.0 && !slot_at_max && slot > 65536 && hc.arena_used_max) {
-            /* learn: aim the next batch's group slots at 1.5x the largest use seen */
-            const double r = 1.5 * (double)hc.arena_used_max / (double)slot;
-            ctx->lane_scale = std::min(64.0, std::max(1.0 / 64, ctx->lane_scale * std::min(1.0, std::max(r, 0.25))));
+            else { again.push_back(pair); if (st == ST_OPS) ops_full = true; }
         }
         if (hc.retry_n == 0) break;
         ctx->stats.retries += (uint32_t)again.size();
         if (ops_full && (rc = grow_ops_pool(ctx, hc.ops_cursor))) return rc;
-        if (arena_full) {
-            if (slot_at_max) {
-                /* the whole budget is not enough for one group: let the WARP class place them */
-                std::vector<uint32_t> keep;
-                for (uint64_t r : rl) {
-                    if ((uint32_t)(r >> 32) == ST_ARENA) to_warp->push_back((uint32_t)r);
-                    else if ((uint32_t)(r >> 32) == ST_OPS) keep.push_back((uint32_t)r);
-                }
-                again.swap(keep);
-            } else boost *= 4.0;
-            ctx->lane_scale = std::min(64.0, ctx->lane_scale * 2.0);
+        if (scratch_ops >= 512) {
+            /* more ops than a LANE pair can have: let the WARP class place what is left */
+            for (uint32_t pi : again) to_warp->push_back(pi);
+            again.clear();
         }
+        scratch_ops *= 4;
         requeued.swap(again);
     }
     return 0;
@@ -791,7 +875,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->lane_scale = 1.0; ctx->lane_occ = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
