@@ -93,19 +93,25 @@ class ClockSampler:
 
 
 def ncu_traffic(kernel, workload, n_pairs):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    """DRAM bytes per step of the dominant kernel from the committed ncu --set full capture
     (profiles/r1_roofline.json, written by scripts/make_profiles.py); only quoted when this run
-    launches the kernel on the same workload and batch size as the capture."""
+    launches the kernel on the same workload and batch size as the capture.  The LANE class is
+    several launches per step (the stages of lane_kernel, then lane_finish_kernel): their sum.
+    Also returns the executed warp instructions of those launches (INT32-issue evidence)."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_roofline.json")))
     except Exception:
-        return None, None
+        return None, None, None
     size = {"cfg2": ("cfg2_150bp_e5_global", 1_000_000), "cfg3": ("cfg3_1kbp_e10_global_adaptive", 100_000)}
+    stem = "lane_" if kernel.startswith("lane") else kernel.split("<")[0]
+    traffic = instr = 0
     for key, v in d.get("kernels", {}).items():
         cfg, name = key.split(":", 1)
-        if size.get(cfg) == (workload, n_pairs) and kernel.split("<")[0] in name:
-            return int(v["dram_bytes"]), d.get("source")
-    return None, None
+        if size.get(cfg) == (workload, n_pairs) and stem in name:
+            traffic += int(v["dram_bytes"]); instr += int(v["warp_instructions"])
+    if not traffic:
+        return None, None, None
+    return traffic, d.get("source"), instr
 
 
 def algorithmic_bytes(stats, batch):
@@ -269,7 +275,7 @@ def main():
         achieved = B / k_sec / 1e9
         int_ops = 32 * stats["cells"] + 10 * stats["cells"] + 8 * stats["cells"]      # O = 32C + 10V + 8W with V,W ~ C
         kname = max((stats["pairs_lane"], "lane_kernel"), (stats["pairs_warp"], "align_kernel<warp>"), (stats["pairs_cta"], "align_kernel<cta>"))[1]
-        traffic, traffic_src = ncu_traffic(kname, workload, n_pairs)
+        traffic, traffic_src, ncu_instr = ncu_traffic(kname, workload, n_pairs)
         line = {
             "metric": "alignments_per_sec", "value": pairs_all / sec_step, "unit": "alignments/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_step * 1e3,
@@ -299,7 +305,11 @@ def main():
                                "peak": sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "Tops/s",
                                "frac": (int_ops / k_sec) / (sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
                                "algorithmic_ops_per_launch": int(int_ops),
-                               "note": "executed warp instructions and issue-slot utilisation of the same kernel: profiles/r1_ncu_summary.md"},
+                               # what the kernels really issue (committed ncu capture of this workload, all launches of
+                               # the class in one step): warp instructions x 32 lanes per second of the align phase
+                               "executed_warp_instructions": ncu_instr,
+                               "executed_frac": (ncu_instr * 32 / k_sec) / (sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6) if ncu_instr else None,
+                               "note": "executed warp instructions and issue-slot utilisation per kernel: profiles/r1_ncu_summary.md"},
             "device_ms_per_step": ms_dev / args.steps,
             "work": {"cells": int(stats["cells"]), "cells_written": int(stats["cells_written"]), "score_steps": int(stats["score_steps"]),
                      "ops": int(stats["ops"]), "retries": int(stats["retries"]), "pairs_lane": int(stats["pairs_lane"]), "pairs_warp": int(stats["pairs_warp"]),

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Turns the ncu reports / launch lists a GPU pass left under gpurun_out/<tag>/ into the tracked
-summaries under profiles/ (run here, no GPU needed):  make_profiles.py <tag> [round-prefix]"""
+summaries under profiles/ (run here, no GPU needed):  make_profiles.py <tag> [round-prefix]
+(prof_cfg2.ncu-rep = the LANE stages + finish kernel of one step, prof_cfg3.ncu-rep = the WARP kernel, launches_cfg2.csv = launch list)"""
 import csv, json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]; pre = sys.argv[2] if len(sys.argv) > 2 else "r1"
@@ -40,8 +41,11 @@ def summarize(rep, title, fh):
                     pass
         g = lambda k: (float(r[hdr.index(k)]), units[hdr.index(k)])
         rd, ru = g('dram__bytes_read.sum'); wr, wu = g('dram__bytes_write.sum'); t, tu = g('gpu__time_duration.sum')
-        res[name] = {"dram_bytes": rd * UNIT[ru] + wr * UNIT[wu], "duration_ms": t * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}[tu],
-                     "warp_instructions": float(r[hdr.index('smsp__inst_executed.sum')])}
+        # several launches of one kernel in a step (the LANE stages): summed
+        e = res.setdefault(name, {"dram_bytes": 0.0, "duration_ms": 0.0, "warp_instructions": 0.0, "launches": 0})
+        e["dram_bytes"] += rd * UNIT[ru] + wr * UNIT[wu]; e["duration_ms"] += t * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}[tu]
+        e["warp_instructions"] += float(r[hdr.index('smsp__inst_executed.sum')]); e["launches"] += 1
+        e["issue_active_pct_last"] = float(r[hdr.index('smsp__issue_active.avg.pct_of_peak_sustained_active')])
     return res
 
 
@@ -49,7 +53,7 @@ os.makedirs(dst, exist_ok=True)
 roof = {}
 with open(os.path.join(dst, "%s_ncu_summary.md" % pre), "w") as fh:
     fh.write("# ncu summaries (%s), from gpurun_out/%s — `ncu --set full --clock-control none --import-source on`\n" % (pre, tag))
-    fh.write("\nCommands: `scripts/gpu_round.sh %s ncu`.  Times under ncu are cold-cache, serialised; bench values come from `bench.py` runs without a profiler.\n" % tag)
+    fh.write("\nCommands: `WFACUDA_NO_PIPELINE=1 ncu --set full --clock-control none --import-source on -k regex:lane_ -s 7 -c 5 python bench.py --steps 1 --warmup 3 --no-cpu-baseline` (config 2: the four stage launches of `lane_kernel` and `lane_finish_kernel` of one step) and `... -k regex:align_kernel -s 3 -c 1 python bench.py --workload cfg3_1kbp_e10_global_adaptive --pairs 100000 ...` (config 3).  Times under ncu are cold-cache, serialised; bench values come from `bench.py` runs without a profiler.\n")
     for f, title in (("prof_cfg2.ncu-rep", "config 2 (1 M x 150 bp, global) dominant kernel"), ("prof_cfg3.ncu-rep", "config 3 (100 k x 1 kbp, adaptive) dominant kernel")):
         p = os.path.join(src, f)
         if os.path.exists(p):
@@ -57,7 +61,7 @@ with open(os.path.join(dst, "%s_ncu_summary.md" % pre), "w") as fh:
 json.dump({"source": "ncu --set full capture, gpurun_out/%s (see %s_ncu_summary.md)" % (tag, pre), "kernels": roof}, open(os.path.join(dst, "%s_roofline.json" % pre), "w"), indent=1)
 lp = os.path.join(src, "launches_cfg2.csv")
 if os.path.exists(lp):
-    rows = [r for r in csv.reader(open(lp)) if len(r) > 5 and r[0].isdigit()]
+    rows = [r for r in csv.reader(open(lp)) if len(r) > 5 and r[0].isdigit() and "gpu__time_duration" in r[-3]]
     per = {}
     for r in rows:
         per.setdefault(r[4], []).append(float(r[-1]) / 1e6)
