@@ -1,5 +1,6 @@
 """More GPU parity: ragged / degenerate inputs, both worker classes in one batch, context reuse,
 capacity errors, and size-independent properties at BASELINE sizes."""
+import os
 import random
 
 import numpy as np
@@ -201,6 +202,41 @@ def test_page_locked_buffers_and_ops_placement(built_lib):
     sample = batch_slice(batch, 0, 3000)
     ref = parity.oracle_batch(sample)
     parity.assert_same(sample, (r1[:3000], o1, off1[:3000]), ref, "pinned e2e vs oracle")
+
+
+def test_pipeline_graded_chunks_wire_descriptors_and_invalid_pairs(built_lib):
+    """A page-locked batch large enough for the graded chunk sizes of the pipeline (small first and
+    last chunks), whose workers send 20-byte wire descriptors: with empty sequences and non-ACGT
+    bytes sprinkled in, results equal the single-ctx path on ordinary arrays and the oracle."""
+    batch = datagen.generate(340_000, 150, 0.05, config=2)
+    q_len = batch.q_len.copy()
+    seq = batch.seq_bytes.copy()
+    empties = [0, 5, 6655, 6656, 6657, 46_000, 170_001, 339_999]              # incl. the first chunk boundaries
+    for i in empties:
+        q_len[i] = 0
+    for i in (1, 6660, 200_000, 339_998):
+        seq[int(batch.t_off[i]) + 3] = ord("N")
+    a = parity.make_aligner()
+    try:
+        host = [api.pinned_copy(x) for x in (seq, batch.q_off, q_len, batch.t_off, batch.t_len)]
+        r1, o1, off1 = a.align_arrays(*host, copy=True)
+        st = a.stats()
+        os.environ["WFACUDA_NO_PIPELINE"] = "1"
+        try:
+            r2, o2, off2 = a.align_arrays(seq, batch.q_off, q_len, batch.t_off, batch.t_len, copy=True)
+        finally:
+            del os.environ["WFACUDA_NO_PIPELINE"]
+    finally:
+        a.close()
+    assert st["pairs_8bit"] == 4 and (r1["status"][empties] == 1).all() and int((r1["status"] != 0).sum()) == len(empties)
+    for f in parity.FIELDS:
+        assert np.array_equal(r1[f], r2[f]), f
+    assert np.array_equal(parity.ops_in_index_order(r1, o1, off1), parity.ops_in_index_order(r2, o2, off2))
+    mod = datagen.Batch(seq, batch.q_off, q_len, batch.t_off, batch.t_len)
+    for lo, hi in ((0, 2000), (6000, 8000), (338_000, 340_000)):
+        sub = mod.slice(lo, hi)
+        ref = parity.oracle_batch(sub)
+        parity.assert_same(sub, (r1[lo:hi], o1, off1[lo:hi]), ref, "pipeline pairs %d..%d vs oracle" % (lo, hi))
 
 
 def batch_slice(batch, a, b):

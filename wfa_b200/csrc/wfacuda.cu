@@ -46,6 +46,27 @@ struct DevBuf { void *p = nullptr; size_t cap = 0; };
 
 } // namespace
 
+/* What a pipeline worker sends per pair instead of a 40-byte PairDesc: offsets relative to the
+ * chunk (32 bits are enough below 4 GB of sequence / 2^32 packed words per chunk); t_word follows
+ * from q_word and n.  expand_descs_kernel turns them into PairDescs on the device -- the e2e path
+ * is bound by host-to-device bytes, and this is 20 MB less per million pairs. */
+struct WireDesc { uint32_t q_byte, t_byte, q_word, n, m; };
+
+namespace {
+__global__ void expand_descs_kernel(const WireDesc *__restrict__ w, uint32_t n_pairs, PairDesc *__restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        const WireDesc d = w[i];
+        PairDesc o;
+        o.q_byte = d.q_byte; o.t_byte = d.t_byte; o.q_word = d.q_word;
+        o.t_word = (uint64_t)d.q_word + ((((uint64_t)d.n + 15) >> 4) + 3 & ~3ull);
+        o.n = d.n; o.m = d.m;
+        if (d.n == 0) { o.q_byte = o.t_byte = o.q_word = o.t_word = 0; o.m = 0; }
+        out[i] = o;
+    }
+}
+} // namespace
+
 struct wfacuda_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;     /* the stream work is issued on (normally stream_main) */
@@ -95,7 +116,8 @@ struct wfacuda_ctx {
     std::mutex h2d_mu;                 /* parent: serialises the enqueue + event record */
     wfacuda_ctx *h2d_parent = nullptr; /* worker: whose h2d_fifo to use */
     cudaEvent_t ev_h2d = nullptr;      /* worker: completion of its chunk's sequence upload */
-    PairDesc *pin_descs = nullptr; size_t pin_descs_cap = 0;   /* worker: page-locked descriptors, DMA'd without a staging copy */
+    WireDesc *pin_descs = nullptr; size_t pin_descs_cap = 0;   /* worker: page-locked wire descriptors, DMA'd without a staging copy */
+    DevBuf wire_dev;                                           /* their landing place on the device */
     const wfacuda_batch *pin_descs_owner = nullptr;
 };
 
@@ -105,8 +127,11 @@ struct wfacuda_batch {
     std::vector<uint32_t> order_warp, order_cta, order_lane;
     int identity_cls = -1;                  /* class (0 warp, 1 cta, 2 lane) whose order is 0..n-1: no work list needed */
     uint32_t lane_maxlen = 1;               /* longest sequence of the LANE class */
-    PairDesc *descs = nullptr;              /* descs_own's storage, or the ctx's page-locked descriptor buffer (pipeline workers) */
+    PairDesc *descs = nullptr;              /* descs_own's storage; nullptr when the batch was uploaded with wire descriptors */
     std::vector<PairDesc> descs_own;
+    const WireDesc *wire = nullptr;         /* pipeline workers: the ctx's page-locked wire descriptors (expanded on the device) */
+    uint32_t n_of(uint64_t i) const { return wire ? wire[i].n : descs[i].n; }
+    uint32_t m_of(uint64_t i) const { return wire ? wire[i].m : descs[i].m; }
     uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
     void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
     void *d_results = nullptr, *d_where = nullptr;
@@ -356,10 +381,10 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     /* the list is sorted longest first; a prefix sample bounds the estimate cheaply */
     const size_t sample = std::min<size_t>(order.size(), 4096);
     for (size_t i = 0; i < sample; i++) {
-        const PairDesc &d = b->descs[order[i]];
-        const Need nd = estimate(ctx, d.n, d.m);
+        const uint32_t dn = b->n_of(order[i]), dm = b->m_of(order[i]);
+        const Need nd = estimate(ctx, dn, dm);
         need_max = std::max(need_max, nd.arena); width_max = std::max(width_max, nd.width);
-        seq_words_max = std::max(seq_words_max, ((d.n + 15) >> 4) + ((d.m + 15) >> 4) + 2);
+        seq_words_max = std::max(seq_words_max, ((dn + 15) >> 4) + ((dm + 15) >> 4) + 2);
     }
     /* WARP worker, 2-bit: pairs of up to ~2 kbp keep their packed sequences in shared memory
      * (the kernel checks every pair against this capacity and reads longer ones from global) */
@@ -831,7 +856,7 @@ void wfacuda_destroy(wfacuda_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream_main) cudaStreamSynchronize(ctx->stream_main);
     if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
-    for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool}) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool, &ctx->wire_dev}) if (b->p) cudaFree(b->p);
     for (auto &f : ctx->free_dev) cudaFree(f.first);
     for (int i = 0; i < 2; i++) { if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]); if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]); }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -927,36 +952,47 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         if (ctx->pin_descs_cap < n_pairs) {
             if (ctx->pin_descs) cudaFreeHost(ctx->pin_descs);
             ctx->pin_descs = nullptr; ctx->pin_descs_cap = 0;
-            if (cudaHostAlloc((void **)&ctx->pin_descs, (n_pairs + n_pairs / 8) * sizeof(PairDesc), cudaHostAllocDefault) != cudaSuccess) {
+            if (cudaHostAlloc((void **)&ctx->pin_descs, (n_pairs + n_pairs / 8) * sizeof(WireDesc), cudaHostAllocDefault) != cudaSuccess) {
                 cudaGetLastError(); fail(ctx, WFACUDA_E_NOMEM, "page-locked descriptor buffer allocation failed"); delete b; return nullptr;
             }
             ctx->pin_descs_cap = n_pairs + n_pairs / 8;
         }
-        b->descs = ctx->pin_descs; ctx->pin_descs_owner = b;
-    } else { b->descs_own.resize(n_pairs); b->descs = b->descs_own.data(); }
+        ctx->pin_descs_owner = b;
+    }
     auto body = [&]() -> int {
         const double t0 = now_ms();
         ctx->stats = wfacuda_stats{};
         /* validation (wfa.go:202-209) + extent of the byte pool actually referenced */
         uint64_t lo = UINT64_MAX, hi = 0, words = 0;
         for (uint64_t i = 0; i < n_pairs; i++) {
-            PairDesc &d = b->descs[i];
-            d.n = q_len[i]; d.m = t_len[i]; d.q_byte = d.t_byte = d.q_word = d.t_word = 0;
-            if (d.n == 0 || d.m == 0) { b->host_status[i] = ST_EMPTY; d.n = d.m = 0; b->n_invalid++; continue; }
-            if (d.n > WFACUDA_MAX_SEQ_LEN || d.m > WFACUDA_MAX_SEQ_LEN) { b->host_status[i] = ST_TOO_LONG; d.n = d.m = 0; b->n_invalid++; continue; }
+            const uint32_t dn = q_len[i], dm = t_len[i];
+            if (dn == 0 || dm == 0) { b->host_status[i] = ST_EMPTY; b->n_invalid++; continue; }
+            if (dn > WFACUDA_MAX_SEQ_LEN || dm > WFACUDA_MAX_SEQ_LEN) { b->host_status[i] = ST_TOO_LONG; b->n_invalid++; continue; }
             lo = std::min(lo, std::min(q_off[i], t_off[i]));
-            hi = std::max(hi, std::max(q_off[i] + d.n, t_off[i] + d.m));
+            hi = std::max(hi, std::max(q_off[i] + dn, t_off[i] + dm));
+            words += (((uint64_t)((dn + 15) >> 4) + 3) & ~3ull) + (((uint64_t)((dm + 15) >> 4) + 3) & ~3ull);
         }
         if (lo == UINT64_MAX) { lo = 0; hi = 0; }
         const uint64_t base = lo & ~(uint64_t)15;            /* keep the caller's alignment mod 16 */
+        /* pipeline worker: 20-byte wire descriptors when the chunk's offsets fit 32 bits */
+        const bool wire = fifo && hi - base < 0xfffffff0ull && words < 0xfffffff0ull;
+        if (!wire) { b->descs_own.resize(n_pairs); b->descs = b->descs_own.data(); }
+        else b->wire = ctx->pin_descs;
+        words = 0;
+        const bool any_invalid = b->n_invalid != 0;
         for (uint64_t i = 0; i < n_pairs; i++) {
-            if (b->host_status[i] != ST_PENDING) continue;
-            PairDesc &d = b->descs[i];
-            d.q_byte = q_off[i] - base; d.t_byte = t_off[i] - base;
-            d.q_word = words; words += ((uint64_t)((d.n + 15) >> 4) + 3) & ~3ull;
-            d.t_word = words; words += ((uint64_t)((d.m + 15) >> 4) + 3) & ~3ull;
-            b->seq_bases += (uint64_t)d.n + d.m;
-            b->max_nm = std::max<uint64_t>(b->max_nm, (uint64_t)d.n + d.m);
+            const bool ok = !any_invalid || b->host_status[i] == ST_PENDING;
+            const uint32_t dn = ok ? q_len[i] : 0, dm = ok ? t_len[i] : 0;
+            const uint64_t qb = ok ? q_off[i] - base : 0, tb = ok ? t_off[i] - base : 0, qw = ok ? words : 0;
+            if (ok) {
+                words += ((uint64_t)((dn + 15) >> 4) + 3) & ~3ull;
+                b->seq_bases += (uint64_t)dn + dm;
+                b->max_nm = std::max<uint64_t>(b->max_nm, (uint64_t)dn + dm);
+            }
+            const uint64_t tw = ok ? words : 0;
+            if (ok) words += ((uint64_t)((dm + 15) >> 4) + 3) & ~3ull;
+            if (wire) { WireDesc &w = ctx->pin_descs[i]; w.q_byte = (uint32_t)qb; w.t_byte = (uint32_t)tb; w.q_word = (uint32_t)qw; w.n = dn; w.m = dm; }
+            else { PairDesc &d = b->descs[i]; d.q_byte = qb; d.t_byte = tb; d.q_word = qw; d.t_word = tw; d.n = dn; d.m = dm; }
         }
         b->raw_bytes = hi - base; b->packed_words = words;
         const double t1 = now_ms();
@@ -971,12 +1007,14 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             /* descriptors first, then the sequence bytes, queued together: the copy engine serves
              * copies in the order they were issued, whatever stream they are on */
             wfacuda_ctx *par = ctx->h2d_parent;
+            if (wire && (rc = ensure(ctx, ctx->wire_dev, n_pairs * sizeof(WireDesc)))) return rc;
             ctx->h2d_turn->acquire();            /* bounded queue depth: released when this chunk's copies are done */
             std::lock_guard<std::mutex> lk(par->h2d_mu);
-            CU(ctx, cudaMemcpyAsync(b->d_descs, b->descs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
+            if (wire) CU(ctx, cudaMemcpyAsync(ctx->wire_dev.p, ctx->pin_descs, n_pairs * sizeof(WireDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
+            else CU(ctx, cudaMemcpyAsync(b->d_descs, b->descs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
             if (b->raw_bytes) CU(ctx, cudaMemcpyAsync(b->d_raw, seq_bytes + base, b->raw_bytes, cudaMemcpyHostToDevice, par->h2d_fifo));
             CU(ctx, cudaEventRecord(ctx->ev_h2d, par->h2d_fifo));
-            ctx->stats.h2d_bytes += b->raw_bytes + n_pairs * sizeof(PairDesc);
+            ctx->stats.h2d_bytes += b->raw_bytes + n_pairs * (wire ? sizeof(WireDesc) : sizeof(PairDesc));
         } else if (b->raw_bytes) {
             if (ctx->h2d_turn && b->raw_bytes >= 65536 && is_pinned(seq_bytes + base)) {
                 struct Turn { wfacuda_ctx::Turns *t; Turn(wfacuda_ctx::Turns *t_) : t(t_) { t->acquire(); } ~Turn() { t->release(); } } turn(ctx->h2d_turn);
@@ -1003,7 +1041,7 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         int first_key = -1; bool uniform = true;
         for (uint64_t i = 0; i < n_pairs; i++) {
             if (b->host_status[i] != ST_PENDING) { key[i] = 255; uniform = false; continue; }
-            const PairDesc &d = b->descs[i];
+            const struct { uint32_t n, m; } d = {b->n_of(i), b->m_of(i)};
             const uint64_t nm = (uint64_t)d.n + d.m;
             const int lg = 63 - __builtin_clzll(nm | 1);
             const int bk = 63 - (2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1));
@@ -1044,6 +1082,10 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
          * event wait were seen to hold up the other workers' streams -- streams share hardware
          * queues); the copies queued behind these are not affected by when this thread wakes up */
         if (fifo) { const cudaError_t e = cudaEventSynchronize(ctx->ev_h2d); ctx->h2d_turn->release(); CU(ctx, e); }
+        if (b->wire && n_pairs) {
+            expand_descs_kernel<<<(int)std::min<uint64_t>((n_pairs + 255) / 256, 1184), 256, 0, ctx->stream>>>((const WireDesc *)ctx->wire_dev.p, (uint32_t)n_pairs, (PairDesc *)b->d_descs);
+            CU(ctx, cudaGetLastError());
+        }
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         if (dbg) fprintf(stderr, "[wfacuda] upload: validate+descs %.2f ms, alloc+seq h2d %.2f, descs h2d %.2f, binning %.2f, sync %.2f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now_ms() - t4);
         return 0;
@@ -1228,7 +1270,25 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     const bool src_pinned = is_pinned(seq_bytes);
     uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 16e6 : 24e6) / mean_bytes)));
     if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
-    const uint64_t n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+    /* Chunk boundaries.  Every worker validates its chunk before it can queue the upload, so the
+     * first chunks are small and double in size (the copy engine gets its first bytes after an
+     * eighth of a chunk's host work and is never idle afterwards), and the last ones shrink again:
+     * what is left to do when the last upload completes is one small chunk's kernels + download. */
+    std::vector<uint64_t> cuts{0};
+    {
+        const uint64_t C = chunk_pairs;
+        std::vector<uint64_t> head, tail;
+        if (n_pairs >= 6 * C && C >= 32768 && !getenv("WFACUDA_UNIFORM_CHUNKS")) { head = {C / 8, C / 4, C / 2}; tail = {C / 2, C / 4}; }
+        uint64_t used = 0;
+        for (uint64_t h : head) used += h;
+        for (uint64_t t : tail) used += t;
+        const uint64_t rem = n_pairs - used, nm = std::max<uint64_t>(1, (rem + C - 1) / C);
+        for (uint64_t h : head) cuts.push_back(cuts.back() + (h & ~31ull));
+        const uint64_t mid0 = cuts.back(), mid_total = n_pairs - mid0 - [&] { uint64_t t2 = 0; for (uint64_t t : tail) t2 += t & ~31ull; return t2; }();
+        for (uint64_t j = 1; j <= nm; j++) cuts.push_back(j == nm ? mid0 + mid_total : mid0 + ((mid_total * j / nm) & ~31ull));
+        for (size_t j = 0; j < tail.size(); j++) cuts.push_back(j + 1 == tail.size() ? n_pairs : cuts.back() + (tail[j] & ~31ull));
+    }
+    const uint64_t n_chunks = cuts.size() - 1;
     const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
     /* one worker per chunk in flight: enough of them that uploads (PCIe-bound, taken in turns)
      * never wait for a worker that is still computing or downloading */
@@ -1273,7 +1333,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         for (;;) {
             const uint64_t c = next.fetch_add(1);
             if (c >= n_chunks || first_err.load()) break;
-            const uint64_t a = c * chunk_pairs, cnt = std::min(chunk_pairs, n_pairs - a);
+            const uint64_t a = cuts[c], cnt = cuts[c + 1] - cuts[c];
             const double w0 = now_ms();
             wfacuda_batch *b = wfacuda_batch_upload(sub, cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
             const double w1 = now_ms();
@@ -1303,7 +1363,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     ctx->stats = total;
     ctx->last_ops_total = cursor.load();
     if (getenv("WFACUDA_DEBUG")) {
-        fprintf(stderr, "[wfacuda] align_batch: %llu chunks of %llu pairs on %d workers, %.2f ms; per worker upload/run/download ms:",
+        fprintf(stderr, "[wfacuda] align_batch: %llu chunks of up to %llu pairs on %d workers, %.2f ms; per worker upload/run/download ms:",
                 (unsigned long long)n_chunks, (unsigned long long)chunk_pairs, K, now_ms() - t_begin);
         for (int k = 0; k < K; k++) fprintf(stderr, " %.1f/%.1f/%.1f", t_up[k], t_run[k], t_down[k]);
         fprintf(stderr, "\n");
