@@ -180,7 +180,7 @@ __device__ __forceinline__ Cell3O next_off3(uint32_t mo_l, uint32_t ie_l, uint32
 __device__ __forceinline__ uint32_t lane_chunk(uint32_t seq_sa, int pos)
 {
     const uint32_t a = seq_sa + ((uint32_t)pos >> 4) * 128u;
-    return __funnelshift_r(lds_u32(a), lds_u32(a + 128u), ((uint32_t)pos & 15u) * 2u);
+    return __funnelshift_r(lds_u32(a), lds_u32(a + 128u), (uint32_t)pos * 2u);     /* the shift count wraps at 32: (pos % 16) * 2 */
 }
 
 /* extend (wfa.go:394-455) of one M offset on diagonal k: returns the extended offset */
@@ -266,13 +266,16 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
     const int clamp_lo = -(__reduce_min_sync(FULL, act ? n : INT_MAX) - 1), clamp_hi = __reduce_min_sync(FULL, act ? m : INT_MAX) - 1;
 
     const int si0 = stg == 0 ? 0 : G.stage_end[stg - 1] + 1, si1 = G.stage_end[stg];
-    const int ring_rows = RM + 2 * RE, wpr = W >> 2;                     /* saved state: ring_rows x wpr words of 4 columns each */
+    /* saved state of a pair: ring_rows x 16 words of 4 columns each, in the frame of a 64-column
+     * ring (diagonal k in column k + 32) whatever this stage's own ring width is -- a stage whose
+     * rows are narrow runs with fewer columns (more warps per SM) and shifts by wshift words */
+    const int ring_rows = RM + 2 * RE, wpr = W >> 2, wshift = (32 - KC) >> 2;
     bool done = false; uint32_t minS = 0; int my_si = 0;
     uint32_t c_cells = 0, c_written = 0, c_steps = 0;
     /* ring columns (in words of 4) that hold anything after row sb: those of the last row that exists up to sb */
     auto ring_span = [&](int sb, int &c0, int &c1) {
         while (sb > 0 && G.lo[sb] > G.hi[sb]) sb--;
-        c0 = (G.lo[sb] + KC) >> 2; c1 = (G.hi[sb] + KC) >> 2;
+        c0 = (G.lo[sb] + 32) >> 2; c1 = (G.hi[sb] + 32) >> 2;
     };
     if (stg > 0 && act) {
         /* rings as the previous stage left them; only the columns its last row could reach.  A
@@ -280,18 +283,18 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
          * together (each lane reads its own pair's record, so every load is a DRAM round trip) */
         const uint4 *st = reinterpret_cast<const uint4 *>(P.la.state + (size_t)ticket * G.state_words);
         int cw0, cw1; ring_span(si0 - 1, cw0, cw1);
-        const int q0 = cw0 >> 2, q1 = cw1 >> 2, qpr = wpr >> 2;
+        const int q0 = cw0 >> 2, q1 = cw1 >> 2, qpr = 4;
 #pragma unroll 1
         for (int r = 0; r < ring_rows; r++) {
             uint4 v[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = (q >= q0 && q <= q1 && q < qpr) ? st[r * qpr + q] : make_uint4(0u, 0u, 0u, 0u);
+            for (int q = 0; q < 4; q++) v[q] = (q >= q0 && q <= q1) ? st[r * qpr + q] : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const uint32_t w4[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
 #pragma unroll
-                for (int j = 0; j < 4; j++) if (w4[j]) {
-                    const uint32_t a = ringL + (uint32_t)r * rowB + (uint32_t)(q * 4 + j) * 128u;
+                for (int j = 0; j < 4; j++) if (w4[j] && (uint32_t)(q * 4 + j - wshift) < (uint32_t)wpr) {
+                    const uint32_t a = ringL + (uint32_t)r * rowB + (uint32_t)(q * 4 + j - wshift) * 128u;
                     sts_u8o<0>(a, w4[j] & 255u); sts_u8o<32>(a, (w4[j] >> 8) & 255u); sts_u8o<64>(a, (w4[j] >> 16) & 255u); sts_u8o<96>(a, w4[j] >> 24);
                 }
             }
@@ -326,27 +329,29 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
                     const bool inb = (uint32_t)(k - klo) <= kspan;
                     q.c = next_off3(mo_l, ie_l, mo_r, de_r, mx, inb ? um : 0u, inb ? (uint32_t)(n + k) : 0u);
                 } else q.c = next_off3(mo_l, ie_l, mo_r, de_r, mx, um, (uint32_t)(n + k));
+                /* extend applies iff the cell exists, v > 0, v < n and h < m (wfa.go:404).  A present
+                 * cell always has v >= 1: the start cell is (1, 1) and every step of next / extend
+                 * keeps or raises v -- so the test is "exists and min(n - v, m - h) > 0". */
                 const int h = (int)q.c.M, v = h - k;
-                const bool ex = q.c.M != 0 && v > 0 && v < n && h < m;                /* extend applies (wfa.go:404) */
-                q.ext = ex ? min(n - v, m - h) : 0;
+                q.ext = q.c.M != 0u ? max(min(n - v, m - h), 0) : 0;
                 /* positions are only meaningful when ex; masked so that the loads stay inside the block */
                 q.xr = lane_chunk(sQ, v & 255) ^ lane_chunk(sT, h);
                 return q;
             };
             /* phase B: rest of extend (wfa.go:411-454) */
             auto cell_b = [&](Pend &q, const int k) {
-                if (q.ext) {
-                    int l = q.xr ? (__ffs((int)q.xr) - 1) >> 1 : 16;
-                    if (q.xr == 0 && q.ext > 16) {
-                        const int h = (int)q.c.M, v = h - k;
-                        while (l < q.ext) {
-                            const uint32_t xx = lane_chunk(sQ, v + l) ^ lane_chunk(sT, h + l);
-                            if (xx) { l += (__ffs((int)xx) - 1) >> 1; break; }
-                            l += 16;
-                        }
+                /* bases matched by the first compare: index of the lowest differing bit pair, 16 when
+                 * there is none (brev(0) = 0 has 32 leading zeros).  ext = 0 adds nothing. */
+                int l = __clz((int)__brev(q.xr)) >> 1;
+                if (l == 16 && q.ext > 16) {
+                    const int h = (int)q.c.M, v = h - k;
+                    while (l < q.ext) {
+                        const uint32_t xx = lane_chunk(sQ, v + l) ^ lane_chunk(sT, h + l);
+                        if (xx) { l += __clz((int)__brev(xx)) >> 1; break; }
+                        l += 16;
                     }
-                    q.c.M += (uint32_t)min(l, q.ext);
                 }
+                q.c.M += (uint32_t)min(l, q.ext);
             };
             auto row = [&](auto clamp) {
                 int k = lo;
@@ -427,7 +432,7 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
                     P.la.list[stg + 1][pos] = ticket;
                     uint4 *st = reinterpret_cast<uint4 *>(P.la.state + (size_t)ticket * G.state_words);
                     int cw0, cw1; ring_span(si1, cw0, cw1);
-                    const int q0 = cw0 >> 2, q1 = cw1 >> 2, qpr = wpr >> 2;
+                    const int q0 = cw0 >> 2, q1 = cw1 >> 2, qpr = 4;
 #pragma unroll 1
                     for (int r = 0; r < ring_rows; r++)
 #pragma unroll 1
@@ -435,8 +440,11 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
                             uint32_t w4[4];
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const uint32_t a = ringL + (uint32_t)r * rowB + (uint32_t)(q * 4 + j) * 128u;
-                                w4[j] = lds_u8o<0>(a) | lds_u8o<32>(a) << 8 | lds_u8o<64>(a) << 16 | lds_u8o<96>(a) << 24;
+                                w4[j] = 0u;
+                                if ((uint32_t)(q * 4 + j - wshift) < (uint32_t)wpr) {
+                                    const uint32_t a = ringL + (uint32_t)r * rowB + (uint32_t)(q * 4 + j - wshift) * 128u;
+                                    w4[j] = lds_u8o<0>(a) | lds_u8o<32>(a) << 8 | lds_u8o<64>(a) << 16 | lds_u8o<96>(a) << 24;
+                                }
                             }
                             st[r * qpr + q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                         }

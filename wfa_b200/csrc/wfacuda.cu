@@ -89,7 +89,7 @@ struct wfacuda_ctx {
      * finished, and the stage boundaries taken from it */
     uint64_t lane_hist[64] = {}; uint64_t lane_hist_n = 0;
     int lane_bounds[3] = {0, 0, 0}; int lane_n_bounds = 0;
-    int lane_occ = 0, lane_occ_sw = 0;   /* LANE kernel: resident blocks per SM for lane_occ_sw words per sequence */
+    int lane_occ[2] = {0, 0}, lane_occ_sw = 0;   /* LANE kernel: resident blocks per SM for lane_occ_sw words per sequence, rings of 64 / 48 columns */
     int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
     int occ_cache[2][2][8] = {};   /* [cta][bits==8][log2(ring_cap/64)+1]: blocks per SM, 0 = unknown */
     uint64_t budget_cache = 0;     /* arena budget; refreshed when the arena has to grow */
@@ -640,10 +640,16 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         if (attempt > 8) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
         /* words per sequence in shared memory: the longest of the class + 1 for the funnel shift */
         const int sw = (int)((b->lane_maxlen + 15) / 16) + 1;
-        const size_t smem = lane_smem_bytes(ctx->dM, ctx->dE, kLaneW, sw) * WFA_LANE_WARPS;
+        /* ring columns per stage: a stage whose rows all fit 48 columns (diagonals -23..22) runs
+         * with the narrower ring -- 12 KB instead of 15 KB of shared memory per warp, 9 instead
+         * of 7 blocks per SM */
+        const int ring_w[2] = {kLaneW, 48};
+        size_t smem_w[2];
+        for (int i = 0; i < 2; i++) smem_w[i] = lane_smem_bytes(ctx->dM, ctx->dE, ring_w[i], sw) * WFA_LANE_WARPS;
         if (ctx->lane_occ_sw != sw) {
             ctx->lane_occ_sw = sw;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ, lane_kernel, threads, smem) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ = 1; }
+            for (int i = 0; i < 2; i++)
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ[i], lane_kernel, threads, smem_w[i]) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ[i] = 1; }
         }
         /* stages: where the previous batch's pairs finished (score-index quantiles); the first
          * batch of a ctx, retries and tiny launches run in one stage */
@@ -704,7 +710,15 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         P.arena = abase; P.slot_bytes = (uint64_t)G.slot_words[0] * 4; P.group = sw;      /* LANE kernel: group = words per sequence */
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
-        const uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ) * WFA_LANE_WARPS;
+        int stage_w[LANE_MAX_STAGES];
+        {
+            int si = 0;
+            for (int j = 0; j < G.n_stages; j++) {
+                bool narrow = !getenv("WFACUDA_LANE_W64");
+                for (; si <= G.stage_end[j]; si++) if (G.lo[si] <= G.hi[si] && (G.lo[si] < -23 || G.hi[si] > 22)) narrow = false;
+                stage_w[j] = narrow ? 1 : 0;
+            }
+        }
         const double tl0 = now_ms();
         int blocks = 0;
         for (uint64_t g0 = 0; g0 < groups; g0 += round_groups) {
@@ -714,9 +728,11 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             P.work = ident ? nullptr : (const uint32_t *)ctx->work.p + p0; P.pair_base = (uint32_t)p0; P.n_work = (uint32_t)(p1 - p0);
             for (int j = 0; j < G.n_stages; j++) {
                 const uint64_t gj = j == 0 ? g1 - g0 : std::min<uint64_t>(cap[j], g1 - g0);
+                const uint64_t workers = (uint64_t)ctx->sm_count * std::max(1, ctx->lane_occ[stage_w[j]]) * WFA_LANE_WARPS;
                 const uint64_t w = std::min<uint64_t>(workers, ((gj + WFA_LANE_WARPS - 1) / WFA_LANE_WARPS) * WFA_LANE_WARPS);
                 blocks = (int)(w / WFA_LANE_WARPS);
-                lane_kernel<<<blocks, threads, smem, ctx->stream>>>(P, j);
+                P.ring_cap = ring_w[stage_w[j]];
+                lane_kernel<<<blocks, threads, smem_w[stage_w[j]], ctx->stream>>>(P, j);
                 CU(ctx, cudaGetLastError());
             }
             const int fblocks = (int)std::min<uint64_t>((g1 - g0 + LANE_FINISH_WARPS - 1) / LANE_FINISH_WARPS, (uint64_t)ctx->sm_count * 16);
@@ -900,7 +916,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -1260,7 +1276,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         if (rc == 0 || rc == WFACUDA_E_OPS_CAPACITY) return rc;
         return rc;
     }
-    /* chunk size: about 16 MB of sequence (0.3 ms of PCIe), at least kMinChunk pairs */
+    /* chunk size: about 20 MB of sequence (0.45 ms of PCIe; ~one full wave of the LANE kernel for 150 bp reads), at least kMinChunk pairs */
     uint64_t sample_bytes = 0;
     const uint64_t sample_n = std::min<uint64_t>(n_pairs, 4096);
     for (uint64_t i = 0; i < sample_n; i++) sample_bytes += (uint64_t)q_len[i * (n_pairs / sample_n)] + t_len[i * (n_pairs / sample_n)];
@@ -1268,7 +1284,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     /* pageable caller memory is staged by the workers themselves (host memcpy, memory-bound):
      * fewer, larger chunks there */
     const bool src_pinned = is_pinned(seq_bytes);
-    uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 16e6 : 24e6) / mean_bytes)));
+    uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 20e6 : 24e6) / mean_bytes)));
     if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
     /* Chunk boundaries.  Every worker validates its chunk before it can queue the upload, so the
      * first chunks are small and double in size (the copy engine gets its first bytes after an
