@@ -166,10 +166,11 @@ __device__ __forceinline__ Cell3O next_off3(uint32_t mo_l, uint32_t ie_l, uint32
                                             uint32_t um, uint32_t ubk)
 {
     Cell3O r;
-    const uint32_t a = (mo_l - 1u) < um ? mo_l : 0u, b = (ie_l - 1u) < um ? ie_l : 0u;
+    /* a source is valid iff 1 <= offset <= bound; an absent source (0) may pass the test, it selects 0 either way */
+    const uint32_t a = mo_l <= um ? mo_l : 0u, b = ie_l <= um ? ie_l : 0u;
     const uint32_t mi = max(a, b);
     r.I = mi + (mi != 0u);
-    const uint32_t c = (mo_r - 1u) < ubk ? mo_r : 0u, d = (de_r - 1u) < ubk ? de_r : 0u;
+    const uint32_t c = mo_r <= ubk ? mo_r : 0u, d = de_r <= ubk ? de_r : 0u;
     r.D = max(c, d);
     const uint32_t e = (mx - 1u) < min(um, ubk) ? mx + 1u : 0u;
     r.M = max(max(e, r.I), r.D);
