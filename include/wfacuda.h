@@ -152,6 +152,23 @@ int  wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *
 uint64_t wfacuda_batch_ops_total(const wfacuda_batch *b);
 void wfacuda_batch_free(wfacuda_ctx *ctx, wfacuda_batch *b);
 
+/* (*AlignmentResult).CIGAR(onlyAignedRegion) (wfa_cigar.go:236-257) and AlignmentText
+ * (wfa_cigar.go:261-333, incl. trimOps :217-233) for every pair of a batch, rendered on the GPU
+ * from what wfacuda_batch_run left in HBM (call it before the next run on the same ctx).
+ *   cigar / cigar_capacity     receives the CIGAR bytes of all pairs, no terminators
+ *   cigar_off / cigar_len[n]   pair i's string is cigar[cigar_off[i], cigar_off[i] + cigar_len[i])
+ *   text / text_capacity       receives the alignment text; NULL skips it (text_off / text_len unused)
+ *   text_off / text_len[n]     pair i's lines Q, A, T (query, '|' marks, target) have text_len[i] bytes
+ *                              each and start at text_off[i] + j * text_len[i], j = 0, 1, 2
+ * Pairs with status != 0 get empty strings, and so does the aligned region of an alignment without
+ * any M (the reference's trimOps slices ops[-1:0] there and panics).  The order of the pairs'
+ * strings in the buffers is unspecified, like that of the ops.  WFACUDA_E_OPS_CAPACITY: a buffer is
+ * too small, wfacuda_last_render_total() then tells the sizes needed. */
+int wfacuda_batch_render(wfacuda_ctx *ctx, wfacuda_batch *b, int only_aligned_region,
+                         uint8_t *cigar, uint64_t cigar_capacity, uint64_t *cigar_off, uint32_t *cigar_len,
+                         uint8_t *text, uint64_t text_capacity, uint64_t *text_off, uint32_t *text_len);
+void wfacuda_last_render_total(const wfacuda_ctx *ctx, uint64_t *cigar_bytes, uint64_t *text_bytes);
+
 /* One host thread per device, work-balanced static sharding, no collective
  * (pairs are independent): the C side of AlignBatch over several GPUs. */
 int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs,

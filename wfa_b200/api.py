@@ -99,7 +99,8 @@ EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda
            "wfacuda_align_batch", "wfacuda_last_ops_total", "wfacuda_batch_upload", "wfacuda_batch_run",
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
            "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error",
-           "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister"]
+           "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister",
+           "wfacuda_batch_render", "wfacuda_last_render_total"]
 
 _LIB = None
 
@@ -132,6 +133,9 @@ def load_library():
     L.wfacuda_batch_ops_total.restype = u64
     L.wfacuda_batch_ops_total.argtypes = [vp]
     L.wfacuda_batch_free.argtypes = [vp, vp]
+    L.wfacuda_batch_render.restype = C.c_int
+    L.wfacuda_batch_render.argtypes = [vp, vp, C.c_int, vp, u64, vp, vp, vp, u64, vp, vp]
+    L.wfacuda_last_render_total.argtypes = [vp, vp, vp]
     L.wfacuda_align_batch_multi.restype = C.c_int
     L.wfacuda_align_batch_multi.argtypes = [C.POINTER(vp), C.c_int, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
     L.wfacuda_shard_plan.restype = C.c_int
@@ -425,6 +429,22 @@ def RecycleAlignmentText(Q, A, T):              # wfa_cigar.go:346-360
     return None
 
 
+class RenderedBatch:
+    """Strings of a batch as wfacuda_batch_render left them: byte buffers + per-pair offsets."""
+
+    def __init__(self, cigar, cigar_off, cigar_len, text, text_off, text_len):
+        self.cigar, self.cigar_off, self.cigar_len = cigar, cigar_off, cigar_len
+        self.text, self.text_off, self.text_len = text, text_off, text_len
+
+    def CIGAR(self, i):
+        o, n = int(self.cigar_off[i]), int(self.cigar_len[i])
+        return self.cigar[o:o + n].tobytes().decode("latin-1")
+
+    def AlignmentText(self, i):
+        o, n = int(self.text_off[i]), int(self.text_len[i])
+        return tuple(self.text[o + j * n:o + (j + 1) * n].tobytes() for j in range(3))
+
+
 class ResidentBatch:
     """upload / run / download split (wfacuda_batch_*): keeps a batch in HBM."""
 
@@ -455,6 +475,28 @@ class ResidentBatch:
         if rc != 0:
             raise WfaError("wfacuda_batch_download failed (%d): %s" % (rc, self.algn._err()))
         return results, ops[:total], ops_off
+
+    def render(self, onlyAignedRegion=False, text=True):
+        """CIGAR strings and AlignmentText lines of every pair, rendered on the GPU
+        (wfacuda_batch_render; wfa_cigar.go:236-333).  Returns a RenderedBatch."""
+        L = self.algn._L
+        n = self.n
+        c_off, c_len = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        t_off, t_len = np.zeros(n, np.uint64), np.zeros(n, np.uint32)
+        cig, txt = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+        for _ in range(2):      # first call sizes the buffers (WFACUDA_E_OPS_CAPACITY), second fills them
+            rc = L.wfacuda_batch_render(self.algn._ctx, self._b, int(bool(onlyAignedRegion)),
+                                        cig.ctypes.data, len(cig), c_off.ctypes.data, c_len.ctypes.data,
+                                        txt.ctypes.data if text else None, len(txt) if text else 0,
+                                        t_off.ctypes.data if text else None, t_len.ctypes.data if text else None)
+            if rc != -4:
+                break
+            a, b = C.c_uint64(0), C.c_uint64(0)
+            L.wfacuda_last_render_total(self.algn._ctx, C.byref(a), C.byref(b))
+            cig, txt = np.zeros(max(a.value, 1), np.uint8), np.zeros(max(b.value, 1), np.uint8)
+        if rc != 0:
+            raise WfaError("wfacuda_batch_render failed (%d): %s" % (rc, self.algn._err()))
+        return RenderedBatch(cig, c_off, c_len, txt if text else None, t_off, t_len)
 
     def free(self):
         if self._b:

@@ -15,6 +15,7 @@
 #include "../../include/wfacuda.h"
 #include "wfa_kernels.cuh"
 #include "wfa_lane.cuh"
+#include "wfa_render.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -118,6 +119,8 @@ struct wfacuda_ctx {
     cudaEvent_t ev_h2d = nullptr;      /* worker: completion of its chunk's sequence upload */
     WireDesc *pin_descs = nullptr; size_t pin_descs_cap = 0;   /* worker: page-locked wire descriptors, DMA'd without a staging copy */
     DevBuf wire_dev;                                           /* their landing place on the device */
+    DevBuf render_meta, render_cigar, render_text;             /* wfacuda_batch_render: offsets / lengths / cursors, strings */
+    uint64_t render_cigar_total = 0, render_text_total = 0;
     const wfacuda_batch *pin_descs_owner = nullptr;
 };
 
@@ -872,7 +875,7 @@ void wfacuda_destroy(wfacuda_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream_main) cudaStreamSynchronize(ctx->stream_main);
     if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
-    for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool, &ctx->wire_dev}) if (b->p) cudaFree(b->p);
+    for (DevBuf *b : {&ctx->arena, &ctx->retry, &ctx->work, &ctx->ctr, &ctx->ops_pool, &ctx->wire_dev, &ctx->render_meta, &ctx->render_cigar, &ctx->render_text}) if (b->p) cudaFree(b->p);
     for (auto &f : ctx->free_dev) cudaFree(f.first);
     for (int i = 0; i < 2; i++) { if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]); if (ctx->pin_ev[i]) cudaEventDestroy(ctx->pin_ev[i]); }
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1235,6 +1238,72 @@ int wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *r
     CU(ctx, cudaStreamSynchronize(ctx->stream));       /* copies into page-locked caller memory were left in flight */
     if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] download: %.2f ms for %.1f MB\n", now_ms() - t0, ctx->stats.d2h_bytes / 1e6);
     return 0;
+}
+
+/* CIGAR strings and alignment text of a batch that has been run (wfa_cigar.go:217-333), rendered
+ * by the kernels of wfa_render.cuh from what the run left in HBM. */
+int wfacuda_batch_render(wfacuda_ctx *ctx, wfacuda_batch *b, int only_aligned_region,
+                         uint8_t *cigar, uint64_t cigar_capacity, uint64_t *cigar_off, uint32_t *cigar_len,
+                         uint8_t *text, uint64_t text_capacity, uint64_t *text_off, uint32_t *text_len)
+{
+    if (!ctx || !b) return fail(ctx, WFACUDA_E_INVALID, "NULL ctx or batch");
+    if (!b->ran || ctx->pool_owner != b) return fail(ctx, WFACUDA_E_INVALID, "render needs the batch that ran last on this ctx (its ops live in the ctx's pool)");
+    const uint64_t n = b->n_pairs;
+    if (n && (!cigar_off || !cigar_len)) return fail(ctx, WFACUDA_E_INVALID, "cigar_off / cigar_len are NULL");
+    if (text && n && (!text_off || !text_len)) return fail(ctx, WFACUDA_E_INVALID, "text_off / text_len are NULL");
+    CU(ctx, cudaSetDevice(ctx->device));
+    ctx->render_cigar_total = ctx->render_text_total = 0;
+    if (n == 0) return 0;
+    int rc;
+    /* meta: cursors[2] | cigar_off[n] | text_off[n] | cigar_len[n] | text_len[n] */
+    if ((rc = ensure(ctx, ctx->render_meta, 16 + n * 24))) return rc;
+    uint8_t *meta = (uint8_t *)ctx->render_meta.p;
+    RenderParams R{};
+    R.pairs = (const PairDesc *)b->d_descs; R.results = (const Result *)b->d_results;
+    R.ops_pool = (const uint64_t *)ctx->ops_pool.p; R.ops_where = (const uint64_t *)b->d_where;
+    R.raw = (const uint8_t *)b->d_raw; R.n_pairs = (uint32_t)n; R.only_aligned = only_aligned_region ? 1 : 0;
+    R.cursors = (unsigned long long *)meta;
+    R.cigar_off = (uint64_t *)(meta + 16); R.text_off = R.cigar_off + n;
+    R.cigar_len = (uint32_t *)(R.text_off + n); R.text_len = R.cigar_len + n;
+    CU(ctx, dev_fill(meta, 0, 16, ctx->stream));
+    const int blocks = (int)((n + 255) / 256);
+    render_measure_kernel<<<blocks, 256, 0, ctx->stream>>>(R);
+    CU(ctx, cudaGetLastError());
+    unsigned long long tot[2];
+    if ((rc = fetch_small(ctx, tot, meta, 16))) return rc;
+    ctx->render_cigar_total = tot[0]; ctx->render_text_total = tot[1];
+    ctx->stats.kernel_launches++;
+    if (tot[0] > cigar_capacity || (tot[0] && !cigar)) return fail(ctx, WFACUDA_E_OPS_CAPACITY, "cigar buffer holds %llu bytes, %llu needed", (unsigned long long)cigar_capacity, tot[0]);
+    if (text && tot[1] > text_capacity) return fail(ctx, WFACUDA_E_OPS_CAPACITY, "text buffer holds %llu bytes, %llu needed", (unsigned long long)text_capacity, tot[1]);
+    if ((rc = ensure(ctx, ctx->render_cigar, tot[0] + 16))) return rc;
+    R.cigar = (uint8_t *)ctx->render_cigar.p; R.cigar_cap = tot[0];
+    render_cigar_kernel<<<blocks, 256, 0, ctx->stream>>>(R);
+    CU(ctx, cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    if (text) {
+        if ((rc = ensure(ctx, ctx->render_text, tot[1] + 16))) return rc;
+        R.text = (uint8_t *)ctx->render_text.p; R.text_cap = tot[1];
+        const int tblocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);
+        render_text_kernel<<<tblocks, 256, 0, ctx->stream>>>(R);
+        CU(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches++;
+    }
+    if ((rc = staged_d2h(ctx, cigar_off, R.cigar_off, n * 8))) return rc;
+    if ((rc = staged_d2h(ctx, cigar_len, R.cigar_len, n * 4))) return rc;
+    if (tot[0] && (rc = staged_d2h(ctx, cigar, R.cigar, tot[0]))) return rc;
+    if (text) {
+        if ((rc = staged_d2h(ctx, text_off, R.text_off, n * 8))) return rc;
+        if ((rc = staged_d2h(ctx, text_len, R.text_len, n * 4))) return rc;
+        if (tot[1] && (rc = staged_d2h(ctx, text, R.text, tot[1]))) return rc;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void wfacuda_last_render_total(const wfacuda_ctx *ctx, uint64_t *cigar_bytes, uint64_t *text_bytes)
+{
+    if (cigar_bytes) *cigar_bytes = ctx ? ctx->render_cigar_total : 0;
+    if (text_bytes) *text_bytes = ctx ? ctx->render_text_total : 0;
 }
 
 static int align_batch_single(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
