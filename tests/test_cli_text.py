@@ -66,6 +66,12 @@ def test_cli_end_to_end(built_lib, tmp_path):
     with redirect_stdout(buf):
         assert cli.main(["-g", "Bioinformatics helps Biology", "We learn bioinformatics to help biologists"]) == 0
     assert _norm(buf.getvalue()) == _norm(README_BLOCK_1)
+    buf = io.StringIO()
+    with redirect_stdout(buf):          # -t: only the aligned region, strings rendered by the GPU
+        assert cli.main(["-g", "-t", "Bioinformatics helps Biology", "We learn bioinformatics to help biologists"]) == 0
+    out = buf.getvalue()
+    assert "query   ioinformatics ---helps Biolog\n" in out and "target  ioinformatics to help- biolog\n" in out
+    assert "cigar   14M3I4M1D1M1X5M\n" in out
     import json
     G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "readme_vectors.json")))
     path = tmp_path / "seqs.txt"

@@ -237,6 +237,26 @@ class AlignmentResult:
         return bytes(Q), bytes(A), bytes(T)
 
 
+class RenderedAlignmentResult(AlignmentResult):
+    """An AlignmentResult whose CIGAR() / AlignmentText() return what the GPU rendered for the
+    `onlyAignedRegion` setting of the batch call (any other setting is formatted on the host)."""
+    __slots__ = ("_rendered", "_index", "_trim")
+
+    def __init__(self, rec, ops, rendered, index, trim):
+        AlignmentResult.__init__(self, rec, ops)
+        self._rendered, self._index, self._trim = rendered, index, trim
+
+    def CIGAR(self, onlyAignedRegion=False):
+        if bool(onlyAignedRegion) != self._trim:
+            return AlignmentResult.CIGAR(self, onlyAignedRegion)
+        return self._rendered.CIGAR(self._index)
+
+    def AlignmentText(self, q, t, onlyAignedRegion=False):
+        if bool(onlyAignedRegion) != self._trim:
+            return AlignmentResult.AlignmentText(self, q, t, onlyAignedRegion)
+        return self._rendered.AlignmentText(self._index)
+
+
 def ops_in_index_order(results, ops, ops_off):
     """Concatenate every pair's ops slice in pair-index order (the buffer order of pairs is
     unspecified for internally chunked batches)."""
@@ -371,6 +391,30 @@ class Aligner:
             if st == 0:
                 a = int(ops_off[i])
                 out.append(AlignmentResult(results[i], ops[a:a + int(results["n_ops"][i])]))
+                errs.append(None)
+            else:
+                out.append(None)
+                errs.append({1: ErrEmptySeq, 2: ErrSeqTooLong}.get(st, ErrResources))
+        return out, errs
+
+    def AlignBatchRendered(self, qs, ts, onlyAignedRegion=False):
+        """AlignBatch whose results carry the CIGAR string and the three AlignmentText lines as the
+        GPU rendered them (wfacuda_batch_render) instead of formatting them on the host."""
+        from .datagen import Batch
+        b = Batch.from_pairs(zip(qs, ts))
+        rb = ResidentBatch(self, b.seq_bytes, b.q_off, b.q_len, b.t_off, b.t_len)
+        try:
+            rb.run()
+            results, ops, ops_off = rb.download()
+            rendered = rb.render(onlyAignedRegion=onlyAignedRegion, text=True)
+        finally:
+            rb.free()
+        out, errs = [], []
+        for i in range(len(results)):
+            st = int(results["status"][i])
+            if st == 0:
+                a = int(ops_off[i])
+                out.append(RenderedAlignmentResult(results[i], ops[a:a + int(results["n_ops"][i])], rendered, i, bool(onlyAignedRegion)))
                 errs.append(None)
             else:
                 out.append(None)

@@ -88,7 +88,12 @@ def main(argv=None):
     if not args.a:
         algn.AdaptiveReduction(api.AdaptiveReductionOption(10, 50, 1))       # :100-106
     try:
-        results, errs = algn.AlignBatch([p[0] for p in pairs], [p[1] for p in pairs])
+        # one batched call; with output wanted the CIGAR strings and the three text lines are
+        # rendered on the GPU as well (wfacuda_batch_render)
+        if args.N:
+            results, errs = algn.AlignBatch([p[0] for p in pairs], [p[1] for p in pairs])
+        else:
+            results, errs = algn.AlignBatchRendered([p[0] for p in pairs], [p[1] for p in pairs], args.t)
         for (q, t), r, e in zip(pairs, results, errs):
             if e is not None:                                                # checkError, :185-190
                 sys.stderr.write("%s\n" % e)
