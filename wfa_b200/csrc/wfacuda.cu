@@ -90,7 +90,7 @@ struct wfacuda_ctx {
      * finished, and the stage boundaries taken from it */
     uint64_t lane_hist[64] = {}; uint64_t lane_hist_n = 0;
     int lane_bounds[3] = {0, 0, 0}; int lane_n_bounds = 0;
-    int lane_occ[2] = {0, 0}, lane_occ_sw = 0;   /* LANE kernel: resident blocks per SM for lane_occ_sw words per sequence, rings of 64 / 48 columns */
+    int lane_occ[3] = {0, 0, 0}, lane_occ_sw = 0;   /* LANE kernel: resident blocks per SM for lane_occ_sw words per sequence, rings of 64 / 56 / 48 columns */
     int ring_cap_learned = 0;      /* learned: ring width that the WARP class needed */
     int occ_cache[2][2][8] = {};   /* [cta][bits==8][log2(ring_cap/64)+1]: blocks per SM, 0 = unknown */
     uint64_t budget_cache = 0;     /* arena budget; refreshed when the arena has to grow */
@@ -643,15 +643,16 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         if (attempt > 8) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
         /* words per sequence in shared memory: the longest of the class + 1 for the funnel shift */
         const int sw = (int)((b->lane_maxlen + 15) / 16) + 1;
-        /* ring columns per stage: a stage whose rows all fit 48 columns (diagonals -23..22) runs
-         * with the narrower ring -- 12 KB instead of 15 KB of shared memory per warp, 9 instead
-         * of 7 blocks per SM */
-        const int ring_w[2] = {kLaneW, 48};
-        size_t smem_w[2];
-        for (int i = 0; i < 2; i++) smem_w[i] = lane_smem_bytes(ctx->dM, ctx->dE, ring_w[i], sw) * WFA_LANE_WARPS;
+        /* ring columns per stage: a stage runs with the narrowest ring its rows fit -- 48 columns
+         * (diagonals -23..22) are 12 KB instead of 15 KB of shared memory per warp, 9 instead of
+         * 7 blocks per SM; 56 columns (-27..26) give 8 */
+        constexpr int NW = 3;
+        const int ring_w[NW] = {kLaneW, 56, 48};
+        size_t smem_w[NW];
+        for (int i = 0; i < NW; i++) smem_w[i] = lane_smem_bytes(ctx->dM, ctx->dE, ring_w[i], sw) * WFA_LANE_WARPS;
         if (ctx->lane_occ_sw != sw) {
             ctx->lane_occ_sw = sw;
-            for (int i = 0; i < 2; i++)
+            for (int i = 0; i < NW; i++)
                 if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->lane_occ[i], lane_kernel, threads, smem_w[i]) != cudaSuccess) { cudaGetLastError(); ctx->lane_occ[i] = 1; }
         }
         /* stages: where the previous batch's pairs finished (score-index quantiles); the first
@@ -717,9 +718,11 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         {
             int si = 0;
             for (int j = 0; j < G.n_stages; j++) {
-                bool narrow = !getenv("WFACUDA_LANE_W64");
-                for (; si <= G.stage_end[j]; si++) if (G.lo[si] <= G.hi[si] && (G.lo[si] < -23 || G.hi[si] > 22)) narrow = false;
-                stage_w[j] = narrow ? 1 : 0;
+                int klo = 0, khi = 0;
+                for (; si <= G.stage_end[j]; si++) if (G.lo[si] <= G.hi[si]) { klo = std::min(klo, (int)G.lo[si]); khi = std::max(khi, (int)G.hi[si]); }
+                stage_w[j] = 0;
+                if (!getenv("WFACUDA_LANE_W64"))
+                    for (int i = NW - 1; i > 0; i--) if (klo >= -(ring_w[i] / 2 - 1) && khi <= ring_w[i] / 2 - 2) { stage_w[j] = i; break; }
             }
         }
         const double tl0 = now_ms();
@@ -919,7 +922,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = ctx->lane_occ[2] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
