@@ -1408,7 +1408,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
      * (the next copy is already queued when one completes) without letting chunks arrive late */
     ctx->h2d_turns.free_slots = ctx->h2d_fifo && !getenv("WFACUDA_NO_FIFO") ? 2 : 1;
     if (const char *e = getenv("WFACUDA_H2D_TURNS")) ctx->h2d_turns.free_slots = std::max(1, atoi(e));
-    std::atomic<uint64_t> next{0}, cursor{0};
+    std::atomic<uint64_t> cursor{0};
     std::atomic<int> first_err{0};
     std::mutex mu;
     wfacuda_stats total{};
@@ -1418,9 +1418,11 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     std::vector<double> t_up(K, 0.0), t_run(K, 0.0), t_down(K, 0.0);
     auto work = [&](int k) {
         wfacuda_ctx *sub = ctx->subs[k];
-        for (;;) {
-            const uint64_t c = next.fetch_add(1);
-            if (c >= n_chunks || first_err.load()) break;
+        /* chunk c belongs to worker c mod K, call after call: every worker sees the same chunk
+         * sizes again, so none of its device buffers (arena, staging) is ever re-allocated after
+         * the first call -- a cudaMalloc / cudaFree in the middle of a batch stalls the whole device */
+        for (uint64_t c = (uint64_t)k; c < n_chunks; c += (uint64_t)K) {
+            if (first_err.load()) break;
             const uint64_t a = cuts[c], cnt = cuts[c + 1] - cuts[c];
             const double w0 = now_ms();
             wfacuda_batch *b = wfacuda_batch_upload(sub, cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
@@ -1445,8 +1447,8 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         }
     };
     std::vector<std::thread> th;
-    for (int k = 1; k < K; k++) th.emplace_back(work, k);
-    work(0);
+    for (int k = 0; k + 1 < K; k++) th.emplace_back(work, k);     /* the calling thread starts last: it takes the last worker's chunks */
+    work(K - 1);
     for (auto &t : th) t.join();
     ctx->stats = total;
     ctx->last_ops_total = cursor.load();
