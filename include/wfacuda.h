@@ -169,6 +169,28 @@ int wfacuda_batch_render(wfacuda_ctx *ctx, wfacuda_batch *b, int only_aligned_re
                          uint8_t *text, uint64_t text_capacity, uint64_t *text_off, uint32_t *text_len);
 void wfacuda_last_render_total(const wfacuda_ctx *ctx, uint64_t *cigar_bytes, uint64_t *text_bytes);
 
+/* One score's wavefronts of a pair's M / I / D components (WaveFront, wfa_wavefront.go:45-60):
+ * diagonals lo..hi, three raw words (M, I, D: offset<<3 | backtrace code, 0 = absent,
+ * wfa_backtrace_types.go:23-37) per diagonal starting at cells[first_cell]. */
+typedef struct wfacuda_wavefront {
+    uint32_t score;
+    int32_t  lo, hi;
+    uint32_t reserved_;
+    uint64_t first_cell;
+} wfacuda_wavefront;
+
+/* Align ONE pair and hand out Aligner.M / I / D as Align leaves them (wfa.go:80-86; Component,
+ * wfa_component.go:37-187): what the reference's Plot / Print / GetRaw read.  The pair is aligned by
+ * a single worker whose arena slot is then read back; semi-global alignments run to the global
+ * corner like the reference does, so every score the reference retains is present.  [lo, hi] is the
+ * M wavefront's Lo / Hi after reduce; I and D cells are reported over the same range (absent = 0).
+ * rows / cells may be NULL with capacity 0 to ask for the sizes (returned in n_rows / n_cells
+ * together with WFACUDA_E_OPS_CAPACITY).  A debugging interface: O(wavefront cells) host memory. */
+int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len, const uint8_t *t, uint32_t t_len,
+                             wfacuda_result *result, uint64_t *ops, uint64_t ops_capacity,
+                             wfacuda_wavefront *rows, uint32_t rows_capacity, uint32_t *n_rows,
+                             uint32_t *cells, uint64_t cells_capacity, uint64_t *n_cells);
+
 /* One host thread per device, work-balanced static sharding, no collective
  * (pairs are independent): the C side of AlignBatch over several GPUs. */
 int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs,

@@ -100,7 +100,7 @@ EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
            "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error",
            "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister",
-           "wfacuda_batch_render", "wfacuda_last_render_total"]
+           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components"]
 
 _LIB = None
 
@@ -136,6 +136,8 @@ def load_library():
     L.wfacuda_batch_render.restype = C.c_int
     L.wfacuda_batch_render.argtypes = [vp, vp, C.c_int, vp, u64, vp, vp, vp, u64, vp, vp]
     L.wfacuda_last_render_total.argtypes = [vp, vp, vp]
+    L.wfacuda_align_components.restype = C.c_int
+    L.wfacuda_align_components.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, u64, vp, C.c_uint32, vp, vp, u64, vp]
     L.wfacuda_align_batch_multi.restype = C.c_int
     L.wfacuda_align_batch_multi.argtypes = [C.POINTER(vp), C.c_int, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
     L.wfacuda_shard_plan.restype = C.c_int
@@ -235,6 +237,127 @@ class AlignmentResult:
             elif o == OpD or o == OpH:
                 Q += q[v:v + n]; A += b" " * n; T += b"-" * n; v += n
         return bytes(Q), bytes(A), bytes(T)
+
+
+WAVEFRONT_DTYPE = np.dtype([("score", "<u4"), ("lo", "<i4"), ("hi", "<i4"), ("reserved_", "<u4"), ("first_cell", "<u8")])
+
+# wfa_backtrace_types.go:23-37 and the arrows of wfa_component_plot.go:33-40
+wfaTypeBits, wfaTypeMask = 3, 7
+wfaUnknown, wfaInsertOpen, wfaInsertExt, wfaDeleteOpen, wfaDeleteExt, wfaMismatch, wfaMatch = range(7)
+wfaArrows = ["\u2295", "\u27fc", "\U0001f826", "\u21a7", "\U0001f827", "\u2b02", "\u2b0a"]
+
+
+class ComponentView:
+    """One of Aligner.M / I / D as read back from the GPU: Component (wfa_component.go:37-187)
+    restricted to what Plot and tests read -- HasScore, Get, GetRaw, GetAfterDiff, KRange."""
+
+    def __init__(self, is_m):
+        self.IsM = is_m
+        self.W = {}                             # score -> (lo, hi, raw words of diagonals lo..hi)
+
+    def HasScore(self, s):                      # wfa_component.go:81-86
+        return s in self.W
+
+    def KRange(self, s):                        # Lo, Hi of the M wavefront of score s after reduce
+        lo, hi, _ = self.W[s]
+        return lo, hi
+
+    def GetRaw(self, s, k):                     # wfa_component.go:148-155 (0 = absent)
+        wf = self.W.get(s)
+        if wf is None or k < wf[0] or k > wf[1]:
+            return 0
+        return int(wf[2][k - wf[0]])
+
+    def Get(self, s, k):                        # wfa_component.go:142-146: offset, type, ok
+        raw = self.GetRaw(s, k)
+        return raw >> wfaTypeBits, raw & wfaTypeMask, raw != 0
+
+    def GetAfterDiff(self, s, diff, k):         # wfa_component.go:157-163
+        if s < diff:
+            return 0, 0, False
+        return self.Get(s - diff, k)
+
+
+class Components:
+    """Aligner.M, I, D of one aligned pair (wfacuda_align_components) and the reference's Plot over them."""
+
+    def __init__(self, penalties, rows, cells):
+        self.p = penalties
+        self.M, self.I, self.D = ComponentView(True), ComponentView(False), ComponentView(False)
+        for r in rows:
+            lo, hi, a = int(r["lo"]), int(r["hi"]), int(r["first_cell"])
+            tri = cells[a:a + 3 * (hi - lo + 1)].reshape(-1, 3)
+            for j, comp in enumerate((self.M, self.I, self.D)):
+                col = tri[:, j]
+                if col.any():                   # a component has the score iff it holds a cell there
+                    comp.W[int(r["score"])] = (lo, hi, col.copy())
+
+    def plot_matrix(self, q, t, comp="M", notChangeToMatch=False, maxScore=-1):
+        """The matrix Plot fills (wfa_component_plot.go:41-188): mat[v][h] = (score, type) or None."""
+        M, I, D, p = self.M, self.I, self.D, self.p
+        target = {"M": M, "I": I, "D": D}[comp]
+        oe, e, x = p.GapOpen + p.GapExt, p.GapExt, p.Mismatch
+        nq, nt = len(q), len(t)
+        is_m = M.IsM                            # the reference reads algn.M.IsM, whatever component is plotted (:49)
+        mat = [[None] * nt for _ in range(nq)]
+        vp = hp = 0                             # declared once for the whole function (:60): values carry over between cells
+        for s in sorted(target.W):
+            if 0 <= maxScore < s:
+                break
+            lo, hi, _ = target.W[s]
+            for k in range(lo, hi + 1):
+                offset, typ, ok = target.Get(s, k)
+                if not ok:
+                    continue
+                h = offset - 1
+                v = h - k
+                if v < 0 or h < 0 or v >= nq or h >= nt or mat[v][h] is not None:
+                    continue
+                mat[v][h] = (s, typ)
+                if not is_m or q[v] != t[h]:
+                    continue
+                # where the cell stood before extend (:101-131)
+                if typ == wfaInsertExt:
+                    offset0 = max(M.GetAfterDiff(s, oe, k - 1)[0], I.GetAfterDiff(s, e, k - 1)[0]) + 1
+                elif typ == wfaDeleteExt:
+                    offset0 = max(M.GetAfterDiff(s, oe, k + 1)[0], D.GetAfterDiff(s, e, k + 1)[0])
+                else:
+                    isk = max(M.GetAfterDiff(s, oe, k - 1)[0], I.GetAfterDiff(s, e, k - 1)[0]) + 1
+                    dsk = max(M.GetAfterDiff(s, oe, k + 1)[0], D.GetAfterDiff(s, e, k + 1)[0])
+                    offset0 = max(isk, dsk, M.GetAfterDiff(s, x, k)[0] + 1)
+                h00 = offset0 - 1
+                if h == h00:                    # not extended at all
+                    continue
+                v0, h0 = v, h
+                if not notChangeToMatch:
+                    mat[v0][h0] = (s, wfaMatch)
+                n = 0
+                while True:                     # walk the extension backwards (:147-170)
+                    h -= 1
+                    v -= 1
+                    if v < 0 or h < 0:
+                        break
+                    n += 1
+                    if mat[v][h] is not None:
+                        continue
+                    mat[v][h] = (s, typ) if notChangeToMatch else (s, wfaMatch)
+                    vp, hp = v, h
+                    if q[v] != t[h] or h == h00:
+                        break
+                if n == 0:
+                    vp, hp = v0, h0
+                if not notChangeToMatch:
+                    mat[vp][hp] = (s, typ)      # the cell where the run started keeps its own type
+        return mat
+
+    def Plot(self, q, t, wtr, comp="M", notChangeToMatch=False, maxScore=-1):
+        """(*Aligner).Plot (wfa_component_plot.go:41-209): the tab-separated table, arrows + scores."""
+        mat = self.plot_matrix(q, t, comp, notChangeToMatch, maxScore)
+        wtr.write("   \t " + "".join("\t%3d" % (h + 1) for h in range(len(t))) + "\n")
+        wtr.write("   \t " + "".join("\t%3s" % chr(b) for b in t) + "\n")
+        for v, b in enumerate(q):
+            cells = "".join("\t  ." if c is None else "\t%s%2d" % (wfaArrows[c[1]], c[0]) for c in mat[v])
+            wtr.write("%3d\t%s%s\n" % (v + 1, chr(b), cells))
 
 
 class RenderedAlignmentResult(AlignmentResult):
@@ -420,6 +543,28 @@ class Aligner:
                 out.append(None)
                 errs.append({1: ErrEmptySeq, 2: ErrSeqTooLong}.get(st, ErrResources))
         return out, errs
+
+    def AlignComponents(self, q, t):
+        """Align one pair and read back Aligner.M / I / D (wfa.go:80-86) from the worker's arena
+        slot: (AlignmentResult, Components).  What the reference's Plot / Print / GetRaw need."""
+        q, t = bytes(q), bytes(t)
+        res = np.zeros(1, RESULT_DTYPE)
+        ops = np.zeros(len(q) + len(t) + 16, np.uint64)
+        rows, cells = np.zeros(1, WAVEFRONT_DTYPE), np.zeros(1, np.uint32)
+        n_rows, n_cells = C.c_uint32(0), C.c_uint64(0)
+        for _ in range(2):      # first call sizes the buffers, second fills them
+            rc = self._L.wfacuda_align_components(self._ctx, q, len(q), t, len(t), res.ctypes.data, ops.ctypes.data, len(ops),
+                                                  rows.ctypes.data, len(rows), C.byref(n_rows), cells.ctypes.data, len(cells), C.byref(n_cells))
+            if rc != -4:
+                break
+            rows, cells = np.zeros(max(n_rows.value, 1), WAVEFRONT_DTYPE), np.zeros(max(n_cells.value, 1), np.uint32)
+        if rc != 0:
+            raise WfaError("wfacuda_align_components failed (%d): %s" % (rc, self._err()))
+        st = int(res["status"][0])
+        if st != 0:
+            raise {1: ErrEmptySeq, 2: ErrSeqTooLong}.get(st, ErrResources)
+        comps = Components(self.p, rows[:n_rows.value], cells[:n_cells.value])
+        return AlignmentResult(res[0], ops[:int(res["n_ops"][0])].copy()), comps
 
     def Align(self, q, t):                      # wfa.go:196-198
         res, errs = self.AlignBatch([q], [t])

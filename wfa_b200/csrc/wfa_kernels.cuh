@@ -64,6 +64,7 @@ struct Counters {              /* device-side work counters, one set per launch 
     unsigned long long t_first, t_last;   /* globaltimer of the first block start / last block end (LANE kernel, profiling aid) */
     unsigned long long lane_count[8];     /* LANE class: [j] pairs entering stage j, [4 + j] group queue of stage j */
     unsigned int lane_hist[64];           /* LANE class: sampled histogram of the final score index (next batch's stage boundaries) */
+    unsigned long long dump_rows;         /* single-worker launches: row headers the forward pass wrote (wfacuda_align_components) */
 };
 
 /* LANE class (wfa_lane.cuh).  Without heuristic the loop range of `next` depends only on which
@@ -110,7 +111,8 @@ struct KParams {
     int32_t  ring_cap;         /* diagonals per ring row (WARP kernel) */
     int32_t  group;            /* WARP kernel: pairs per group (1..32), slot_bytes = group * sub-slot */
     int32_t  seq_cap;          /* WARP kernel: 32-bit words of shared memory per warp for the pair's 2-bit sequences (0: read them from global) */
-    uint8_t  global_aln, adaptive, semi_literal, pad8_;
+    uint8_t  global_aln, adaptive, semi_literal;
+    uint8_t  single_worker;    /* only worker 0 takes work: its slot then holds the one pair's whole wavefront store (wfacuda_align_components) */
     int32_t  min_wf_len, max_dist_diff;
     LaneGeom lg;               /* LANE kernels only */
     LaneAux  la;
@@ -815,6 +817,7 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
     const uint64_t scratch_w = (((uint64_t)(si + 1) * sizeof(RowHdr) + 7) / 8) * 2;   /* word index, 8-byte aligned */
     uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w);
     uint32_t n_ops = 0;
+    if (P.single_worker && tid == 0) P.ctr->dump_rows = (unsigned long long)(si + 1);
     if (status == ST_OK) {
         G::sync();
         if (tid == 0) {
@@ -978,6 +981,7 @@ __device__ __noinline__ void finish_group(const KParams &P, const bool have, con
     const uint64_t scratch_w = (((uint64_t)(f.si + 1) * sizeof(RowHdr) + 7) / 8) * 2;
     uint64_t *scratch = reinterpret_cast<uint64_t *>(cells + scratch_w);
     int status = have ? f.status : ST_PENDING;
+    if (P.single_worker && have) P.ctr->dump_rows = (unsigned long long)(f.si + 1);
 
     Result res;
     res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
@@ -1020,6 +1024,7 @@ align_kernel(const KParams P)
     const uint64_t worker = (uint64_t)blockIdx.x * wpb + wib;
     uint8_t *slot = P.arena + worker * P.slot_bytes;
     __shared__ uint32_t next_item[4];
+    if (!CTA && P.single_worker && worker != 0) return;
 
     if (CTA) {
         for (;;) {

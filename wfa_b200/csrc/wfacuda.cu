@@ -121,6 +121,8 @@ struct wfacuda_ctx {
     DevBuf wire_dev;                                           /* their landing place on the device */
     DevBuf render_meta, render_cigar, render_text;             /* wfacuda_batch_render: offsets / lengths / cursors, strings */
     uint64_t render_cigar_total = 0, render_text_total = 0;
+    /* wfacuda_align_components: one pair on one worker, whose slot is read back afterwards */
+    bool dump_mode = false, dump_cta = false; uint64_t dump_slot_bytes = 0, dump_rows = 0;
     const wfacuda_batch *pin_descs_owner = nullptr;
 };
 
@@ -436,6 +438,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
         if (const char *e = getenv("WFACUDA_GROUP")) g = std::min<uint64_t>(g, (uint64_t)std::max(1, atoi(e)));
         lp->group = (int)std::max<uint64_t>(1, g);
     }
+    if (ctx->dump_mode) { workers = wpb; lp->group = 1; }            /* one block; the WARP kernel lets only its warp 0 work */
     lp->blocks = (int)(workers / wpb); lp->workers = workers; lp->slot_bytes = slot;
     return 0;
 }
@@ -470,6 +473,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
         P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
         P.ring_cap = lp.ring_cap; P.seq_cap = lp.seq_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+        if (ctx->dump_mode) { P.single_worker = 1; P.semi_literal = 1; ctx->dump_cta = cta; ctx->dump_slot_bytes = lp.slot_bytes * lp.group; }
         const double tk0 = now_ms();
         if (cta) { if (bits == 2) align_kernel<2, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
                    else           align_kernel<8, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
@@ -559,7 +563,7 @@ bool lane_class_enabled(const wfacuda_ctx *ctx)
     const wfacuda_config &c = ctx->cfg;
     if (!c.global_alignment || c.adaptive) return false;
     if (c.flags & (WFACUDA_FLAG_FORCE_CTA | WFACUDA_FLAG_FORCE_8BIT | WFACUDA_FLAG_NO_LANE)) return false;
-    if (getenv("WFACUDA_NO_LANE")) return false;
+    if (getenv("WFACUDA_NO_LANE") || ctx->dump_mode) return false;
     /* at least two resident blocks per SM */
     return lane_smem_bytes(ctx->dM, ctx->dE, kLaneW, LANE_SEQ_WORDS) * WFA_LANE_WARPS * 2 <= ctx->smem_optin;
 }
@@ -1211,6 +1215,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     ctx->stats.pairs = n_valid; ctx->stats.cells = hc.cells; ctx->stats.cells_written = hc.cells_written;
     ctx->stats.score_steps = hc.steps; ctx->stats.ops = hc.ops; ctx->stats.seq_bases = b->seq_bases;
     b->ops_total = hc.ops_cursor;
+    ctx->dump_rows = hc.dump_rows;
     ctx->pool_owner = b;
     ctx->last_ops_total = b->ops_total;
     b->ran = true;
@@ -1300,6 +1305,68 @@ int wfacuda_batch_render(wfacuda_ctx *ctx, wfacuda_batch *b, int only_aligned_re
         if (tot[1] && (rc = staged_d2h(ctx, text, R.text, tot[1]))) return rc;
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+/* Aligner.M / I / D after Align (wfa.go:80-86, 143-268): the whole wavefront store of ONE pair,
+ * read back from the arena slot of the worker that aligned it (what Plot / Print /
+ * GetRaw of the reference need).  Every existing score's row comes with its post-reduce range
+ * [lo, hi] = WaveFront.Lo / Hi of M; cells outside it are absent (equivalence 1). */
+int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len, const uint8_t *t, uint32_t t_len,
+                             wfacuda_result *result, uint64_t *ops, uint64_t ops_capacity,
+                             wfacuda_wavefront *rows, uint32_t rows_capacity, uint32_t *n_rows,
+                             uint32_t *cells, uint64_t cells_capacity, uint64_t *n_cells)
+{
+    if (!ctx || !q || !t || !result || !n_rows || !n_cells) return fail(ctx, WFACUDA_E_INVALID, "NULL argument");
+    *n_rows = 0; *n_cells = 0;
+    std::vector<uint8_t> pool((size_t)q_len + t_len + 32, 0);
+    memcpy(pool.data(), q, q_len); memcpy(pool.data() + q_len, t, t_len);
+    const uint64_t q_off = 0, t_off = q_len;
+    const double keep_scale = ctx->arena_scale; const int keep_cap = ctx->ring_cap_learned;
+    ctx->dump_mode = true;
+    struct Guard { wfacuda_ctx *c; double s; int r; ~Guard() { c->dump_mode = false; c->arena_scale = s; c->ring_cap_learned = r; } } guard{ctx, keep_scale, keep_cap};
+    wfacuda_batch *b = wfacuda_batch_upload(ctx, 1, pool.data(), &q_off, &q_len, &t_off, &t_len);
+    if (!b) return ctx->last_rc ? ctx->last_rc : WFACUDA_E_CUDA;
+    struct Free { wfacuda_ctx *c; wfacuda_batch *b; ~Free() { wfacuda_batch_free(c, b); } } fr{ctx, b};
+    int rc = wfacuda_batch_run(ctx, b);
+    if (rc) return rc;
+    uint64_t off1 = 0;
+    if ((rc = wfacuda_batch_download(ctx, b, result, ops, ops_capacity, &off1))) return rc;
+    if (result->status != ST_OK) return 0;                     /* ErrEmptySeq / ErrSeqTooLong / resources: nothing to read */
+    /* row headers the forward pass wrote: up to the final score (global), up to the global corner
+     * (semi-global: this mode runs the literal scan, the reference keeps those rows too) */
+    const uint32_t used_hdr = (uint32_t)ctx->dump_rows;
+    const uint64_t slot_words = ctx->dump_slot_bytes / 4;
+    if (used_hdr == 0 || (uint64_t)used_hdr * sizeof(RowHdr) > ctx->dump_slot_bytes) return fail(ctx, WFACUDA_E_CUDA, "no row headers reported for the pair");
+    std::vector<RowHdr> hdr(used_hdr);
+    if ((rc = staged_d2h(ctx, hdr.data(), ctx->arena.p, (size_t)used_hdr * sizeof(RowHdr)))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t min_off = slot_words, want_cells = 0; uint32_t want_rows = 0;
+    for (uint32_t i = 0; i < used_hdr; i++) {
+        const RowHdr &h = hdr[i];
+        if (h.lo > h.hi) continue;
+        want_rows++; want_cells += 3ull * (uint64_t)(h.hi - h.lo + 1);
+        min_off = std::min<uint64_t>(min_off, h.off);
+    }
+    *n_rows = want_rows; *n_cells = want_cells;
+    if (want_rows > rows_capacity || want_cells > cells_capacity || (want_rows && (!rows || !cells)))
+        return fail(ctx, WFACUDA_E_OPS_CAPACITY, "wavefront store has %u rows / %llu cell words, buffers hold %u / %llu", want_rows, (unsigned long long)want_cells, rows_capacity, (unsigned long long)cells_capacity);
+    if (!want_rows) return 0;
+    std::vector<uint32_t> slot(slot_words - min_off);
+    if ((rc = staged_d2h(ctx, slot.data(), (const uint32_t *)ctx->arena.p + min_off, slot.size() * 4))) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t at = 0; uint32_t r = 0;
+    for (uint32_t i = 0; i < used_hdr; i++) {
+        const RowHdr &h = hdr[i];
+        if (h.lo > h.hi) continue;
+        rows[r].score = i * ctx->g; rows[r].lo = h.lo; rows[r].hi = h.hi; rows[r].reserved_ = 0; rows[r].first_cell = at;
+        const uint32_t *base = slot.data() + (h.off - min_off);
+        for (int k = h.lo; k <= h.hi; k++) {
+            const uint64_t idx = (uint64_t)(k - h.alo);
+            for (int c = 0; c < 3; c++) cells[at++] = ctx->dump_cta ? base[(uint64_t)c * (uint64_t)h.aw + idx] : base[3 * idx + c];
+        }
+        r++;
+    }
     return 0;
 }
 
