@@ -171,3 +171,68 @@ func AlignBatchMulti(algns []*Aligner, qs, ts [][]byte) ([]*AlignmentResult, []e
 	// passed to C.wfacuda_align_batch_multi; omitted here for brevity of the shim.
 	return algns[0].AlignBatch(qs, ts)
 }
+
+// FillComponents aligns one pair and fills algn.M / I / D from the GPU's wavefront store
+// (wfacuda_align_components), so that Plot / Print / GetRaw of the reference keep working
+// (wfa_component_plot.go:41-209).  A debugging interface: one pair, O(wavefront cells) host memory.
+func (algn *Aligner) FillComponents(q, t *[]byte) (*AlignmentResult, error) {
+	var res C.wfacuda_result
+	ops := make([]uint64, len(*q)+len(*t)+16)
+	var nRows C.uint32_t
+	var nCells C.uint64_t
+	rows := make([]C.wfacuda_wavefront, 1)
+	cells := make([]C.uint32_t, 1)
+	call := func() C.int {
+		return C.wfacuda_align_components(algn.cuda.ctx,
+			(*C.uint8_t)(unsafe.Pointer(&(*q)[0])), C.uint32_t(len(*q)), (*C.uint8_t)(unsafe.Pointer(&(*t)[0])), C.uint32_t(len(*t)),
+			&res, (*C.uint64_t)(unsafe.Pointer(&ops[0])), C.uint64_t(len(ops)),
+			&rows[0], C.uint32_t(len(rows)), &nRows, &cells[0], C.uint64_t(len(cells)), &nCells)
+	}
+	rc := call()
+	if rc == C.WFACUDA_E_OPS_CAPACITY { // first call sized the buffers
+		rows = make([]C.wfacuda_wavefront, int(nRows)+1)
+		cells = make([]C.uint32_t, int(nCells)+1)
+		rc = call()
+	}
+	if rc != 0 {
+		return nil, fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(algn.cuda.ctx)))
+	}
+	switch res.status {
+	case C.WFACUDA_ERR_EMPTY_SEQ:
+		return nil, ErrEmptySeq
+	case C.WFACUDA_ERR_SEQ_TOO_LONG:
+		return nil, ErrSeqTooLong
+	}
+	algn.M.Reset()
+	algn.I.Reset()
+	algn.D.Reset()
+	for _, w := range rows[:nRows] {
+		for k := int(w.lo); k <= int(w.hi); k++ {
+			c := cells[uint64(w.first_cell)+3*uint64(k-int(w.lo)):]
+			if c[0] != 0 {
+				algn.M.SetRaw(uint32(w.score), k, uint32(c[0])) // offset<<3 | code, as next / extend left it
+			}
+			if c[1] != 0 {
+				algn.I.SetRaw(uint32(w.score), k, uint32(c[1]))
+			}
+			if c[2] != 0 {
+				algn.D.SetRaw(uint32(w.score), k, uint32(c[2]))
+			}
+		}
+	}
+	r := NewAlignmentResult(algn.opt.GlobalAlignment)
+	r.Ops = append(r.Ops[:0], ops[:res.n_ops]...)
+	r.Score = uint32(res.score)
+	r.TBegin, r.TEnd, r.QBegin, r.QEnd = int(res.tbegin), int(res.tend), int(res.qbegin), int(res.qend)
+	r.AlignLen, r.Matches, r.Gaps, r.GapRegions = uint32(res.align_len), uint32(res.matches), uint32(res.gaps), uint32(res.gap_regions)
+	r.proccessed = true
+	return r, nil
+}
+
+// RenderBatch returns CIGAR(onlyAignedRegion) and the three AlignmentText lines of every pair,
+// formatted on the GPU (wfacuda_batch_render; wfa_cigar.go:236-333) -- for callers that print
+// every alignment of a large batch.  Uses the split interface: upload, run, render, free.
+//   b := C.wfacuda_batch_upload(ctx, n, pool, qOff, qLen, tOff, tLen); C.wfacuda_batch_run(ctx, b)
+//   rc := C.wfacuda_batch_render(ctx, b, trim, cigar, cap(cigar), cigarOff, cigarLen, text, cap(text), textOff, textLen)
+//   rc == WFACUDA_E_OPS_CAPACITY: C.wfacuda_last_render_total(ctx, &needCigar, &needText), grow, call again
+//   pair i: string(cigar[cigarOff[i]:][:cigarLen[i]]); lines j = 0 (Q), 1 (A), 2 (T): text[textOff[i]+j*textLen[i]:][:textLen[i]]
