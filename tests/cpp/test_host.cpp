@@ -58,6 +58,22 @@ int main()
     CHECK(Q == "---------Bioinformatics ---helps Biology---");
     CHECK(T == "We learn bioinformatics to help- biologists");
     wfa::RecycleAlignmentResult(r);
+
+    // the same strings formatted on the GPU for a whole batch (wfa-go -g -t prints these)
+    std::vector<std::string> cg, bQ, bA, bT; std::vector<wfa::Error> bes;
+    CHECK(algn->AlignBatchRendered({q, "", "ACGT"}, {t, "A", "ACGT"}, true, &cg, &bQ, &bA, &bT, &bes) == nullptr);
+    CHECK(cg[0] == "14M3I4M1D1M1X5M" && bQ[0] == "ioinformatics ---helps Biolog" && bT[0] == "ioinformatics to help- biolog");
+    CHECK(bA[0].size() == bQ[0].size() && bes[1] == wfa::ErrEmptySeq && cg[1].empty() && cg[2] == "4M" && bA[2] == "||||");
+    wfa::RecycleAligner(algn);
+
+    // Aligner.M / I / D from the GPU's wavefront store: the known-answer trace of README.md:101-124
+    algn = wfa::New(&p, &opt);
+    wfa::Aligner::Components comps;
+    CHECK(algn->AlignComponents("ACCATACTCG", "AGGATGCTCG", &r, &comps) == nullptr && r->CIGAR(false) == "1M2X2M1X4M");
+    CHECK(comps.GetRaw(0, 0, 0) == (1u << 3 | 6u) && comps.GetRaw(0, 8, 0) == (5u << 3 | 5u));     // M[0][0] = Match 1, M[8][0] = Mismatch 5 (after extend)
+    CHECK(comps.GetRaw(2, 8, -1) == (1u << 3 | 3u) && comps.GetRaw(1, 8, 1) == (2u << 3 | 1u));    // D[8][-1] = DelOpen 1, I[8][1] = InsOpen 2
+    CHECK(comps.GetRaw(0, 12, 0) == (10u << 3 | 5u) && comps.GetRaw(0, 6, 0) == 0u);
+    wfa::RecycleAlignmentResult(r);
     wfa::RecycleAligner(algn);
     std::printf("host API ok\n");
     return 0;

@@ -175,6 +175,89 @@ public:
         return nullptr;
     }
 
+    /* CIGAR(onlyAignedRegion) and the AlignmentText lines of every pair of a batch, formatted on the
+     * GPU (wfacuda_batch_render; wfa_cigar.go:236-333).  cigars[i] / Q,A,T[i] are empty where errors[i] != nil. */
+    Error AlignBatchRendered(const std::vector<std::string> &qs, const std::vector<std::string> &ts, bool onlyAignedRegion,
+                             std::vector<std::string> *cigars, std::vector<std::string> *Q, std::vector<std::string> *A,
+                             std::vector<std::string> *T, std::vector<Error> *errors)
+    {
+        const size_t n = qs.size();
+        std::vector<uint8_t> pool; std::vector<uint64_t> qo(n), to(n); std::vector<uint32_t> ql(n), tl(n);
+        for (size_t i = 0; i < n; i++) {
+            qo[i] = pool.size(); ql[i] = (uint32_t)qs[i].size(); pool.insert(pool.end(), qs[i].begin(), qs[i].end());
+            to[i] = pool.size(); tl[i] = (uint32_t)ts[i].size(); pool.insert(pool.end(), ts[i].begin(), ts[i].end());
+        }
+        pool.resize(pool.size() + 16);
+        wfacuda_batch *b = wfacuda_batch_upload(ctx_, n, pool.data(), qo.data(), ql.data(), to.data(), tl.data());
+        if (!b) { err_ = wfacuda_last_error(ctx_); return err_.c_str(); }
+        std::vector<wfacuda_result> res(n); std::vector<uint64_t> off(n);
+        int rc = wfacuda_batch_run(ctx_, b);
+        if (rc == 0) rc = wfacuda_batch_download(ctx_, b, res.data(), nullptr, 0, off.data());
+        std::vector<uint8_t> cig(1), txt(1); std::vector<uint64_t> co(n), xo(n); std::vector<uint32_t> cl(n), xl(n);
+        for (int pass = 0; rc == 0 && pass < 2; pass++) {       /* first call sizes the buffers */
+            rc = wfacuda_batch_render(ctx_, b, onlyAignedRegion ? 1 : 0, cig.data(), cig.size(), co.data(), cl.data(),
+                                      txt.data(), txt.size(), xo.data(), xl.data());
+            if (rc != WFACUDA_E_OPS_CAPACITY) break;
+            uint64_t a = 0, c = 0;
+            wfacuda_last_render_total(ctx_, &a, &c);
+            cig.resize(a + 1); txt.resize(c + 1);
+            rc = 0;
+            if (pass == 1) rc = WFACUDA_E_OPS_CAPACITY;
+        }
+        wfacuda_batch_free(ctx_, b);
+        if (rc != 0) { err_ = wfacuda_last_error(ctx_); return err_.c_str(); }
+        cigars->assign(n, ""); Q->assign(n, ""); A->assign(n, ""); T->assign(n, ""); errors->assign(n, nullptr);
+        for (size_t i = 0; i < n; i++) {
+            if (res[i].status == WFACUDA_ERR_EMPTY_SEQ) { (*errors)[i] = ErrEmptySeq; continue; }
+            if (res[i].status == WFACUDA_ERR_SEQ_TOO_LONG) { (*errors)[i] = ErrSeqTooLong; continue; }
+            if (res[i].status != WFACUDA_OK) { (*errors)[i] = ErrResources; continue; }
+            (*cigars)[i].assign((const char *)cig.data() + co[i], cl[i]);
+            (*Q)[i].assign((const char *)txt.data() + xo[i], xl[i]);
+            (*A)[i].assign((const char *)txt.data() + xo[i] + xl[i], xl[i]);
+            (*T)[i].assign((const char *)txt.data() + xo[i] + 2ull * xl[i], xl[i]);
+        }
+        return nullptr;
+    }
+
+    /* Aligner.M / I / D of one pair (wfa.go:80-86) from the GPU's wavefront store: rows of
+     * {score, lo, hi, first_cell} and three raw words offset<<3|code per diagonal (wfacuda_align_components). */
+    struct Components {
+        std::vector<wfacuda_wavefront> rows; std::vector<uint32_t> cells;
+        /* Component.GetRaw (wfa_component.go:148-155): comp 0 = M, 1 = I, 2 = D; 0 = absent */
+        uint32_t GetRaw(int comp, uint32_t s, int k) const
+        {
+            for (const wfacuda_wavefront &w : rows)
+                if (w.score == s) return (k < w.lo || k > w.hi) ? 0u : cells[w.first_cell + 3ull * (uint64_t)(k - w.lo) + (uint64_t)comp];
+            return 0u;
+        }
+    };
+    Error AlignComponents(const std::string &q, const std::string &t, AlignmentResult **out, Components *comps)
+    {
+        wfacuda_result res{}; std::vector<uint64_t> ops(q.size() + t.size() + 16);
+        uint32_t nr = 0; uint64_t nc = 0;
+        comps->rows.assign(1, wfacuda_wavefront{}); comps->cells.assign(1, 0u);
+        int rc = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            rc = wfacuda_align_components(ctx_, (const uint8_t *)q.data(), (uint32_t)q.size(), (const uint8_t *)t.data(), (uint32_t)t.size(),
+                                          &res, ops.data(), ops.size(), comps->rows.data(), (uint32_t)comps->rows.size(), &nr,
+                                          comps->cells.data(), comps->cells.size(), &nc);
+            if (rc != WFACUDA_E_OPS_CAPACITY) break;
+            comps->rows.assign(nr + 1, wfacuda_wavefront{}); comps->cells.assign(nc + 1, 0u);
+        }
+        *out = nullptr;
+        if (rc != 0) { err_ = wfacuda_last_error(ctx_); return err_.c_str(); }
+        if (res.status == WFACUDA_ERR_EMPTY_SEQ) return ErrEmptySeq;
+        if (res.status == WFACUDA_ERR_SEQ_TOO_LONG) return ErrSeqTooLong;
+        if (res.status != WFACUDA_OK) return ErrResources;
+        comps->rows.resize(nr); comps->cells.resize(nc);
+        AlignmentResult *r = new AlignmentResult();
+        r->Ops.assign(ops.begin(), ops.begin() + res.n_ops);
+        r->Score = res.score; r->TBegin = res.tbegin; r->TEnd = res.tend; r->QBegin = res.qbegin; r->QEnd = res.qend;
+        r->AlignLen = res.align_len; r->Matches = res.matches; r->Gaps = res.gaps; r->GapRegions = res.gap_regions;
+        *out = r;
+        return nullptr;
+    }
+
 private:
     wfacuda_config config() const
     {
