@@ -263,6 +263,14 @@ def main():
     barrier()
     wall_pageable = time.perf_counter() - t2
 
+    # ---- INT32 issue peak of this device, measured ---------------
+    int32_peaks = None
+    if rank == 0:
+        try:
+            int32_peaks = algn.measure_int32_peak()
+        except Exception:
+            int32_peaks = None
+
     # ---- max over ranks ------------------------------------------------------
     (wall, wall_e2e, ms_align, ms_dev, wall_pageable), (pairs_all, cells_all, ok_all) = wdist.reduce_times_and_totals(
         [wall, wall_e2e, ms_align, ms_dev, wall_pageable], [float(n_pairs), float(batch.cells_equiv()), float(ok)], world, device="cuda")
@@ -304,6 +312,11 @@ def main():
             "roofline_int32": {"bound": "int32-issue", "achieved": int_ops / k_sec / 1e12,
                                "peak": sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12, "unit": "Tops/s",
                                "frac": (int_ops / k_sec) / (sm_count * 4 * 32 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                               # the same peak measured on this device by the library's microbenchmark
+                               # (wfacuda_measure_issue_peak): add + xor chains, and add + mad.lo chains
+                               "peak_measured": {"add_xor": int32_peaks[0], "add_mad": int32_peaks[1]} if int32_peaks else None,
+                               "frac_of_measured": (int_ops / k_sec / 1e12) / max(int32_peaks) if int32_peaks else None,
+                               "executed_frac_of_measured": (ncu_instr * 32 / k_sec / 1e12) / max(int32_peaks) if (int32_peaks and ncu_instr) else None,
                                "algorithmic_ops_per_launch": int(int_ops),
                                # what the kernels really issue (committed ncu capture of this workload, all launches of
                                # the class in one step): warp instructions x 32 lanes per second of the align phase

@@ -215,6 +215,11 @@ void  wfacuda_host_free(void *p);
 int   wfacuda_host_register(void *p, size_t bytes);
 int   wfacuda_host_unregister(void *p);
 
+/* Measured INT32 issue peaks of the ctx's device in thread-level Tops/s (the roofline of SURVEY
+ * section 8d names INT32 issue as a bound and asks for a measured peak): add / xor only, and add
+ * alternating with mad.lo (integer ALU pipe + FMA pipe). */
+int wfacuda_measure_issue_peak(wfacuda_ctx *ctx, double *alu_tops, double *mixed_tops);
+
 int wfacuda_get_stats(const wfacuda_ctx *ctx, wfacuda_stats *out);
 /* Last error text of the ctx (or of the calling thread when ctx is NULL). */
 const char *wfacuda_last_error(const wfacuda_ctx *ctx);

@@ -100,7 +100,7 @@ EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
            "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error",
            "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister",
-           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components"]
+           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components", "wfacuda_measure_issue_peak"]
 
 _LIB = None
 
@@ -136,6 +136,8 @@ def load_library():
     L.wfacuda_batch_render.restype = C.c_int
     L.wfacuda_batch_render.argtypes = [vp, vp, C.c_int, vp, u64, vp, vp, vp, u64, vp, vp]
     L.wfacuda_last_render_total.argtypes = [vp, vp, vp]
+    L.wfacuda_measure_issue_peak.restype = C.c_int
+    L.wfacuda_measure_issue_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.wfacuda_align_components.restype = C.c_int
     L.wfacuda_align_components.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, u64, vp, C.c_uint32, vp, vp, u64, vp]
     L.wfacuda_align_batch_multi.restype = C.c_int
@@ -594,6 +596,13 @@ class Aligner:
                 raise WfaError("wfacuda_align_batch_multi failed (%d): %s" % (rc, self._err()))
             total = int(self._L.wfacuda_last_ops_total(self._ctx)) if want_ops else 0
             return results, ops[:total], ops_off
+
+    def measure_int32_peak(self):
+        """(add/xor only, add + mad.lo) INT32 issue peaks of the device in thread-level Tops/s."""
+        a, b = C.c_double(0), C.c_double(0)
+        if self._L.wfacuda_measure_issue_peak(self._ctx, C.byref(a), C.byref(b)) != 0:
+            raise WfaError(self._err())
+        return a.value, b.value
 
     def stats(self):
         st = Stats()

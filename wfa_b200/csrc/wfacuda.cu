@@ -68,6 +68,42 @@ __global__ void expand_descs_kernel(const WireDesc *__restrict__ w, uint32_t n_p
 }
 } // namespace
 
+namespace {
+/* INT32 issue microbenchmark ("INT32 peak must be measured on the box"): eight
+ * independent chains per thread, mode 0 = add and xor (xor issues on the ALU pipe; ptxas turns part
+ * of the adds into IMAD.IADD on the FMA pipe by itself), mode 1 = add alternating with mad.lo
+ * (ALU pipe + FMA pipe).  Inline PTX, every op mixing in a neighbouring chain, so that nothing is
+ * folded away: 32 ops per thread and iteration in the SASS. */
+template <int mode>
+__global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *out, int iters)
+{
+    uint32_t a[8];
+    const uint32_t b = threadIdx.x * 2654435761u + 12345u, c = blockIdx.x | 1u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = b + (uint32_t)j;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            /* every op mixes in a neighbouring chain, so that ptxas cannot fold repeated steps */
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (mode == 0) {
+                    if (u & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(a[(j + 1) & 7]));
+                    else       asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[j]) : "r"(a[(j + 3) & 7]));
+                } else {
+                    if (u & 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(a[(j + 1) & 7]));
+                    else       asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(a[(j + 3) & 7]), "r"(c));
+                }
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= a[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+} // namespace
+
 struct wfacuda_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;     /* the stream work is issued on (normally stream_main) */
@@ -1367,6 +1403,36 @@ int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len,
         }
         r++;
     }
+    return 0;
+}
+
+/* Measured INT32 instruction-issue peaks of the ctx's device, in thread-level Tops/s: add / xor
+ * only (ALU pipe) and add + mad.lo alternating (ALU + FMA pipes) -- the denominators of the INT32
+ * roofline in bench.py. */
+int wfacuda_measure_issue_peak(wfacuda_ctx *ctx, double *alu_tops, double *mixed_tops)
+{
+    if (!ctx || !alu_tops || !mixed_tops) return fail(ctx, WFACUDA_E_INVALID, "NULL argument");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    DevBuf out;
+    int rc = ensure(ctx, out, (size_t)blocks * threads * 4);
+    if (rc) return rc;
+    double res[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {                    /* first repetition warms up */
+            cudaEventRecord(ctx->ev[0], ctx->stream);
+            if (mode == 0) int32_peak_kernel<0><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)out.p, iters);
+            else           int32_peak_kernel<1><<<blocks, threads, 0, ctx->stream>>>((uint32_t *)out.p, iters);
+            cudaEventRecord(ctx->ev[1], ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaFree(out.p); return fail(ctx, WFACUDA_E_CUDA, "int32 peak kernel failed: %s", cudaGetErrorString(cudaGetLastError())); }
+            float ms = 0; cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+            if (rep > 0) best = std::min(best, ms);
+        }
+        res[mode] = (double)blocks * threads * (double)iters * 32.0 / (best * 1e-3) / 1e12;
+    }
+    cudaFree(out.p);
+    *alu_tops = res[0]; *mixed_tops = res[1];
     return 0;
 }
 
