@@ -792,20 +792,24 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   lane kernels: host launch at %.2f (took %.2f), sync returned %.2f ms since call; device span %.3f ms\n", tl0 - g_dbg_t0, tl1 - tl0, now_ms() - g_dbg_t0, (hc.t_last - hc.t_first) / 1e6);
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d stages (ends %d %d %d %d; entered %llu %llu %llu), rows %d, slot0 %.1f KB, %.1f MB device, retry %llu\n", attempt, order.size(), G.n_stages, G.stage_end[0], G.stage_end[1], G.stage_end[2], G.stage_end[3], (unsigned long long)hc.lane_count[1], (unsigned long long)hc.lane_count[2], (unsigned long long)hc.lane_count[3], G.n_rows, G.slot_words[0] / 256.0, total / 1e6, (unsigned long long)hc.retry_n);
-        /* learn the next batch's stage boundaries: the score indices by which 30 %, 75 % and
-         * 92 % of the sampled pairs had finished (first attempt of a batch only) */
+        /* learn the next batch's stage boundaries: the score indices by which 40 % and 85 % of
+         * the sampled pairs had finished (first attempt of a batch only) */
         if (attempt == 0) {
             uint64_t tot = 0;
             for (int i = 0; i < 64; i++) tot += hc.lane_hist[i];
             if (tot >= 256) {
                 for (int i = 0; i < 64; i++) ctx->lane_hist[i] = hc.lane_hist[i];
                 ctx->lane_hist_n = tot;
-                const double qs[3] = {0.30, 0.75, 0.92};
+                double qs[3] = {0.40, 0.85, 1.0}; int nq = 2;           /* measured best on config 2 (profiles/r1_lane_stages.md) */
+                if (const char *e = getenv("WFACUDA_LANE_QUANTILES")) {          /* e.g. "0.3,0.8": experiments */
+                    nq = 0;
+                    for (const char *p = e; *p && nq < 3; ) { char *end; const double v = strtod(p, &end); if (end == p) break; qs[nq++] = v; p = *end ? end + 1 : end; }
+                }
                 ctx->lane_n_bounds = 0;
                 uint64_t cum = 0; int qi = 0;
-                for (int i = 0; i < 64 && qi < 3; i++) {
+                for (int i = 0; i < 64 && qi < nq; i++) {
                     cum += hc.lane_hist[i];
-                    while (qi < 3 && (double)cum >= qs[qi] * (double)tot) {
+                    while (qi < nq && (double)cum >= qs[qi] * (double)tot) {
                         if (ctx->lane_n_bounds == 0 || ctx->lane_bounds[ctx->lane_n_bounds - 1] < i) ctx->lane_bounds[ctx->lane_n_bounds++] = i;
                         qi++;
                     }
