@@ -139,12 +139,23 @@ struct wfacuda_ctx {
     /* Pipeline workers take turns on the H2D copy engine: copies issued from several streams at
      * once are served round-robin, so every chunk would arrive late and no kernel could start
      * before most of the batch is across PCIe; one chunk at a time keeps arrival FIFO. */
-    struct Turns {                     /* counting semaphore */
-        std::mutex mu; std::condition_variable cv; int free_slots = 1;
+    struct Turns {                     /* counting semaphore, optionally served in ticket (= chunk) order */
+        std::mutex mu; std::condition_variable cv; int free_slots = 1; uint64_t next_ticket = 0;
         void acquire() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return free_slots > 0; }); free_slots--; }
-        void release() { { std::lock_guard<std::mutex> lk(mu); free_slots++; } cv.notify_one(); }
+        /* uploads go out in chunk order, so that the small chunks at the end of a batch really are
+         * the last ones across PCIe (a worker that is free early would otherwise overtake) */
+        void acquire_ordered(uint64_t ticket)
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return free_slots > 0 && next_ticket >= ticket; });
+            free_slots--; if (next_ticket == ticket) next_ticket = ticket + 1;
+            lk.unlock(); cv.notify_all();
+        }
+        void pass(uint64_t ticket) { { std::lock_guard<std::mutex> lk(mu); if (next_ticket <= ticket) next_ticket = ticket + 1; } cv.notify_all(); }
+        void release() { { std::lock_guard<std::mutex> lk(mu); free_slots++; } cv.notify_all(); }
     } h2d_turns;                       /* owned by the parent ctx; one copy at a time measured best (WFACUDA_H2D_TURNS) */
     Turns *h2d_turn = nullptr;         /* set in a worker ctx: the parent's semaphore */
+    int64_t h2d_ticket = -1;           /* worker: index of the chunk it is about to upload (-1: unordered) */
     /* The pipeline workers' sequence uploads all go through ONE stream of the parent ctx: copies
      * queued on one stream run back to back in FIFO order with no host round trip between them
      * (the semaphore above left ~50 us of PCIe idle per chunk: sync wake-up, hand-over, launch);
@@ -1074,7 +1085,8 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
              * copies in the order they were issued, whatever stream they are on */
             wfacuda_ctx *par = ctx->h2d_parent;
             if (wire && (rc = ensure(ctx, ctx->wire_dev, n_pairs * sizeof(WireDesc)))) return rc;
-            ctx->h2d_turn->acquire();            /* bounded queue depth: released when this chunk's copies are done */
+            /* bounded queue depth, chunk order: released when this chunk's copies are done */
+            if (ctx->h2d_ticket >= 0) ctx->h2d_turn->acquire_ordered((uint64_t)ctx->h2d_ticket); else ctx->h2d_turn->acquire();
             std::lock_guard<std::mutex> lk(par->h2d_mu);
             if (wire) CU(ctx, cudaMemcpyAsync(ctx->wire_dev.p, ctx->pin_descs, n_pairs * sizeof(WireDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
             else CU(ctx, cudaMemcpyAsync(b->d_descs, b->descs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
@@ -1544,6 +1556,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     /* uploads in flight: with the shared FIFO stream two keep the copy engine fed back to back
      * (the next copy is already queued when one completes) without letting chunks arrive late */
     ctx->h2d_turns.free_slots = ctx->h2d_fifo && !getenv("WFACUDA_NO_FIFO") ? 2 : 1;
+    ctx->h2d_turns.next_ticket = 0;
     if (const char *e = getenv("WFACUDA_H2D_TURNS")) ctx->h2d_turns.free_slots = std::max(1, atoi(e));
     std::atomic<uint64_t> cursor{0};
     std::atomic<int> first_err{0};
@@ -1559,10 +1572,13 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
          * sizes again, so none of its device buffers (arena, staging) is ever re-allocated after
          * the first call -- a cudaMalloc / cudaFree in the middle of a batch stalls the whole device */
         for (uint64_t c = (uint64_t)k; c < n_chunks; c += (uint64_t)K) {
-            if (first_err.load()) break;
+            if (first_err.load()) { ctx->h2d_turns.pass(n_chunks); break; }      /* nobody may wait for a chunk that will not come */
             const uint64_t a = cuts[c], cnt = cuts[c + 1] - cuts[c];
             const double w0 = now_ms();
+            sub->h2d_ticket = getenv("WFACUDA_UNORDERED_UPLOADS") ? -1 : (int64_t)c;
             wfacuda_batch *b = wfacuda_batch_upload(sub, cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
+            ctx->h2d_turns.pass(c);            /* whatever happened in there, later chunks may go */
+            sub->h2d_ticket = -1;
             const double w1 = now_ms();
             int rc = b ? wfacuda_batch_run(sub, b) : (sub->last_rc ? sub->last_rc : WFACUDA_E_CUDA);
             const double w2 = now_ms();
@@ -1579,6 +1595,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
                 std::lock_guard<std::mutex> lk(mu);
                 add_stats(total, sub->stats);
                 if (rc != 0 && first_err.load() == 0) { first_err.store(rc); err_text = sub->err; }
+                if (rc != 0) ctx->h2d_turns.pass(n_chunks);
             }
             if (b) wfacuda_batch_free(sub, b);
         }
