@@ -974,7 +974,6 @@ __device__ __forceinline__ void group_emit(const KParams &P, const bool have, co
  * backtrace costs one warp instruction stream for the whole group instead of one per pair. */
 __device__ __noinline__ void finish_group(const KParams &P, const bool have, const uint32_t pair, const FwdOut &f, uint8_t *slot, const uint64_t slot_bytes)
 {
-    const int lane = threadIdx.x & 31;
     RowHdr   *hdrs  = reinterpret_cast<RowHdr *>(slot);
     uint32_t *cells = reinterpret_cast<uint32_t *>(slot);
     const uint64_t slot_words = slot_bytes >> 2, top = f.top;

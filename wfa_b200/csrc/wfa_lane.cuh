@@ -528,7 +528,6 @@ struct LaneView {
 __device__ __forceinline__ void lane_finish(const KParams &P, const bool have, const uint32_t ticket, const uint32_t pair,
                                             const LaneGeomS *Gs, const uint32_t **seg, uint16_t *sops, const bool sample, WorkAcc *acc)
 {
-    const uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const LaneGeom &G = P.lg;
     int status = ST_PENDING; bool first_eq = false; int my_si = 0, nseg = 0;
