@@ -112,6 +112,25 @@ def test_lane_worker_boundaries(built_lib):
     parity.check(batch, what="lane boundaries, LANE off", gpu_kw=dict(flags=api.FLAG_NO_LANE))
 
 
+def test_lane_stages_follow_a_changing_workload(built_lib):
+    """The LANE class cuts its rows into stages at the quantiles of the PREVIOUS batch's final
+    scores and sizes the later stages' slots from that histogram.  Batches whose score
+    distribution jumps (low error -> high error -> short reads -> low error) on one aligner must
+    stay exact: pairs that find a later stage full are re-queued."""
+    a = parity.make_aligner()
+    try:
+        for it, (L, e) in enumerate(((150, 0.02), (150, 0.12), (60, 0.05), (200, 0.08), (150, 0.02))):
+            batch = datagen.generate(6000, L, e, config=2, first=it * 6000)
+            for rep in range(2):                                    # second run uses what the first learned
+                gpu = a.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len, copy=True)
+                st = a.stats()
+                ref = parity.oracle_batch(batch) if rep == 0 else ref
+                parity.assert_same(batch, gpu, ref, "L=%d e=%.2f run %d" % (L, e, rep))
+                assert st["pairs_lane"] > 0 and st["cells"] == ref[3]["cells"], (L, e, rep, st)
+    finally:
+        a.close()
+
+
 def test_text_and_8bit_path(built_lib):
     pairs = _random_pairs(11, 200, alpha=b"abcdefgh -N") + [(b"Bioinformatics helps Biology", b"We learn bioinformatics to help biologists"),
                                                             (b"acgt", b"ACGT"), (b"ACGTN", b"ACGTN")]
