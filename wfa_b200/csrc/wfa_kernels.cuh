@@ -65,6 +65,8 @@ struct Counters {              /* device-side work counters, one set per launch 
     unsigned long long lane_count[8];     /* LANE class: [j] pairs entering stage j, [4 + j] group queue of stage j */
     unsigned int lane_hist[64];           /* LANE class: sampled histogram of the final score index (next batch's stage boundaries) */
     unsigned long long dump_rows;         /* single-worker launches: row headers the forward pass wrote (wfacuda_align_components) */
+    unsigned long long retry2_n;          /* hand-over launch (KParams.handover): its own failures, listed in its own retry buffer */
+    unsigned long long handover_other;    /* hand-over launch: entries of the LANE list it left alone (not ST_RING) */
 };
 
 /* LANE class (wfa_lane.cuh).  Without heuristic the loop range of `next` depends only on which
@@ -112,6 +114,11 @@ struct KParams {
     int32_t  group;            /* WARP kernel: pairs per group (1..32), slot_bytes = group * sub-slot */
     int32_t  seq_cap;          /* WARP kernel: 32-bit words of shared memory per warp for the pair's 2-bit sequences (0: read them from global) */
     uint8_t  global_aln, adaptive, semi_literal;
+    /* Hand-over launch of the WARP kernel: the work list is the retry list the LANE class just wrote
+     * (status << 32 | pair, Counters.retry_n entries, only known on the device); entries with
+     * ST_RING are aligned, the others are counted in Counters.handover_other and left to the host. */
+    const uint64_t *handover;
+    unsigned long long *retry_ctr;   /* where this launch counts its failures: &Counters.retry_n, or &Counters.retry2_n */
     uint8_t  single_worker;    /* only worker 0 takes work: its slot then holds the one pair's whole wavefront store (wfacuda_align_components) */
     int32_t  min_wf_len, max_dist_diff;
     LaneGeom lg;               /* LANE kernels only */
@@ -874,7 +881,7 @@ __device__ void finish_single(const KParams &P, const uint32_t pair, const FwdOu
     if (tid == 0) {
         res.status = (uint8_t)status;
         if (status != ST_OK) {
-            const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+            const unsigned long long r = atomicAdd(P.retry_ctr, 1ull);
             P.retry[r] = (uint64_t)status << 32 | pair;
         } else {
             atomicAdd(&P.ctr->cells, f.c_cells); atomicAdd(&P.ctr->cells_written, f.c_written);
@@ -945,7 +952,7 @@ __device__ __forceinline__ void group_emit(const KParams &P, const bool have, co
     if (have) {
         res.status = (uint8_t)status;
         if (status != ST_OK) {
-            const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+            const unsigned long long r = atomicAdd(P.retry_ctr, 1ull);
             P.retry[r] = (uint64_t)status << 32 | pair;
         }
         P.results[pair] = res;
@@ -1035,7 +1042,7 @@ align_kernel(const KParams P)
             const uint32_t pair = P.work ? P.work[item] : item;
             if (BITS == 2 && (P.pflags[pair] & 1)) {
                 if (threadIdx.x == 0) {
-                    const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+                    const unsigned long long r = atomicAdd(P.retry_ctr, 1ull);
                     P.retry[r] = (uint64_t)ST_NEED8 << 32 | pair;
                 }
                 continue;
@@ -1049,20 +1056,26 @@ align_kernel(const KParams P)
         const int lane = threadIdx.x & 31;
         const uint32_t G = (uint32_t)P.group;
         const uint64_t sub_bytes = P.slot_bytes / G;
+        const uint32_t n_work = P.handover ? (uint32_t)P.ctr->retry_n : P.n_work;
         for (;;) {
             uint32_t first = 0;
             if (lane == 0) first = (uint32_t)atomicAdd(&P.ctr->work_next, (unsigned long long)G);
             first = __shfl_sync(0xffffffffu, first, 0);
-            if (first >= P.n_work) break;
-            const uint32_t cnt = min(G, P.n_work - first);
+            if (first >= n_work) break;
+            const uint32_t cnt = min(G, n_work - first);
             FwdOut mine; mine.status = ST_PENDING; mine.minS = 0; mine.lastK = 0; mine.si = 0; mine.n = mine.m = 0; mine.top = 0;
             mine.c_cells = mine.c_written = mine.c_steps = 0;
             bool have = false; uint32_t my_pair = 0;
             for (uint32_t j = 0; j < cnt; j++) {
-                const uint32_t pair = P.work ? P.work[first + j] : first + j;
+                uint32_t pair;
+                if (P.handover) {
+                    const uint64_t e = P.handover[first + j];
+                    if ((uint32_t)(e >> 32) != ST_RING) { if (lane == 0) atomicAdd(&P.ctr->handover_other, 1ull); continue; }
+                    pair = (uint32_t)e;
+                } else pair = P.work ? P.work[first + j] : first + j;
                 if (BITS == 2 && (P.pflags[pair] & 1)) {
                     if (lane == 0) {
-                        const unsigned long long r = atomicAdd(&P.ctr->retry_n, 1ull);
+                        const unsigned long long r = atomicAdd(P.retry_ctr, 1ull);
                         P.retry[r] = (uint64_t)ST_NEED8 << 32 | pair;
                     }
                     continue;

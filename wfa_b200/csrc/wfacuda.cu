@@ -170,6 +170,7 @@ struct wfacuda_ctx {
     uint64_t render_cigar_total = 0, render_text_total = 0;
     /* wfacuda_align_components: one pair on one worker, whose slot is read back afterwards */
     bool dump_mode = false, dump_cta = false; uint64_t dump_slot_bytes = 0, dump_rows = 0;
+    uint64_t lane_handed = 0;          /* pairs of the last run that the LANE class handed to the WARP kernel on the device */
     const wfacuda_batch *pin_descs_owner = nullptr;
 };
 
@@ -518,7 +519,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         KParams P = base;
         P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
-        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
+        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc; P.retry_ctr = &dc->retry_n;
         P.ring_cap = lp.ring_cap; P.seq_cap = lp.seq_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         if (ctx->dump_mode) { P.single_worker = 1; P.semi_literal = 1; ctx->dump_cta = cta; ctx->dump_slot_bytes = lp.slot_bytes * lp.group; }
         const double tk0 = now_ms();
@@ -745,10 +746,22 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             total += (round_pairs * G.state_words * 4 + 255) & ~255ull;
             for (int j = 1; j < G.n_stages; j++) { list_off[j] = total; total += (cap[j] * 32 * 4 + 255) & ~255ull; }
         }
+        /* Hand-over on the device: the pairs the byte rings cannot hold (ST_RING in the retry list
+         * the finish kernel writes) go to a WARP launch queued right behind the finish kernel, which
+         * reads that list and its length from device memory -- no host round trip in between.  Its
+         * slots are generous (these are the high-score pairs); what still fails there (wider ring,
+         * more arena, ops pool) lands in a second list and takes the host path below. */
+        const uint32_t Lmax = b->lane_maxlen;
+        const uint64_t ho_slot = (std::max<uint64_t>(estimate(ctx, Lmax, Lmax).arena * 4, 65536) + 255) & ~255ull;
+        const int ho_seq_cap = (int)((((Lmax + 15) >> 4) * 2 + 2 + 3) & ~3u);
+        const size_t ho_smem = worker_smem_bytes<false>(ctx->dM, ctx->dE, 64, ho_seq_cap) * 4;
+        const int ho_blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->sm_count, (order.size() + 511) / 512));
+        const bool handover = !getenv("WFACUDA_HOST_HANDOVER") && ho_smem <= ctx->smem_optin && ho_slot * (uint64_t)ho_blocks * 4 <= budget;
+        const uint64_t retry2_off = order.size() + 2;                          /* in 8-byte entries */
         int rc;
-        if ((rc = ensure(ctx, ctx->arena, total))) return rc;
+        if ((rc = ensure(ctx, ctx->arena, std::max<uint64_t>(total, handover ? ho_slot * (uint64_t)ho_blocks * 4 : 0)))) return rc;
         if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->retry, order.size() * 8 + 16))) return rc;
+        if ((rc = ensure(ctx, ctx->retry, (retry2_off + order.size() + 2) * 8))) return rc;
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         Counters *dc = (Counters *)ctx->ctr.p;
         CU(ctx, dev_fill(&dc->retry_n, 0, 8, ctx->stream));
@@ -763,7 +776,7 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         }
         P.la.rec = (uint32_t *)(abase + rec_off); P.la.state = (uint32_t *)(abase + state_off);
         P.arena = abase; P.slot_bytes = (uint64_t)G.slot_words[0] * 4; P.group = sw;      /* LANE kernel: group = words per sequence */
-        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc;
+        P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc; P.retry_ctr = &dc->retry_n;
         P.ring_cap = kLaneW; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         int stage_w[LANE_MAX_STAGES];
         {
@@ -797,6 +810,18 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             CU(ctx, cudaGetLastError());
             ctx->stats.kernel_launches += G.n_stages + 1; ctx->stats.align_launches++;
         }
+        if (handover) {
+            CU(ctx, dev_fill(&dc->work_next, 0, 8, ctx->stream));
+            CU(ctx, dev_fill(&dc->retry2_n, 0, 16, ctx->stream));              /* retry2_n, handover_other */
+            KParams H = base;
+            H.handover = (const uint64_t *)ctx->retry.p; H.retry = (uint64_t *)ctx->retry.p + retry2_off; H.retry_ctr = &dc->retry2_n;
+            H.ctr = dc; H.work = nullptr; H.n_work = 0;
+            H.arena = (uint8_t *)ctx->arena.p; H.slot_bytes = ho_slot; H.group = 1; H.ring_cap = 64; H.seq_cap = ho_seq_cap;
+            H.ops_pool = (uint64_t *)ctx->ops_pool.p; H.ops_cap = ctx->ops_pool.cap / 8;
+            align_kernel<2, false><<<ho_blocks, 128, ho_smem, ctx->stream>>>(H);
+            CU(ctx, cudaGetLastError());
+            ctx->stats.kernel_launches++; ctx->stats.align_launches++;
+        }
         const double tl1 = now_ms();
         ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, total);
         Counters hc;
@@ -827,16 +852,29 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
                 }
             }
         }
-        std::vector<uint64_t> rl(hc.retry_n);
+        if (handover && hc.retry2_n == 0 && hc.handover_other == 0) {
+            /* every entry of the list was a ring overflow and the WARP launch aligned them all */
+            ctx->lane_handed += hc.retry_n;
+            break;
+        }
+        std::vector<uint64_t> rl(hc.retry_n), rl2(handover ? hc.retry2_n : 0);
         if (hc.retry_n) { int rc2 = fetch_small(ctx, rl.data(), ctx->retry.p, hc.retry_n * 8); if (rc2) return rc2; }
+        if (!rl2.empty()) { int rc2 = fetch_small(ctx, rl2.data(), (const uint64_t *)ctx->retry.p + retry2_off, rl2.size() * 8); if (rc2) return rc2; }
         std::vector<uint32_t> again;
         bool ops_full = false;
+        uint64_t rings = 0;
         for (uint64_t r : rl) {
             const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
-            if (st == ST_RING) to_warp->push_back(pair);
+            if (st == ST_RING) { if (handover) rings++; else to_warp->push_back(pair); }
             else if (st == ST_NEED8) to_8bit->push_back(pair);
             else { again.push_back(pair); if (st == ST_OPS) ops_full = true; }
         }
+        for (uint64_t r : rl2) {                                               /* what the hand-over launch could not place */
+            const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
+            if (st == ST_NEED8) to_8bit->push_back(pair); else to_warp->push_back(pair);
+            if (st == ST_OPS) ops_full = true;
+        }
+        if (handover) ctx->lane_handed += rings - std::min<uint64_t>(rings, rl2.size());
         if (hc.retry_n == 0) break;
         ctx->stats.retries += (uint32_t)again.size();
         if (ops_full && (rc = grow_ops_pool(ctx, hc.ops_cursor))) return rc;
@@ -1236,9 +1274,10 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     /* everything after the first (big) launch of a batch has been waited for by the host, so
      * moving to the high-priority stream needs no event; restored (and drained) before returning */
     struct StreamGuard { wfacuda_ctx *c; ~StreamGuard() { if (c->stream != c->stream_main) { cudaStreamSynchronize(c->stream); c->stream = c->stream_main; } } } guard{ctx};
+    ctx->lane_handed = 0;
     if ((rc = run_lane_class(ctx, b, b->order_lane, b->identity_cls == 2, P, &to_warp, &warp8))) return rc;
     if (!b->order_lane.empty()) ctx->stream = ctx->stream_hi;
-    ctx->stats.pairs_lane = (uint32_t)(b->order_lane.size() - to_warp.size() - warp8.size());
+    ctx->stats.pairs_lane = (uint32_t)(b->order_lane.size() - to_warp.size() - warp8.size() - ctx->lane_handed);
     std::vector<uint32_t> warp_extra;                       /* only built when the LANE class handed pairs over */
     if (!to_warp.empty()) { warp_extra = b->order_warp; warp_extra.insert(warp_extra.end(), to_warp.begin(), to_warp.end()); }
     const std::vector<uint32_t> &warp_order = to_warp.empty() ? b->order_warp : warp_extra;
@@ -1248,7 +1287,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     std::vector<uint32_t> cta_extra;
     if (!to_cta.empty()) { cta_extra = b->order_cta; cta_extra.insert(cta_extra.end(), to_cta.begin(), to_cta.end()); }
     const std::vector<uint32_t> &cta_order = to_cta.empty() ? b->order_cta : cta_extra;
-    ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size());
+    ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size() + ctx->lane_handed);
     ctx->stats.pairs_cta = (uint32_t)cta_order.size();
     if ((rc = run_class(ctx, b, cta_order, b->identity_cls == 1 && to_cta.empty(), true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
     if ((rc = run_class(ctx, b, cta8, false, true, 8, P, nullptr, nullptr))) return rc;
