@@ -1554,7 +1554,12 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     {
         const uint64_t C = chunk_pairs;
         std::vector<uint64_t> head, tail;
-        if (n_pairs >= 6 * C && C >= 32768 && !getenv("WFACUDA_UNIFORM_CHUNKS")) { head = {C / 8, C / 4, C / 2}; tail = {C / 2, C / 4}; }
+        if (n_pairs >= 6 * C && C >= 32768 && !getenv("WFACUDA_UNIFORM_CHUNKS")) {
+            head = {C / 8, C / 4, C / 2};
+            int levels = 2;
+            if (const char *e = getenv("WFACUDA_TAIL_LEVELS")) levels = std::max(0, std::min(5, atoi(e)));
+            for (int l = 1; l <= levels; l++) tail.push_back(C >> l);
+        }
         uint64_t used = 0;
         for (uint64_t h : head) used += h;
         for (uint64_t t : tail) used += t;
