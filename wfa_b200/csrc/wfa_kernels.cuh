@@ -59,14 +59,19 @@ struct Result {                /* == wfacuda_result */
     uint8_t  pad_[3];
 };
 
-struct Counters {              /* device-side work counters, one set per launch */
-    unsigned long long cells, cells_written, steps, ops, retry_n, ops_cursor, work_next, arena_used_max;
-    unsigned long long t_first, t_last;   /* globaltimer of the first block start / last block end (LANE kernel, profiling aid) */
-    unsigned long long lane_count[8];     /* LANE class: [j] pairs entering stage j, [4 + j] group queue of stage j */
-    unsigned int lane_hist[64];           /* LANE class: sampled histogram of the final score index (next batch's stage boundaries) */
-    unsigned long long dump_rows;         /* single-worker launches: row headers the forward pass wrote (wfacuda_align_components) */
+struct Counters {              /* device-side work counters, one set per run */
+    unsigned long long cells, cells_written, steps, ops, ops_cursor;    /* accumulate over all launches of a run */
+    /* --- reset before every class launch with ONE fill: [retry_n, launch_end) ------------------- */
+    unsigned long long retry_n, work_next, arena_used_max;
+    unsigned long long t_last;            /* globaltimer of the last block end (LANE kernels, profiling aid) */
     unsigned long long retry2_n;          /* hand-over launch (KParams.handover): its own failures, listed in its own retry buffer */
     unsigned long long handover_other;    /* hand-over launch: entries of the LANE list it left alone (not ST_RING) */
+    unsigned long long lane_count[8];     /* LANE class: [j] pairs entering stage j, [4 + j] group queue of stage j */
+    unsigned int lane_hist[64];           /* LANE class: sampled histogram of the final score index (next batch's stage boundaries) */
+    unsigned long long launch_end;        /* (marker: end of the per-launch block) */
+    /* ------------------------------------------------------------------------------------------- */
+    unsigned long long t_first;           /* globaltimer of the first block start (only initialised under WFACUDA_DEBUG) */
+    unsigned long long dump_rows;         /* single-worker launches: row headers the forward pass wrote (wfacuda_align_components) */
 };
 
 /* LANE class (wfa_lane.cuh).  Without heuristic the loop range of `next` depends only on which

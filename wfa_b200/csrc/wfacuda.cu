@@ -224,6 +224,7 @@ __global__ void fill_kernel(uint4 *p16, size_t n16, unsigned char *p1, size_t n1
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p16[i] = v;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n1; i += (size_t)gridDim.x * blockDim.x) p1[i] = (unsigned char)byte;
 }
+thread_local uint32_t g_fill_launches = 0;     /* fill kernels launched by this thread (counted into stats.kernel_launches per run) */
 cudaError_t dev_fill(void *p, int byte, size_t bytes, cudaStream_t stream)
 {
     if (!bytes) return cudaSuccess;
@@ -231,10 +232,11 @@ cudaError_t dev_fill(void *p, int byte, size_t bytes, cudaStream_t stream)
     size_t head = (16 - ((uintptr_t)c & 15)) & 15; if (head > bytes) head = bytes;
     /* bytes before the first 16-byte boundary and after the last one go through the byte loop */
     const size_t n16 = (bytes - head) / 16, tail = bytes - head - n16 * 16;
-    if (head) fill_kernel<<<1, 32, 0, stream>>>(nullptr, 0, c, head, (unsigned int)(byte & 255));
+    if (head) { fill_kernel<<<1, 32, 0, stream>>>(nullptr, 0, c, head, (unsigned int)(byte & 255)); g_fill_launches++; }
     if (n16 || tail) {
         const int blocks = (int)std::min<size_t>(std::max<size_t>((n16 + 255) / 256, 1), 1184);
         fill_kernel<<<blocks, 256, 0, stream>>>((uint4 *)(c + head), n16, c + head + n16 * 16, tail, (unsigned int)(byte & 255));
+        g_fill_launches++;
     }
     return cudaGetLastError();
 }
@@ -513,9 +515,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         /* reset queue + retry counters, keep the work counters and the ops cursor */
         Counters *dc = (Counters *)ctx->ctr.p;
-        CU(ctx, dev_fill(&dc->retry_n, 0, 8, ctx->stream));
-        CU(ctx, dev_fill(&dc->work_next, 0, 8, ctx->stream));
-        CU(ctx, dev_fill(&dc->arena_used_max, 0, 8, ctx->stream));
+        CU(ctx, dev_fill(&dc->retry_n, 0, (size_t)((char *)&dc->launch_end - (char *)&dc->retry_n), ctx->stream));   /* the per-launch block */
         KParams P = base;
         P.work = ident ? nullptr : (const uint32_t *)ctx->work.p; P.n_work = (uint32_t)order.size();
         P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = lp.slot_bytes * lp.group; P.group = lp.group;
@@ -764,11 +764,9 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         if ((rc = ensure(ctx, ctx->retry, (retry2_off + order.size() + 2) * 8))) return rc;
         if (!ident) { int rc2 = staged_h2d(ctx, ctx->work.p, order.data(), order.size() * 4); if (rc2) return rc2; }
         Counters *dc = (Counters *)ctx->ctr.p;
-        CU(ctx, dev_fill(&dc->retry_n, 0, 8, ctx->stream));
-        CU(ctx, dev_fill(&dc->arena_used_max, 0, 8, ctx->stream));
-        CU(ctx, dev_fill(&dc->t_first, 0xff, 8, ctx->stream));
-        CU(ctx, dev_fill(&dc->t_last, 0, 8, ctx->stream));
-        CU(ctx, dev_fill(dc->lane_hist, 0, sizeof dc->lane_hist, ctx->stream));
+        /* one fill for everything a launch of the class counts (retry lists, queues, histogram) */
+        CU(ctx, dev_fill(&dc->retry_n, 0, (size_t)((char *)&dc->launch_end - (char *)&dc->retry_n), ctx->stream));
+        if (getenv("WFACUDA_DEBUG")) CU(ctx, dev_fill(&dc->t_first, 0xff, 8, ctx->stream));
         uint8_t *abase = (uint8_t *)ctx->arena.p;
         for (int j = 0; j < G.n_stages; j++) {
             P.la.arena[j] = abase + arena_off[j]; P.la.cap[j] = (uint32_t)cap[j];
@@ -794,7 +792,7 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         for (uint64_t g0 = 0; g0 < groups; g0 += round_groups) {
             const uint64_t g1 = std::min(groups, g0 + round_groups);
             const uint64_t p0 = g0 * 32, p1 = std::min<uint64_t>(order.size(), g1 * 32);
-            CU(ctx, dev_fill(dc->lane_count, 0, sizeof dc->lane_count, ctx->stream));
+            if (g0) CU(ctx, dev_fill(dc->lane_count, 0, sizeof dc->lane_count, ctx->stream));      /* later rounds: the stage queues start over */
             P.work = ident ? nullptr : (const uint32_t *)ctx->work.p + p0; P.pair_base = (uint32_t)p0; P.n_work = (uint32_t)(p1 - p0);
             for (int j = 0; j < G.n_stages; j++) {
                 const uint64_t gj = j == 0 ? g1 - g0 : std::min<uint64_t>(cap[j], g1 - g0);
@@ -811,8 +809,6 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             ctx->stats.kernel_launches += G.n_stages + 1; ctx->stats.align_launches++;
         }
         if (handover) {
-            CU(ctx, dev_fill(&dc->work_next, 0, 8, ctx->stream));
-            CU(ctx, dev_fill(&dc->retry2_n, 0, 16, ctx->stream));              /* retry2_n, handover_other */
             KParams H = base;
             H.handover = (const uint64_t *)ctx->retry.p; H.retry = (uint64_t *)ctx->retry.p + retry2_off; H.retry_ctr = &dc->retry2_n;
             H.ctr = dc; H.work = nullptr; H.n_work = 0;
@@ -1226,6 +1222,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     }
     CU(ctx, cudaSetDevice(ctx->device));
     const uint64_t n = b->n_pairs;
+    const uint32_t fills0 = g_fill_launches;
     int rc;
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1303,6 +1300,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     cudaEventElapsedTime(&ctx->stats.ms_pack, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.ms_align, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->stats.ms_total_device, ctx->ev[0], ctx->ev[3]);
+    ctx->stats.kernel_launches += g_fill_launches - fills0;              /* the device fills are kernels of ours too */
     ctx->stats.pairs = n_valid; ctx->stats.cells = hc.cells; ctx->stats.cells_written = hc.cells_written;
     ctx->stats.score_steps = hc.steps; ctx->stats.ops = hc.ops; ctx->stats.seq_bases = b->seq_bases;
     b->ops_total = hc.ops_cursor;
