@@ -74,7 +74,7 @@ def _compare_store(q, t, **kw):
     assert res.Score == r["score"] and res.CIGAR(False) == oracle_lib.ops_to_cigar(r["ops"])
     n_cells = 0
     for ci, comp in enumerate((comps.M, comps.I, comps.D)):
-        for s in range(o.max_score() + 1):
+        for s in range(o.max_score() + 1 + 8):          # + the wavefront initComponents seeds at score x
             kr = o.krange(ci, s)
             ks = set(range(kr[0], kr[1] + 1)) if kr else set()
             if comp.HasScore(s):
@@ -83,7 +83,7 @@ def _compare_store(q, t, **kw):
             for k in ks:
                 assert comp.GetRaw(s, k) == o.get_raw(ci, s, k), ("comp %d s %d k %d" % (ci, s, k), q, t, kw)
                 n_cells += 1
-        assert all(s <= o.max_score() for s in comp.W)
+        assert all(s <= o.max_score() + 8 for s in comp.W)
     o.close()
     return n_cells
 
@@ -92,7 +92,8 @@ def test_whole_store_matches_oracle(built_lib):
     """M, I, D cell by cell (offset and backtrace code) on random pairs: global with and without
     wf-adaptive, semi-global (which keeps every score up to the global corner), text bytes."""
     rng = random.Random(11)
-    total = 0
+    total = _compare_store(b"CGGCCCCTG", b"CGGCCCCTG", global_alignment=False, adaptive=(10, 50))   # ends at score 0: M[x] is seed-only
+    total += _compare_store(b"ACGTACGT", b"TTACGTACGTCC", global_alignment=False)
     for it in range(24):
         L = rng.choice([3, 10, 40, 120, 400])
         alpha = b"ACGT" if it % 4 else b"ACGTN acgt"

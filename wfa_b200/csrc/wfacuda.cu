@@ -1437,13 +1437,31 @@ int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len,
         want_rows++; want_cells += 3ull * (uint64_t)(h.hi - h.lo + 1);
         min_off = std::min<uint64_t>(min_off, h.off);
     }
+    /* initComponents (wfa.go:155-183) also seeds M[x] -- the start cells whose first bases differ.
+     * The kernels overlay those cells when they reach score x; an alignment that ends before that
+     * (semi-global, a start cell matches all the way at score 0) never gets there, while the
+     * reference keeps the seeded, un-extended wavefront: it is rebuilt here from the same rule. */
+    std::vector<uint32_t> seed; int seed_lo = 1, seed_hi = 0;
+    if (!ctx->cfg.global_alignment && used_hdr <= (uint32_t)ctx->xg) {
+        const int nq = (int)q_len, nt = (int)t_len;
+        for (int k = -(nq - 1); k <= nt - 1; k++)
+            if (q[k < 0 ? -k : 0] != t[k > 0 ? k : 0]) { if (seed_lo > seed_hi) seed_lo = k; seed_hi = k; }
+        if (seed_lo <= seed_hi) {
+            seed.assign((size_t)(seed_hi - seed_lo + 1), 0u);
+            for (int k = seed_lo; k <= seed_hi; k++)
+                if (q[k < 0 ? -k : 0] != t[k > 0 ? k : 0]) seed[(size_t)(k - seed_lo)] = (uint32_t)((k > 0 ? k : 0) + 1) << T_BITS | T_MISMATCH;
+            want_rows++; want_cells += 3ull * seed.size();
+        }
+    }
     *n_rows = want_rows; *n_cells = want_cells;
     if (want_rows > rows_capacity || want_cells > cells_capacity || (want_rows && (!rows || !cells)))
         return fail(ctx, WFACUDA_E_OPS_CAPACITY, "wavefront store has %u rows / %llu cell words, buffers hold %u / %llu", want_rows, (unsigned long long)want_cells, rows_capacity, (unsigned long long)cells_capacity);
     if (!want_rows) return 0;
-    std::vector<uint32_t> slot(slot_words - min_off);
-    if ((rc = staged_d2h(ctx, slot.data(), (const uint32_t *)ctx->arena.p + min_off, slot.size() * 4))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> slot(slot_words > min_off ? slot_words - min_off : 1);
+    if (slot_words > min_off) {
+        if ((rc = staged_d2h(ctx, slot.data(), (const uint32_t *)ctx->arena.p + min_off, slot.size() * 4))) return rc;
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     uint64_t at = 0; uint32_t r = 0;
     for (uint32_t i = 0; i < used_hdr; i++) {
         const RowHdr &h = hdr[i];
@@ -1455,6 +1473,10 @@ int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len,
             for (int c = 0; c < 3; c++) cells[at++] = ctx->dump_cta ? base[(uint64_t)c * (uint64_t)h.aw + idx] : base[3 * idx + c];
         }
         r++;
+    }
+    if (!seed.empty()) {
+        rows[r].score = ctx->cfg.mismatch; rows[r].lo = seed_lo; rows[r].hi = seed_hi; rows[r].reserved_ = 0; rows[r].first_cell = at;
+        for (uint32_t v : seed) { cells[at++] = v; cells[at++] = 0u; cells[at++] = 0u; }
     }
     return 0;
 }
