@@ -1100,6 +1100,31 @@ align_kernel(const KParams P)
  * One warp per pair: lanes 0-15 stride over the 16-base words of the query, lanes 16-31 over
  * those of the target; 5 aligned 32-bit loads in (neighbouring lanes read neighbouring bytes),
  * one 32-bit word out. */
+/* one 16-base word of a sequence: bytes 16 w .. 16 w + 15 of the `len` bytes at src (byte phase sh) */
+__device__ __forceinline__ uint32_t pack_word(const uint32_t *__restrict__ src, uint32_t w, uint32_t len, uint32_t sh, bool &bad)
+{
+    uint32_t in[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) in[j] = __ldg(src + 4 * w + j);
+    const int left = (int)len - (int)(16 * w);                     /* bases from this word on */
+    uint32_t o = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t x = __funnelshift_r(in[j], in[j + 1], sh);       /* bases 16w+4j .. +3 */
+        if (left < 16) {                                           /* last word: bytes past the end read as 'A' */
+            const int rem = left - 4 * j;
+            if (rem < 4) x = rem <= 0 ? 0x41414141u : ((x & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem)));
+        }
+        const uint32_t c = (x >> 1) & 0x03030303u;
+        /* valid iff every byte equals the letter its code maps back to (A,C,T,G) */
+        const uint32_t sel = (c & 3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
+        bad |= __byte_perm(0x47544341u, 0u, sel) != x;
+        const uint32_t p = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
+        o |= p << (8 * j);
+    }
+    return o;
+}
+
 __global__ void __launch_bounds__(256)
 pack_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t *__restrict__ raw,
             uint32_t *__restrict__ packed, uint8_t *__restrict__ pflags)
@@ -1116,29 +1141,39 @@ pack_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t
         const uint32_t *src = raw + (boff >> 2);
         const uint32_t sh = (uint32_t)(boff & 3) * 8;
         bool bad = false;
-        for (uint32_t w = l16; w < nwords; w += 16) {
-            uint32_t in[5];
-#pragma unroll
-            for (int j = 0; j < 5; j++) in[j] = __ldg(src + 4 * w + j);
-            const int left = (int)len - (int)(16 * w);                     /* bases from this word on */
-            uint32_t o = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t x = __funnelshift_r(in[j], in[j + 1], sh);       /* bases 16w+4j .. +3 */
-                if (left < 16) {                                           /* last word: bytes past the end read as 'A' */
-                    const int rem = left - 4 * j;
-                    if (rem < 4) x = rem <= 0 ? 0x41414141u : ((x & ((1u << (8 * rem)) - 1u)) | (0x41414141u << (8 * rem)));
-                }
-                const uint32_t c = (x >> 1) & 0x03030303u;
-                /* valid iff every byte equals the letter its code maps back to (A,C,T,G) */
-                const uint32_t sel = (c & 3u) | ((c >> 4) & 0x30u) | ((c >> 8) & 0x300u) | ((c >> 12) & 0x3000u);
-                bad |= __byte_perm(0x47544341u, 0u, sel) != x;
-                const uint32_t p = (c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu;
-                o |= p << (8 * j);
-            }
-            out[w] = o;
-        }
+        for (uint32_t w = l16; w < nwords; w += 16) out[w] = pack_word(src, w, len, sh, bad);
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(reinterpret_cast<unsigned int *>(pflags) + (pr >> 2), 1u << ((pr & 3) * 8));
+    }
+}
+
+/* The same for batches of short reads (no sequence longer than 160 bases = 10 words): three
+ * pairs per warp, five lanes per sequence, two words per lane -- 30 of 32 lanes busy for 150-base
+ * reads instead of 20 (the kernel is bound by instruction issue, not by bytes in flight). */
+__global__ void __launch_bounds__(256)
+pack_short_kernel(const PairDesc *__restrict__ pairs, uint32_t n_pairs, const uint32_t *__restrict__ raw,
+                  uint32_t *__restrict__ packed, uint8_t *__restrict__ pflags)
+{
+    const uint32_t lane = threadIdx.x & 31, slot = lane / 5, j5 = lane % 5;     /* slot 0..5 = (pair, sequence), 6 = idle lanes 30, 31 */
+    const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t pr0 = warp0 * 3; pr0 < n_pairs; pr0 += nwarps * 3) {
+        const uint64_t pr = pr0 + (slot >> 1);
+        bool bad = false;
+        if (slot < 6 && pr < n_pairs) {
+            const PairDesc pd = pairs[pr];
+            const uint32_t half = slot & 1;
+            const uint64_t boff = half ? pd.t_byte : pd.q_byte;
+            const uint32_t len = half ? pd.m : pd.n;
+            uint32_t *out = packed + (half ? pd.t_word : pd.q_word);
+            const uint32_t nwords = (len + 15) >> 4;
+            const uint32_t *src = raw + (boff >> 2);
+            const uint32_t sh = (uint32_t)(boff & 3) * 8;
+            if (j5 < nwords) out[j5] = pack_word(src, j5, len, sh, bad);
+            if (j5 + 5 < nwords) out[j5 + 5] = pack_word(src, j5 + 5, len, sh, bad);
+        }
+        const unsigned votes = __ballot_sync(0xffffffffu, bad);
+        if (slot < 6 && (slot & 1) == 0 && j5 == 0 && pr < n_pairs && (votes & (0x3ffu << (10 * (slot >> 1)))))
+            atomicOr(reinterpret_cast<unsigned int *>(pflags) + (pr >> 2), 1u << ((pr & 3) * 8));
     }
 }
 

@@ -186,6 +186,7 @@ struct wfacuda_batch {
     uint32_t n_of(uint64_t i) const { return wire ? wire[i].n : descs[i].n; }
     uint32_t m_of(uint64_t i) const { return wire ? wire[i].m : descs[i].m; }
     uint64_t raw_bytes = 0, packed_words = 0, seq_bases = 0, max_nm = 0;
+    uint32_t max_len = 0;                   /* longest single sequence */
     void *d_raw = nullptr, *d_packed = nullptr, *d_descs = nullptr, *d_flags = nullptr;
     void *d_results = nullptr, *d_where = nullptr;
     size_t sz_raw = 0, sz_packed = 0, sz_descs = 0, sz_flags = 0, sz_results = 0, sz_where = 0;
@@ -954,6 +955,7 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
         cudaFuncSetAttribute(align_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        cudaFuncSetAttribute(pack_short_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaGetLastError();
     }
     return ctx;
@@ -1099,6 +1101,7 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
                 words += ((uint64_t)((dn + 15) >> 4) + 3) & ~3ull;
                 b->seq_bases += (uint64_t)dn + dm;
                 b->max_nm = std::max<uint64_t>(b->max_nm, (uint64_t)dn + dm);
+                b->max_len = std::max(b->max_len, std::max(dn, dm));
             }
             const uint64_t tw = ok ? words : 0;
             if (ok) words += ((uint64_t)((dm + 15) >> 4) + 3) & ~3ull;
@@ -1239,9 +1242,15 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     } else if (n) CU(ctx, dev_fill(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
     const uint64_t n_valid = b->order_warp.size() + b->order_cta.size() + b->order_lane.size();
     if (n_valid) {
-        const int pack_blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);      /* one warp per pair */
-        pack_kernel<<<pack_blocks, 256, 0, ctx->stream>>>((const PairDesc *)b->d_descs, (uint32_t)n, (const uint32_t *)b->d_raw,
-                                                         (uint32_t *)b->d_packed, (uint8_t *)b->d_flags);
+        if (b->max_len <= 160 && !getenv("WFACUDA_PACK_GENERIC")) {
+            const int pack_blocks = (int)std::min<uint64_t>((n + 23) / 24, (uint64_t)ctx->sm_count * 16);   /* three pairs per warp */
+            pack_short_kernel<<<pack_blocks, 256, 0, ctx->stream>>>((const PairDesc *)b->d_descs, (uint32_t)n, (const uint32_t *)b->d_raw,
+                                                                   (uint32_t *)b->d_packed, (uint8_t *)b->d_flags);
+        } else {
+            const int pack_blocks = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);      /* one warp per pair */
+            pack_kernel<<<pack_blocks, 256, 0, ctx->stream>>>((const PairDesc *)b->d_descs, (uint32_t)n, (const uint32_t *)b->d_raw,
+                                                             (uint32_t *)b->d_packed, (uint8_t *)b->d_flags);
+        }
         CU(ctx, cudaGetLastError());
         ctx->stats.kernel_launches++;
     }
