@@ -205,6 +205,12 @@ int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pa
 int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
                        int adaptive, uint64_t *cuts);
 
+/* The chunk boundaries wfacuda_align_batch uses for a batch of n_pairs with chunks of about
+ * chunk_pairs (pure host logic, no GPU): cuts[0] = 0 < ... < cuts[n_cuts - 1] = n_pairs; small
+ * first chunks that double in size, `tail_levels` halving chunks at the end (< 0: uniform). */
+int wfacuda_chunk_plan(uint64_t n_pairs, uint64_t chunk_pairs, int tail_levels,
+                       uint64_t *cuts, uint32_t cuts_capacity, uint32_t *n_cuts);
+
 /* Page-locked host memory for the caller's input / output arrays.  Every entry point accepts
  * any host pointer; arrays that live in memory from wfacuda_host_alloc (or registered with
  * wfacuda_host_register) are moved by the DMA engines directly, without the staging copy

@@ -100,7 +100,7 @@ EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
            "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error",
            "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister",
-           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components", "wfacuda_measure_issue_peak"]
+           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components", "wfacuda_measure_issue_peak", "wfacuda_chunk_plan"]
 
 _LIB = None
 
@@ -142,6 +142,8 @@ def load_library():
     L.wfacuda_align_components.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, u64, vp, C.c_uint32, vp, vp, u64, vp]
     L.wfacuda_align_batch_multi.restype = C.c_int
     L.wfacuda_align_batch_multi.argtypes = [C.POINTER(vp), C.c_int, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
+    L.wfacuda_chunk_plan.restype = C.c_int
+    L.wfacuda_chunk_plan.argtypes = [u64, u64, C.c_int, vp, C.c_uint32, vp]
     L.wfacuda_shard_plan.restype = C.c_int
     L.wfacuda_shard_plan.argtypes = [C.c_int, u64, u32p, u32p, C.c_int, vp]
     L.wfacuda_get_stats.restype = C.c_int
@@ -200,6 +202,16 @@ def shard_plan(n_shards, q_len, t_len, adaptive):
     if rc != 0:
         raise WfaError("wfacuda_shard_plan failed (%d)" % rc)
     return cuts
+
+
+def chunk_plan(n_pairs, chunk_pairs, tail_levels=2):
+    """Chunk boundaries of the pipelined wfacuda_align_batch (host logic only)."""
+    cuts = np.zeros(4096, np.uint64)
+    n = C.c_uint32(0)
+    rc = load_library().wfacuda_chunk_plan(int(n_pairs), int(chunk_pairs), int(tail_levels), cuts.ctypes.data, len(cuts), C.byref(n))
+    if rc != 0:
+        raise WfaError("wfacuda_chunk_plan failed (%d)" % rc)
+    return cuts[:n.value].copy()
 
 
 def device_count():

@@ -1526,6 +1526,48 @@ void wfacuda_last_render_total(const wfacuda_ctx *ctx, uint64_t *cigar_bytes, ui
     if (text_bytes) *text_bytes = ctx ? ctx->render_text_total : 0;
 }
 
+/* Chunk boundaries of the pipeline: cuts[0] = 0 < ... < cuts.back() = n_pairs.  Every worker
+ * validates its chunk before it can queue the upload, so the first chunks are small and double in
+ * size (C/8, C/4, C/2: the copy engine gets its first bytes after an eighth of a chunk's host work
+ * and is never idle afterwards), and the last `tail_levels` ones shrink again (C/2, C/4, ...): what
+ * is left to do when the last upload completes is one small chunk's kernels + download.  Batches
+ * below six chunks, and tail_levels < 0, are cut uniformly.  Inner boundaries are multiples of 32
+ * pairs (whole LANE groups).  Pure host logic (exported as wfacuda_chunk_plan for tests). */
+static std::vector<uint64_t> plan_chunks(uint64_t n_pairs, uint64_t C, int tail_levels)
+{
+    std::vector<uint64_t> cuts{0};
+    C = std::max<uint64_t>(C, 32);
+    std::vector<uint64_t> head, tail;
+    if (tail_levels >= 0 && n_pairs >= 6 * C && C >= 32768) {
+        head = {C / 8, C / 4, C / 2};
+        for (int l = 1; l <= tail_levels; l++) tail.push_back(C >> l);
+    }
+    uint64_t used = 0, tail_total = 0;
+    for (uint64_t h : head) used += h;
+    for (uint64_t t : tail) { used += t; tail_total += t & ~31ull; }
+    const uint64_t rem = n_pairs - used, nm = std::max<uint64_t>(1, (rem + C - 1) / C);
+    for (uint64_t h : head) cuts.push_back(cuts.back() + (h & ~31ull));
+    /* the odd pairs (n_pairs mod 32) go to the very last chunk, so that every inner boundary is a multiple of 32 */
+    const uint64_t mid0 = cuts.back(), mid_total = tail.empty() ? n_pairs - mid0 : ((n_pairs - mid0 - tail_total) & ~31ull);
+    for (uint64_t j = 1; j <= nm; j++) cuts.push_back(j == nm ? mid0 + mid_total : mid0 + ((mid_total * j / nm) & ~31ull));
+    for (size_t j = 0; j < tail.size(); j++) cuts.push_back(j + 1 == tail.size() ? n_pairs : cuts.back() + (tail[j] & ~31ull));
+    /* drop empty chunks (tiny batches) */
+    std::vector<uint64_t> out{0};
+    for (size_t j = 1; j < cuts.size(); j++) if (cuts[j] > out.back()) out.push_back(cuts[j]);
+    if (out.back() != n_pairs) out.push_back(n_pairs);
+    return out;
+}
+
+int wfacuda_chunk_plan(uint64_t n_pairs, uint64_t chunk_pairs, int tail_levels, uint64_t *cuts, uint32_t cuts_capacity, uint32_t *n_cuts)
+{
+    if (!n_cuts) return WFACUDA_E_INVALID;
+    const std::vector<uint64_t> c = plan_chunks(n_pairs, chunk_pairs, tail_levels);
+    *n_cuts = (uint32_t)c.size();
+    if (c.size() > cuts_capacity || !cuts) return WFACUDA_E_OPS_CAPACITY;
+    for (size_t i = 0; i < c.size(); i++) cuts[i] = c[i];
+    return 0;
+}
+
 static int align_batch_single(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
                               const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
                               wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
@@ -1575,29 +1617,9 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     const bool src_pinned = is_pinned(seq_bytes);
     uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 20e6 : 24e6) / mean_bytes)));
     if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
-    /* Chunk boundaries.  Every worker validates its chunk before it can queue the upload, so the
-     * first chunks are small and double in size (the copy engine gets its first bytes after an
-     * eighth of a chunk's host work and is never idle afterwards), and the last ones shrink again:
-     * what is left to do when the last upload completes is one small chunk's kernels + download. */
-    std::vector<uint64_t> cuts{0};
-    {
-        const uint64_t C = chunk_pairs;
-        std::vector<uint64_t> head, tail;
-        if (n_pairs >= 6 * C && C >= 32768 && !getenv("WFACUDA_UNIFORM_CHUNKS")) {
-            head = {C / 8, C / 4, C / 2};
-            int levels = 2;
-            if (const char *e = getenv("WFACUDA_TAIL_LEVELS")) levels = std::max(0, std::min(5, atoi(e)));
-            for (int l = 1; l <= levels; l++) tail.push_back(C >> l);
-        }
-        uint64_t used = 0;
-        for (uint64_t h : head) used += h;
-        for (uint64_t t : tail) used += t;
-        const uint64_t rem = n_pairs - used, nm = std::max<uint64_t>(1, (rem + C - 1) / C);
-        for (uint64_t h : head) cuts.push_back(cuts.back() + (h & ~31ull));
-        const uint64_t mid0 = cuts.back(), mid_total = n_pairs - mid0 - [&] { uint64_t t2 = 0; for (uint64_t t : tail) t2 += t & ~31ull; return t2; }();
-        for (uint64_t j = 1; j <= nm; j++) cuts.push_back(j == nm ? mid0 + mid_total : mid0 + ((mid_total * j / nm) & ~31ull));
-        for (size_t j = 0; j < tail.size(); j++) cuts.push_back(j + 1 == tail.size() ? n_pairs : cuts.back() + (tail[j] & ~31ull));
-    }
+    int tail_levels = 2;
+    if (const char *e = getenv("WFACUDA_TAIL_LEVELS")) tail_levels = std::max(0, std::min(5, atoi(e)));
+    const std::vector<uint64_t> cuts = plan_chunks(n_pairs, chunk_pairs, getenv("WFACUDA_UNIFORM_CHUNKS") ? -1 : tail_levels);
     const uint64_t n_chunks = cuts.size() - 1;
     const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
     /* one worker per chunk in flight: enough of them that uploads (PCIe-bound, taken in turns)
