@@ -223,7 +223,6 @@ def main():
         ms_align += st["ms_align"]; ms_dev += st["ms_total_device"]; launches += st["kernel_launches"]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
     stats = algn.stats()
     results, ops, ops_off = rb.download()
     rb.free()
@@ -243,6 +242,7 @@ def main():
         r2, o2, off2 = algn.align_arrays(*host)
         step_ms.append((time.perf_counter() - t1) * 1e3)
     barrier()
+    clocks = sampler.stop()        # SM clocks / throttle reasons sampled over both timed regions (resident and e2e)
     # every step is timed on its own (host clock around the blocking call); with >= 10 steps the
     # single slowest one is set aside as a host-scheduling outlier and reported, not hidden
     discarded = None
