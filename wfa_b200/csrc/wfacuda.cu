@@ -1632,12 +1632,19 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
         cudaFree(ctx->arena.p); ctx->arena.p = nullptr; ctx->arena.cap = 0;
     }
+    /* the workers created now split 70 % of what is free NOW in equal shares (their arenas grow on
+     * demand, so free memory barely moves while they are created: dividing by the number still to
+     * create, as an earlier version did, handed out 2.6x the free memory over 14 workers and ran
+     * out of memory on config 3 at its full size); the rest is for their batch buffers and ops pools */
+    size_t free_now = 0, total_now = 0;
+    const int to_create = K - (int)ctx->subs.size();
+    if (to_create > 0) {
+        cudaSetDevice(ctx->device);
+        if (cudaMemGetInfo(&free_now, &total_now) != cudaSuccess) { cudaGetLastError(); free_now = 8ull << 30; }
+    }
     while ((int)ctx->subs.size() < K) {
         wfacuda_config c = ctx->cfg;
-        size_t free_b = 0, total_b = 0;
-        cudaSetDevice(ctx->device);
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = 8ull << 30; }
-        uint64_t share = (uint64_t)(0.80 * (double)free_b) / (uint64_t)(K - (int)ctx->subs.size());
+        uint64_t share = (uint64_t)(0.70 * (double)free_now) / (uint64_t)to_create;
         if (ctx->cfg.arena_budget_bytes) share = std::min<uint64_t>(share, ctx->cfg.arena_budget_bytes / (uint64_t)K);
         c.arena_budget_bytes = std::max<uint64_t>(share, 64u << 20);
         wfacuda_ctx *sub = wfacuda_create(ctx->device, &c);
