@@ -26,6 +26,14 @@ def test_header_symbols_exported(built_lib):
         assert hasattr(lib, n), n
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/wfacuda.h is what a cgo / FFI binding includes: it must compile as C99 on its own."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "wfacuda.h"\nint main(void) { wfacuda_result r; wfacuda_wavefront w; wfacuda_config c; (void)r; (void)w; (void)c; return 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                           "-I" + os.path.join(ROOT, "include"), str(src)])
+
+
 def test_built_for_sm100a_only(built_lib):
     out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
