@@ -67,3 +67,35 @@ def check(batch, what="", threads=8, gpu_kw=None, **cfgkw):
     ref = oracle_batch(batch, threads=threads, **cfgkw)
     assert_same(batch, gpu, ref, what)
     return gpu, ref, stats
+
+
+def replay_alignments(batch, res, ops, off, penalties=(4, 6, 2)):
+    """Size-independent check of global alignments: every op list, replayed on its two
+    sequences, consumes both completely ('I' consumes target, 'D' query -- wfa_cigar.go:312-328),
+    has equal bases under 'M' and different ones under 'X', and costs what the result says: the
+    score lies between the cost with every merged gap run opened once and the cost with every gap
+    base opened separately (merged runs hide how often the path re-opened a gap)."""
+    x, o, e = penalties
+    for i in range(len(res)):
+        assert res["status"][i] == 0, i
+        q = batch.seq_bytes[int(batch.q_off[i]):int(batch.q_off[i]) + int(batch.q_len[i])]
+        t = batch.seq_bytes[int(batch.t_off[i]):int(batch.t_off[i]) + int(batch.t_len[i])]
+        w = np.asarray(ops[int(off[i]):int(off[i]) + int(res["n_ops"][i])])
+        op, cnt = (w >> np.uint64(32)).astype(np.int64), (w & np.uint64(0xffffffff)).astype(np.int64)
+        isM, isX, isI, isD = op == ord("M"), op == ord("X"), op == ord("I"), op == ord("D")
+        assert (isM | isX | isI | isD).all(), i
+        dq, dt = np.where(isM | isX | isD, cnt, 0), np.where(isM | isX | isI, cnt, 0)
+        assert dq.sum() == len(q) and dt.sum() == len(t), i
+        q0, t0 = np.cumsum(dq) - dq, np.cumsum(dt) - dt
+        mx = isM | isX
+        tot = int(cnt[mx].sum())
+        base = np.repeat(np.cumsum(cnt[mx]) - cnt[mx], cnt[mx])
+        within = np.arange(tot) - base
+        qi, ti = np.repeat(q0[mx], cnt[mx]) + within, np.repeat(t0[mx], cnt[mx]) + within
+        eq = q[qi] == t[ti]
+        assert np.array_equal(eq, np.repeat(isM[mx], cnt[mx])), i
+        gaps = cnt[isI | isD]
+        lo = x * int(cnt[isX].sum()) + o * len(gaps) + e * int(gaps.sum())
+        hi = x * int(cnt[isX].sum()) + (o + e) * int(gaps.sum())
+        assert lo <= int(res["score"][i]) <= hi, (i, lo, int(res["score"][i]), hi)
+        assert int(res["matches"][i]) <= int(cnt[isM].sum())

@@ -1,4 +1,5 @@
 """GPU parity: libwfacuda.so (through the C ABI) vs the CPU oracle, bit-exact."""
+import os
 import random
 
 import numpy as np
@@ -164,15 +165,83 @@ def test_errors_and_empty(built_lib):
         parity.make_aligner().AdaptiveReduction(api.AdaptiveReductionOption(0, 50, 1))
 
 
-@pytest.mark.parametrize("name,count", [("cfg2_150bp_e5_global", 20000), ("cfg3_1kbp_e10_global_adaptive", 2000),
-                                        ("cfg4_10kbp_in_12kbp_e5_semiglobal", 3), ("cfg5_100kbp_e15_global_adaptive", 2)])
+# Pair counts per config: the oracle run on the GPU box's host cores is the only real cost (a few
+# seconds each for configs 2, 3 and 5, about a minute for the 16 semi-global pairs of config 4).
+@pytest.mark.parametrize("name,count", [("cfg2_150bp_e5_global", 20000), ("cfg3_1kbp_e10_global_adaptive", 100000),
+                                        ("cfg4_10kbp_in_12kbp_e5_semiglobal", 16), ("cfg5_100kbp_e15_global_adaptive", 32)])
 def test_synthetic_configs(built_lib, name, count):
     c = datagen.CONFIGS[name]
     batch = datagen.generate_config(name, count)
-    gpu, ref, stats = parity.check(batch, what=name, global_alignment=c["global_alignment"], adaptive=c["adaptive"])
+    gpu, ref, stats = parity.check(batch, what=name, threads=os.cpu_count() or 8, global_alignment=c["global_alignment"], adaptive=c["adaptive"])
     # device work counter C must equal the oracle's (roofline numerator)
     if c["global_alignment"]:
         assert stats["cells"] == ref[3]["cells"], (stats, ref[3])
+    if c["adaptive"]:
+        assert stats["pairs_reg"] > 0.9 * count, stats           # configs 3 and 5 run on the REG worker
+
+
+def test_config5_shard_shape(built_lib):
+    """Config 5 as one GPU of eight sees it: 1 250 pairs of 100 kbp.  The oracle needs minutes for
+    that many, so: (1) the REG worker (registers, 8-byte offset cells, codes re-derived by the
+    backtrace) against the WARP worker (raw words with codes in a shared-memory ring) on all 1 250
+    -- two independent forward passes and arena formats; (2) the oracle on a 40-pair sample of the
+    same batch; (3) every alignment replayed on its sequences."""
+    name = "cfg5_100kbp_e15_global_adaptive"
+    batch = datagen.generate_config(name, 1250)
+    res = {}
+    for flags in (0, api.FLAG_NO_REG):
+        a = parity.make_aligner(adaptive=(10, 50), flags=flags)
+        try:
+            res[flags] = a.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len, copy=True)
+            st = a.stats()
+            assert (st["pairs_reg"] > 1000) == (flags == 0), st
+        finally:
+            a.close()
+    parity.assert_same(batch, res[0], res[api.FLAG_NO_REG], "config 5 shard: REG vs WARP worker")
+    idx = np.r_[0:16, 600:612, 1238:1250]
+    sub = datagen.Batch(batch.seq_bytes, batch.q_off[idx], batch.q_len[idx], batch.t_off[idx], batch.t_len[idx])
+    ref = parity.oracle_batch(sub, threads=os.cpu_count() or 8, adaptive=(10, 50))
+    r, o, off = res[0]
+    parity.assert_same(sub, (r[idx], o, off[idx]), ref, "config 5 shard: oracle sample")
+    parity.replay_alignments(batch, r, o, off, penalties=(4, 6, 2))
+
+
+def test_reg_worker_boundaries(built_lib):
+    """REG worker (wfa_reg.cuh): rows that outgrow 32 S diagonals (more cells per lane, then the WARP
+    worker), targets around the 2 046-base limit of the 32-bit cell word, non-ACGT pairs (8-bit
+    hand-over), pairs that end at score 0, sequences longer than the shared-memory window."""
+    rng = random.Random(41)
+    rnd = lambda n, al=b"ACGT": bytes(rng.choice(al) for _ in range(n))
+    pairs = []
+    for L in (255, 300, 700, 1000, 2040, 2046, 2047, 2048, 2100, 3000, 5000):
+        q = rnd(L)
+        pairs += [(q, q), (q, _mutate(rng, q, 0.02, b"ACGT")), (q, _mutate(rng, q, 0.12, b"ACGT")), (q[:L - 5], q), (q, q[7:])]
+    for _ in range(60):
+        q = rnd(rng.randint(255, 1500))
+        pairs.append((q, _mutate(rng, q, rng.choice([0.0, 0.01, 0.05, 0.1, 0.2, 0.3]), b"ACGT")))
+    for _ in range(10):                                           # unrelated: wide, high scores
+        pairs.append((rnd(rng.randint(255, 600)), rnd(rng.randint(255, 600))))
+    for _ in range(10):
+        q = rnd(400)
+        t = bytearray(q); t[rng.randrange(400)] = ord("N")
+        pairs.append((q, bytes(t)))
+    rng.shuffle(pairs)
+    batch = datagen.Batch.from_pairs(pairs)
+    for ad in ((10, 50), (3, 5), (1, 2), (10, 200), None):
+        for pen in ((4, 6, 2), (2, 3, 1), (8, 12, 4)):
+            gpu, ref, stats = parity.check(batch, what="reg boundaries ad=%s pen=%s" % (ad, pen), adaptive=ad, mismatch=pen[0], gap_open=pen[1], gap_ext=pen[2])
+            assert stats["cells"] == ref[3]["cells"], (ad, pen, stats, ref[3])
+            if ad in ((10, 50), (3, 5), (1, 2)):
+                assert stats["pairs_reg"] > 0 and stats["pairs_8bit"] > 0, stats
+    # every rung of the ladder forced: what does not fit goes straight to the WARP worker
+    try:
+        for s_ in ("2", "3", "4", "5", "6"):
+            os.environ["WFACUDA_REG_S"] = s_
+            gpu, ref, stats = parity.check(batch, what="reg boundaries S=%s" % s_, adaptive=(10, 50))
+            assert stats["pairs_reg"] > 0 and stats["cells"] == ref[3]["cells"], (s_, stats)
+    finally:
+        os.environ.pop("WFACUDA_REG_S", None)
+    parity.check(batch, what="reg boundaries, REG off", adaptive=(10, 50), gpu_kw=dict(flags=api.FLAG_NO_REG))
 
 
 def test_seqs_txt_config1(built_lib):

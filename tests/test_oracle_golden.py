@@ -98,3 +98,21 @@ def test_known_answer_trace_global():
     assert o.get_raw(M, 12, 0) == 10 << 3 | 5 and o.get_raw(M, 12, 3) == 4 << 3 | 2
     for s in (1, 2, 3, 5, 6, 7, 9, 11):
         assert o.krange(M, s) is None
+
+
+def test_replay_property_on_oracle_output():
+    """parity.replay_alignments (the size-independent check used at config 5's shard shape) accepts
+    what the oracle produces for global alignments and rejects a corrupted op list."""
+    import numpy as np
+    import pytest
+    import parity
+    from wfa_b200 import datagen
+    batch = datagen.generate(64, 700, 0.12, config=3)
+    for ad in ((10, 50), None):
+        r, o, off, _ = parity.oracle_batch(batch, adaptive=ad)
+        parity.replay_alignments(batch, r, o, off)
+    bad = o.copy()
+    first_m = int(np.nonzero((bad >> np.uint64(32)) == ord("M"))[0][0])
+    bad[first_m] = (np.uint64(ord("X")) << np.uint64(32)) | (bad[first_m] & np.uint64(0xffffffff))
+    with pytest.raises(AssertionError):
+        parity.replay_alignments(batch, r, bad, off)

@@ -474,6 +474,7 @@ struct FwdOut {
     int      n, m;
     uint64_t top;             /* first used cell word of the slot (rows occupy [top, slot_words)) */
     unsigned long long c_cells, c_written, c_steps;
+    bool     first_eq;        /* REG worker: q[0] == t[0] (which init cell exists, wfa.go:155-158) */
 };
 
 template <int BITS, bool CTA, bool SSEQ = false>
