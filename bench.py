@@ -283,7 +283,7 @@ def main():
         achieved = B / k_sec / 1e9
         int_ops = 32 * stats["cells"] + 10 * stats["cells"] + 8 * stats["cells"]      # O = 32C + 10V + 8W with V,W ~ C
         kname = max((stats["pairs_lane"], "lane_kernel"), (stats["pairs_warp"], "align_kernel<warp>"), (stats["pairs_cta"], "align_kernel<cta>"),
-                    (stats.get("pairs_reg", 0), "reg_kernel"))[1]
+                    (stats.get("pairs_slim", 0), "slim_kernel"))[1]
         traffic, traffic_src, ncu_instr = ncu_traffic(kname, workload, n_pairs)
         line = {
             "metric": "alignments_per_sec", "value": pairs_all / sec_step, "unit": "alignments/s",
@@ -326,7 +326,7 @@ def main():
                                "note": "executed warp instructions and issue-slot utilisation per kernel: profiles/r1_ncu_summary.md"},
             "device_ms_per_step": ms_dev / args.steps,
             "work": {"cells": int(stats["cells"]), "cells_written": int(stats["cells_written"]), "score_steps": int(stats["score_steps"]),
-                     "ops": int(stats["ops"]), "retries": int(stats["retries"]), "pairs_lane": int(stats["pairs_lane"]), "pairs_reg": int(stats.get("pairs_reg", 0)), "pairs_warp": int(stats["pairs_warp"]),
+                     "ops": int(stats["ops"]), "retries": int(stats["retries"]), "pairs_lane": int(stats["pairs_lane"]), "pairs_slim": int(stats.get("pairs_slim", 0)), "pairs_warp": int(stats["pairs_warp"]),
                      "pairs_cta": int(stats["pairs_cta"])},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -72,8 +72,8 @@ typedef struct wfacuda_config {
 #define WFACUDA_FLAG_FORCE_8BIT         4u
 /* Keep short pairs off the LANE kernel (32 pairs per warp in lockstep); testing / comparison. */
 #define WFACUDA_FLAG_NO_LANE            8u
-/* Keep pairs off the REG kernel (one warp per pair, wavefront rows in registers); testing / comparison. */
-#define WFACUDA_FLAG_NO_REG             16u
+/* Keep pairs off the SLIM kernel (one warp per pair, offsets-only cells); testing / comparison. */
+#define WFACUDA_FLAG_NO_SLIM            16u
 
 /* AlignmentResult (wfa_cigar.go:29-46) after process() (wfa_cigar.go:136-214).
  * tend/qend are 0 when the alignment has no match run (the reference leaves
@@ -104,7 +104,7 @@ typedef struct wfacuda_stats {
     uint32_t pairs_warp, pairs_cta, pairs_8bit;
     float    ms_pack, ms_align, ms_total_device;   /* CUDA-event times on the ctx stream */
     uint32_t pairs_lane;         /* pairs aligned by the LANE kernel (not counted in pairs_warp) */
-    uint32_t pairs_reg;          /* pairs aligned by the REG kernel (not counted in pairs_warp) */
+    uint32_t pairs_slim;         /* pairs aligned by the SLIM kernel (not counted in pairs_warp) */
 } wfacuda_stats;
 
 typedef struct wfacuda_ctx   wfacuda_ctx;

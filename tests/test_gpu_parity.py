@@ -177,27 +177,27 @@ def test_synthetic_configs(built_lib, name, count):
     if c["global_alignment"]:
         assert stats["cells"] == ref[3]["cells"], (stats, ref[3])
     if c["adaptive"]:
-        assert stats["pairs_reg"] > 0.9 * count, stats           # configs 3 and 5 run on the REG worker
+        assert stats["pairs_slim"] > 0.9 * count, stats           # configs 3 and 5 run on the SLIM worker
 
 
 def test_config5_shard_shape(built_lib):
     """Config 5 as one GPU of eight sees it: 1 250 pairs of 100 kbp.  The oracle needs minutes for
-    that many, so: (1) the REG worker (registers, 8-byte offset cells, codes re-derived by the
-    backtrace) against the WARP worker (raw words with codes in a shared-memory ring) on all 1 250
+    that many, so: (1) the SLIM worker (8-byte offset cells, codes re-derived by the
+    backtrace, sequences through a moving shared-memory window) against the WARP worker (raw words with codes in a shared-memory ring) on all 1 250
     -- two independent forward passes and arena formats; (2) the oracle on a 40-pair sample of the
     same batch; (3) every alignment replayed on its sequences."""
     name = "cfg5_100kbp_e15_global_adaptive"
     batch = datagen.generate_config(name, 1250)
     res = {}
-    for flags in (0, api.FLAG_NO_REG):
+    for flags in (0, api.FLAG_NO_SLIM):
         a = parity.make_aligner(adaptive=(10, 50), flags=flags)
         try:
             res[flags] = a.align_arrays(batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len, copy=True)
             st = a.stats()
-            assert (st["pairs_reg"] > 1000) == (flags == 0), st
+            assert (st["pairs_slim"] > 1000) == (flags == 0), st
         finally:
             a.close()
-    parity.assert_same(batch, res[0], res[api.FLAG_NO_REG], "config 5 shard: REG vs WARP worker")
+    parity.assert_same(batch, res[0], res[api.FLAG_NO_SLIM], "config 5 shard: REG vs WARP worker")
     idx = np.r_[0:16, 600:612, 1238:1250]
     sub = datagen.Batch(batch.seq_bytes, batch.q_off[idx], batch.q_len[idx], batch.t_off[idx], batch.t_len[idx])
     ref = parity.oracle_batch(sub, threads=os.cpu_count() or 8, adaptive=(10, 50))
@@ -206,14 +206,14 @@ def test_config5_shard_shape(built_lib):
     parity.replay_alignments(batch, r, o, off, penalties=(4, 6, 2))
 
 
-def test_reg_worker_boundaries(built_lib):
-    """REG worker (wfa_reg.cuh): rows that outgrow 32 S diagonals (more cells per lane, then the WARP
-    worker), targets around the 2 046-base limit of the 32-bit cell word, non-ACGT pairs (8-bit
+def test_slim_worker_boundaries(built_lib):
+    """SLIM worker (wfa_slim.cuh): rows that outgrow the ring (the wider instantiation, then the WARP
+    worker), targets around the 1 022-base limit of the 32-bit cell word and the 2 048-base window, non-ACGT pairs (8-bit
     hand-over), pairs that end at score 0, sequences longer than the shared-memory window."""
     rng = random.Random(41)
     rnd = lambda n, al=b"ACGT": bytes(rng.choice(al) for _ in range(n))
     pairs = []
-    for L in (255, 300, 700, 1000, 2040, 2046, 2047, 2048, 2100, 3000, 5000):
+    for L in (255, 300, 700, 1000, 1020, 1022, 1023, 1024, 1030, 2040, 2047, 2048, 2049, 2100, 3000, 5000, 9000):
         q = rnd(L)
         pairs += [(q, q), (q, _mutate(rng, q, 0.02, b"ACGT")), (q, _mutate(rng, q, 0.12, b"ACGT")), (q[:L - 5], q), (q, q[7:])]
     for _ in range(60):
@@ -229,19 +229,19 @@ def test_reg_worker_boundaries(built_lib):
     batch = datagen.Batch.from_pairs(pairs)
     for ad in ((10, 50), (3, 5), (1, 2), (10, 200), None):
         for pen in ((4, 6, 2), (2, 3, 1), (8, 12, 4)):
-            gpu, ref, stats = parity.check(batch, what="reg boundaries ad=%s pen=%s" % (ad, pen), adaptive=ad, mismatch=pen[0], gap_open=pen[1], gap_ext=pen[2])
+            gpu, ref, stats = parity.check(batch, what="slim boundaries ad=%s pen=%s" % (ad, pen), adaptive=ad, mismatch=pen[0], gap_open=pen[1], gap_ext=pen[2])
             assert stats["cells"] == ref[3]["cells"], (ad, pen, stats, ref[3])
             if ad in ((10, 50), (3, 5), (1, 2)):
-                assert stats["pairs_reg"] > 0 and stats["pairs_8bit"] > 0, stats
+                assert stats["pairs_slim"] > 0 and stats["pairs_8bit"] > 0, stats
     # every rung of the ladder forced: what does not fit goes straight to the WARP worker
     try:
-        for s_ in ("2", "3", "4", "5", "6"):
-            os.environ["WFACUDA_REG_S"] = s_
-            gpu, ref, stats = parity.check(batch, what="reg boundaries S=%s" % s_, adaptive=(10, 50))
-            assert stats["pairs_reg"] > 0 and stats["cells"] == ref[3]["cells"], (s_, stats)
+        for p_ in ("4", "8"):
+            os.environ["WFACUDA_SLIM_P"] = p_
+            gpu, ref, stats = parity.check(batch, what="slim boundaries passes=%s" % p_, adaptive=(10, 50))
+            assert stats["pairs_slim"] > 0 and stats["cells"] == ref[3]["cells"], (p_, stats)
     finally:
-        os.environ.pop("WFACUDA_REG_S", None)
-    parity.check(batch, what="reg boundaries, REG off", adaptive=(10, 50), gpu_kw=dict(flags=api.FLAG_NO_REG))
+        os.environ.pop("WFACUDA_SLIM_P", None)
+    parity.check(batch, what="slim boundaries, SLIM off", adaptive=(10, 50), gpu_kw=dict(flags=api.FLAG_NO_SLIM))
 
 
 def test_seqs_txt_config1(built_lib):

@@ -15,7 +15,7 @@
 #include "../../include/wfacuda.h"
 #include "wfa_kernels.cuh"
 #include "wfa_lane.cuh"
-#include "wfa_reg.cuh"
+#include "wfa_slim.cuh"
 #include "wfa_render.cuh"
 
 #include <algorithm>
@@ -105,27 +105,28 @@ __global__ void __launch_bounds__(256) int32_peak_kernel(uint32_t *out, int iter
 }
 } // namespace
 
-/* REG worker (wfa_reg.cuh): one instantiation per (cells per lane, cell width, wf-adaptive) */
+/* SLIM worker (wfa_slim.cuh): one instantiation per (passes per row, size class, wf-adaptive) */
 namespace {
-constexpr int kRegLadder[] = {2, 3, 4, 5, 6};
-constexpr int kRegLadderN = 5;
-typedef void (*RegKernel)(const KParams);
-template <bool WIDE, bool ADAPT> RegKernel reg_kernel_sel(int S)
+constexpr int kSlimLadder[] = {4, 8};           /* MAXP: rows of up to 128 / 256 diagonals */
+constexpr int kSlimLadderN = 2;
+typedef void (*SlimKernel)(const KParams);
+template <int SZ, bool ADAPT> SlimKernel slim_kernel_sel(int maxp)
 {
-    switch (S) {
-    case 2: return reg_kernel<2, WIDE, ADAPT>;
-    case 3: return reg_kernel<3, WIDE, ADAPT>;
-    case 4: return reg_kernel<4, WIDE, ADAPT>;
-    case 5: return reg_kernel<5, WIDE, ADAPT>;
-    case 6: return reg_kernel<6, WIDE, ADAPT>;
+    switch (maxp) {
+    case 4: return slim_kernel<4, SZ, ADAPT>;
+    case 8: return slim_kernel<8, SZ, ADAPT>;
     }
     return nullptr;
 }
-RegKernel reg_kernel_ptr(int S, bool wide, bool adapt)
+SlimKernel slim_kernel_ptr(int maxp, int sz, bool adapt)
 {
-    return wide ? (adapt ? reg_kernel_sel<true, true>(S) : reg_kernel_sel<true, false>(S))
-                : (adapt ? reg_kernel_sel<false, true>(S) : reg_kernel_sel<false, false>(S));
+    switch (sz) {
+    case 0: return adapt ? slim_kernel_sel<0, true>(maxp) : slim_kernel_sel<0, false>(maxp);
+    case 1: return adapt ? slim_kernel_sel<1, true>(maxp) : slim_kernel_sel<1, false>(maxp);
+    default: return adapt ? slim_kernel_sel<2, true>(maxp) : slim_kernel_sel<2, false>(maxp);
+    }
 }
+int slim_size_class(uint32_t max_len) { return max_len <= SLIM_MAX_M10 ? 0 : max_len <= SLIM_MAX_SHORT ? 1 : 2; }
 } // namespace
 
 struct wfacuda_ctx {
@@ -146,9 +147,9 @@ struct wfacuda_ctx {
     void *pinned[2] = {nullptr, nullptr}; size_t pinned_cap = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
-    double arena_scale_reg = 1.0;  /* the same for the REG worker's slots */
-    int reg_s_learned = 0;         /* learned: cells per lane (row capacity / 32) the REG worker needed */
-    int reg_occ[2][2][8] = {};     /* [wide][adaptive][S]: resident blocks per SM, 0 = unknown */
+    double arena_scale_slim = 1.0;  /* the same for the REG worker's slots */
+    int slim_p_learned = 0;         /* learned: cells per lane (row capacity / 32) the REG worker needed */
+    int slim_occ[3][2][9] = {};    /* [size class][adaptive][MAXP]: resident blocks per SM, 0 = unknown */
     /* LANE class: sampled histogram of the score index at which the previous batch's pairs
      * finished, and the stage boundaries taken from it */
     uint64_t lane_hist[64] = {}; uint64_t lane_hist_n = 0;
@@ -439,8 +440,8 @@ Need estimate(const wfacuda_ctx *ctx, uint32_t n, uint32_t m)
     return nd;
 }
 
-/* The same for a REG slot: one 4- or 8-byte word per cell, 16-byte row headers */
-Need estimate_reg(const wfacuda_ctx *ctx, uint32_t n, uint32_t m, bool wide)
+/* The same for a SLIM slot: one 4- or 8-byte word per cell, 16-byte row headers */
+Need estimate_slim(const wfacuda_ctx *ctx, uint32_t n, uint32_t m, bool wide)
 {
     const wfacuda_config &c = ctx->cfg;
     const double L = std::min(n, m), diag = (double)n + m - 1;
@@ -451,8 +452,8 @@ Need estimate_reg(const wfacuda_ctx *ctx, uint32_t n, uint32_t m, bool wide)
     double width_final = std::min(diag, 2.0 * score / c.gap_ext + 3);
     if (c.adaptive) width_final = std::min(width_final, 1.5 * c.max_dist_diff + c.min_wf_len + 16.0);
     const double avg_width = c.adaptive ? width_final : 0.55 * width_final + 3;
-    double bytes = rows * (avg_width * (wide ? 8.0 : 4.0) + sizeof(RegHdr)) + 4096;
-    bytes *= 1.3 * ctx->arena_scale_reg;
+    double bytes = rows * (avg_width * (wide ? 8.0 : 4.0) + sizeof(SlimHdr)) + 4096;
+    bytes *= 1.3 * ctx->arena_scale_slim;
     Need nd; nd.arena = (uint64_t)bytes; nd.width = (int)std::min(diag, width_final);
     return nd;
 }
@@ -476,30 +477,30 @@ uint64_t arena_budget(wfacuda_ctx *ctx, bool refresh = true)
 
 /* choose worker count / slot size for one class launch */
 int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint32_t> &order, bool cta, int bits,
-                double boost, int min_ring_cap, LaunchPlan *lp, int reg_s = 0, bool reg_wide = false)
+                double boost, int min_ring_cap, LaunchPlan *lp, int slim_p = 0, int slim_sz = 0)
 {
     uint64_t need_max = 0; int width_max = 1; uint32_t seq_words_max = 0;
     /* the list is sorted longest first; a prefix sample bounds the estimate cheaply */
     const size_t sample = std::min<size_t>(order.size(), 4096);
     for (size_t i = 0; i < sample; i++) {
         const uint32_t dn = b->n_of(order[i]), dm = b->m_of(order[i]);
-        const Need nd = reg_s ? estimate_reg(ctx, dn, dm, reg_wide) : estimate(ctx, dn, dm);
+        const Need nd = slim_p ? estimate_slim(ctx, dn, dm, slim_sz != 0) : estimate(ctx, dn, dm);
         need_max = std::max(need_max, nd.arena); width_max = std::max(width_max, nd.width);
         seq_words_max = std::max(seq_words_max, ((dn + 15) >> 4) + ((dm + 15) >> 4) + 2);
     }
     /* WARP worker, 2-bit: pairs of up to ~2 kbp keep their packed sequences in shared memory
      * (the kernel checks every pair against this capacity and reads longer ones from global) */
-    lp->seq_cap = (!cta && !reg_s && bits == 2 && seq_words_max <= 264 && !getenv("WFACUDA_NO_SEQ_SMEM")) ? (int)((seq_words_max + 3) & ~3u) : 0;
+    lp->seq_cap = (!cta && !slim_p && bits == 2 && seq_words_max <= 264 && !getenv("WFACUDA_NO_SEQ_SMEM")) ? (int)((seq_words_max + 3) & ~3u) : 0;
     need_max = (uint64_t)((double)need_max * boost);
     lp->cta = cta; lp->slot_at_max = false;
     /* the device is only asked for its free memory when the arena may have to grow */
     uint64_t slot = (std::max<uint64_t>(need_max, 16384) + 255) & ~255ull;
     const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
     int wpb, blocks_per_sm = 1;
-    if (reg_s) {
-        wpb = 4; lp->threads = 128; lp->ring_cap = 0; lp->smem = reg_smem_bytes() * 4;
-        int &oc = ctx->reg_occ[reg_wide][ctx->cfg.adaptive ? 1 : 0][reg_s];
-        if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, reg_kernel_ptr(reg_s, reg_wide, ctx->cfg.adaptive != 0), lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
+    if (slim_p) {
+        wpb = 4; lp->threads = 128; lp->ring_cap = 32 * slim_p; lp->smem = slim_smem_bytes(slim_p) * 4;
+        int &oc = ctx->slim_occ[slim_sz][ctx->cfg.adaptive ? 1 : 0][slim_p];
+        if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, slim_kernel_ptr(slim_p, slim_sz, ctx->cfg.adaptive != 0), lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
         blocks_per_sm = std::max(1, oc);
     } else if (cta) {
         wpb = 1; lp->threads = WFA_CTA_THREADS; lp->ring_cap = 0;
@@ -548,24 +549,24 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
  * ring width (WARP kernel -> wider ring or the CTA kernel through *to_cta),
  * arena (4x slot) or ops pool (pool doubled). */
 int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &order0, bool identity, bool cta, int bits, KParams base,
-              std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit, bool reg = false)
+              std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit, bool slim = false)
 {
-    /* REG worker: `to_cta` takes the pairs whose rows outgrow its widest instantiation (the WARP
-     * worker places them); cells per lane start from what earlier batches needed */
-    const bool reg_wide = reg && b->max_len > REG_MAX_M32;
-    int reg_li = 0;
-    if (reg) {
-        int s0 = ctx->reg_s_learned;
-        if (!s0) {
-            /* wf-adaptive: rows hover around 2 x MaxDistDiff diagonals at most; without heuristic
+    /* SLIM worker: `to_cta` takes the pairs whose rows outgrow its widest instantiation (the WARP
+     * worker places them); passes per row start from what earlier batches needed */
+    const int slim_sz = slim_size_class(b->max_len);
+    int slim_li = 0;
+    if (slim) {
+        int p0 = ctx->slim_p_learned;
+        if (!p0) {
+            /* wf-adaptive: rows hover around MaxDistDiff + a few dozen diagonals; without heuristic
              * they grow by two per score, so the score guess decides */
-            if (ctx->cfg.adaptive) s0 = (int)std::min<uint64_t>(6, (2ull * ctx->cfg.max_dist_diff + 63) / 32);
-            else s0 = std::min(6, (estimate_reg(ctx, b->max_len, b->max_len, reg_wide).width + 31) / 32);
+            if (ctx->cfg.adaptive) p0 = (int)std::min<uint64_t>(8, ((uint64_t)ctx->cfg.max_dist_diff + 60 + 31) / 32);
+            else p0 = std::min(8, (estimate_slim(ctx, b->max_len, b->max_len, slim_sz != 0).width + 31) / 32);
         }
-        if (const char *e = getenv("WFACUDA_REG_S")) s0 = atoi(e);
-        while (reg_li + 1 < kRegLadderN && kRegLadder[reg_li] < s0) reg_li++;
+        if (const char *e = getenv("WFACUDA_SLIM_P")) p0 = atoi(e);
+        while (slim_li + 1 < kSlimLadderN && kSlimLadder[slim_li] < p0) slim_li++;
     }
-    double &scale = reg ? ctx->arena_scale_reg : ctx->arena_scale;
+    double &scale = slim ? ctx->arena_scale_slim : ctx->arena_scale;
     double boost = 1.0; int min_cap = 0;
     std::vector<uint32_t> requeued;
     for (int attempt = 0; ; attempt++) {
@@ -574,8 +575,8 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         const bool ident = identity && attempt == 0;      /* pair index == queue position: no work list */
         if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
         LaunchPlan lp;
-        const int reg_s = reg ? kRegLadder[reg_li] : 0;
-        int rc = plan_launch(ctx, b, order, cta, bits, boost, min_cap, &lp, reg_s, reg_wide);
+        const int slim_p = slim ? kSlimLadder[slim_li] : 0;
+        int rc = plan_launch(ctx, b, order, cta, bits, boost, min_cap, &lp, slim_p, slim_sz);
         if (rc) return rc;
         if ((rc = ensure(ctx, ctx->arena, lp.slot_bytes * lp.group * lp.workers))) return rc;
         if (!ident && (rc = ensure(ctx, ctx->work, order.size() * 4))) return rc;
@@ -591,7 +592,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         P.ring_cap = lp.ring_cap; P.seq_cap = lp.seq_cap; P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
         if (ctx->dump_mode) { P.single_worker = 1; P.semi_literal = 1; ctx->dump_cta = cta; ctx->dump_slot_bytes = lp.slot_bytes * lp.group; }
         const double tk0 = now_ms();
-        if (reg) reg_kernel_ptr(reg_s, reg_wide, ctx->cfg.adaptive != 0)<<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
+        if (slim) slim_kernel_ptr(slim_p, slim_sz, ctx->cfg.adaptive != 0)<<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
         else if (cta) { if (bits == 2) align_kernel<2, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
                    else           align_kernel<8, true><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
         else     { if (bits == 2) align_kernel<2, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
@@ -602,7 +603,7 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         Counters hc;
         { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   %s kernel: host launch at %.2f, sync returned %.2f ms since call\n", cta ? "cta" : "warp", tk0 - g_dbg_t0, now_ms() - g_dbg_t0);
-        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch %s bits=%d attempt %d: %zu pairs, %d blocks x %d thr, ring_cap %d, reg_s %d, group %d, smem %zu, slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", reg ? "reg" : cta ? "cta" : "warp", bits, attempt, order.size(), lp.blocks, lp.threads, lp.ring_cap, reg_s, lp.group, lp.smem, lp.slot_bytes / 1024.0, scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
+        if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch %s bits=%d attempt %d: %zu pairs, %d blocks x %d thr, ring_cap %d, slim passes %d, group %d, smem %zu, slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", slim ? "slim" : cta ? "cta" : "warp", bits, attempt, order.size(), lp.blocks, lp.threads, lp.ring_cap, slim_p, lp.group, lp.smem, lp.slot_bytes / 1024.0, scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
         if (hc.retry_n == 0) {
             /* learn: aim the next batch's slots at 1.5x the largest slot use seen */
             if (boost == 1.0 && !lp.slot_at_max && lp.slot_bytes > 16384 && hc.arena_used_max) {
@@ -633,12 +634,12 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
             ctx->ops_pool = nb;
         }
         bool wide_requeued = false;
-        if (!wide.empty() && reg) {
-            /* a row outgrew 32 S diagonals: more cells per lane (remembered when it was more than a
-             * few pairs), and past the widest instantiation the WARP worker */
-            if (reg_li + 1 < kRegLadderN && !getenv("WFACUDA_REG_S")) {
-                reg_li++; wide_requeued = true;
-                if (wide.size() * 50 > order.size()) ctx->reg_s_learned = std::max(ctx->reg_s_learned, kRegLadder[reg_li]);
+        if (!wide.empty() && slim) {
+            /* a row outgrew the ring: the wider instantiation (remembered when it was more than a
+             * few pairs), and past the widest one the WARP worker */
+            if (slim_li + 1 < kSlimLadderN && !getenv("WFACUDA_SLIM_P")) {
+                slim_li++; wide_requeued = true;
+                if (wide.size() * 50 > order.size()) ctx->slim_p_learned = std::max(ctx->slim_p_learned, kSlimLadder[slim_li]);
                 again.insert(again.end(), wide.begin(), wide.end());
             } else if (to_cta) to_cta->insert(to_cta->end(), wide.begin(), wide.end());
         } else if (!wide.empty()) {
@@ -684,15 +685,13 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
 
 constexpr int kLaneW = 64;                       /* ring columns: diagonals -32..31 */
 
-bool reg_class_enabled(const wfacuda_ctx *ctx)
+bool slim_class_enabled(const wfacuda_ctx *ctx)
 {
     const wfacuda_config &c = ctx->cfg;
     if (!c.global_alignment || ctx->dump_mode) return false;
-    if (c.flags & (WFACUDA_FLAG_FORCE_CTA | WFACUDA_FLAG_FORCE_8BIT | WFACUDA_FLAG_NO_REG)) return false;
-    if (getenv("WFACUDA_NO_REG")) return false;
-    /* without heuristic the wavefront grows by two diagonals per score: rows stay within the
-     * registers only for low scores -- left to the estimate in plan_launch / the ST_RING hand-over */
-    return ctx->xg == REG_XG && ctx->oeg == REG_OEG && ctx->eg == REG_EG;
+    if (c.flags & (WFACUDA_FLAG_FORCE_CTA | WFACUDA_FLAG_FORCE_8BIT | WFACUDA_FLAG_NO_SLIM)) return false;
+    if (getenv("WFACUDA_NO_SLIM")) return false;
+    return ctx->xg == SLIM_XG && ctx->oeg == SLIM_OEG && ctx->eg == SLIM_EG;
 }
 
 bool lane_class_enabled(const wfacuda_ctx *ctx)
@@ -1044,8 +1043,8 @@ wfacuda_ctx *wfacuda_create(int device, const wfacuda_config *cfg)
         cudaFuncSetAttribute(lane_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(pack_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaFuncSetAttribute(pack_short_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, mx);
-        for (int li = 0; li < kRegLadderN; li++) for (int w = 0; w < 2; w++) for (int a = 0; a < 2; a++)
-            cudaFuncSetAttribute(reg_kernel_ptr(kRegLadder[li], w != 0, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, mx);
+        for (int li = 0; li < kSlimLadderN; li++) for (int z = 0; z < 3; z++) for (int a = 0; a < 2; a++)
+            cudaFuncSetAttribute(slim_kernel_ptr(kSlimLadder[li], z, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, mx);
         cudaGetLastError();
     }
     return ctx;
@@ -1103,7 +1102,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->arena_scale_reg = 1.0; ctx->reg_s_learned = 0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = ctx->lane_occ[2] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->arena_scale_slim = 1.0; ctx->slim_p_learned = 0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = ctx->lane_occ[2] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -1377,16 +1376,16 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     std::vector<uint32_t> warp_extra;                       /* only built when the LANE class handed pairs over */
     if (!to_warp.empty()) { warp_extra = b->order_warp; warp_extra.insert(warp_extra.end(), to_warp.begin(), to_warp.end()); }
     const std::vector<uint32_t> &warp_order = to_warp.empty() ? b->order_warp : warp_extra;
-    /* REG worker first (global, narrow wavefronts, penalties of the default shape); what outgrows
-     * its registers goes on to the WARP worker */
-    std::vector<uint32_t> reg_left;
-    bool use_reg = reg_class_enabled(ctx) && b->max_len <= REG_MAX_M64 && !force8 && !warp_order.empty();
-    /* without heuristic a row is as wide as the score allows: not worth a try beyond the registers' reach */
-    if (use_reg && !ctx->cfg.adaptive && !ctx->reg_s_learned && estimate_reg(ctx, b->max_len, b->max_len, false).width > 32 * kRegLadder[kRegLadderN - 1]) use_reg = false;
-    if (use_reg) {
-        if ((rc = run_class(ctx, b, warp_order, b->identity_cls == 0 && to_warp.empty(), false, 2, P, &reg_left, &warp8, true))) return rc;
-        ctx->stats.pairs_reg = (uint32_t)(warp_order.size() - reg_left.size() - warp8.size());
-        if ((rc = run_class(ctx, b, reg_left, false, false, 2, P, &to_cta, &warp8))) return rc;
+    /* SLIM worker first (global, narrow wavefronts, penalties of the default shape); what outgrows
+     * its ring goes on to the WARP worker */
+    std::vector<uint32_t> slim_left;
+    bool use_slim = slim_class_enabled(ctx) && b->max_len <= SLIM_MAX_M21 && !force8 && !warp_order.empty();
+    /* without heuristic a row is as wide as the score allows: not worth a try beyond the ring's reach */
+    if (use_slim && !ctx->cfg.adaptive && !ctx->slim_p_learned && estimate_slim(ctx, b->max_len, b->max_len, false).width > 32 * kSlimLadder[kSlimLadderN - 1]) use_slim = false;
+    if (use_slim) {
+        if ((rc = run_class(ctx, b, warp_order, b->identity_cls == 0 && to_warp.empty(), false, 2, P, &slim_left, &warp8, true))) return rc;
+        ctx->stats.pairs_slim = (uint32_t)(warp_order.size() - slim_left.size() - warp8.size());
+        if ((rc = run_class(ctx, b, slim_left, false, false, 2, P, &to_cta, &warp8))) return rc;
     } else
     if ((rc = run_class(ctx, b, warp_order, b->identity_cls == 0 && to_warp.empty(), false, force8 ? 8 : 2, P, &to_cta, &warp8))) return rc;
     if ((rc = run_class(ctx, b, warp8, false, false, 8, P, &to_cta, nullptr))) return rc;
@@ -1394,7 +1393,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     std::vector<uint32_t> cta_extra;
     if (!to_cta.empty()) { cta_extra = b->order_cta; cta_extra.insert(cta_extra.end(), to_cta.begin(), to_cta.end()); }
     const std::vector<uint32_t> &cta_order = to_cta.empty() ? b->order_cta : cta_extra;
-    ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size() + ctx->lane_handed) - ctx->stats.pairs_reg;
+    ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size() + ctx->lane_handed) - ctx->stats.pairs_slim;
     ctx->stats.pairs_cta = (uint32_t)cta_order.size();
     if ((rc = run_class(ctx, b, cta_order, b->identity_cls == 1 && to_cta.empty(), true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
     if ((rc = run_class(ctx, b, cta8, false, true, 8, P, nullptr, nullptr))) return rc;
@@ -1687,7 +1686,7 @@ static void add_stats(wfacuda_stats &a, const wfacuda_stats &s)
     a.ops += s.ops; a.seq_bases += s.seq_bases; a.arena_bytes = std::max(a.arena_bytes, s.arena_bytes);
     a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes; a.kernel_launches += s.kernel_launches;
     a.align_launches += s.align_launches; a.retries += s.retries; a.pairs_warp += s.pairs_warp;
-    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.pairs_lane += s.pairs_lane; a.pairs_reg += s.pairs_reg; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
+    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.pairs_lane += s.pairs_lane; a.pairs_slim += s.pairs_slim; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
     a.ms_total_device += s.ms_total_device;
 }
 
