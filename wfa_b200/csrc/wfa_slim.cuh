@@ -60,7 +60,13 @@ template <int SZ> struct SlimCell {
     }
 };
 
+/* Shared memory of a warp: M ring (5 rows), I|D ring (2 rows of two planes), the two sequence windows.
+ * A row is stored from its own first diagonal on (column 0 = alo), so a source cell k +- 1 sits at a
+ * fixed distance from the lane's base address whatever the pass; reads that fall outside a source
+ * row's range are discarded and may stray up to one row before and two rows behind it -- into a
+ * neighbouring row, the windows behind the rings, or the pad in front of the block's first warp. */
 __host__ __device__ inline size_t slim_smem_bytes(int maxp) { return 9 * (size_t)maxp * 128 + 2 * (size_t)SLIM_WIN * 8; }   /* per warp */
+__host__ __device__ inline size_t slim_smem_pad(int maxp) { return (size_t)maxp * 128 + 16; }                                /* per block, in front */
 
 /* A sequence seen through the warp's shared-memory window: entry j of the ring holds the 2-bit
  * words j and j+1 of the sequence, for j in [wbase, wend).  A compare that would leave the
@@ -108,18 +114,24 @@ struct SeqWin {
 };
 
 
+/* f(integral_constant<int, 0>) ... f(integral_constant<int, N - 1>): a loop whose index is a constant
+ * expression in the body (offsets of the shared-memory accesses become immediates) */
+template <class F, int... Is>
+__device__ __forceinline__ void static_for(F &&f, std::integer_sequence<int, Is...>) { (f(std::integral_constant<int, Is>{}), ...); }
+
 /* Forward pass of one pair: wfa.go:228-251 with next + extend fused per cell. */
 template <int MAXP, int SZ, bool ADAPT>
 __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t pair, const uint32_t smem_sa, uint8_t *slot, const uint64_t slot_bytes)
 {
-    constexpr int WR = 32 * MAXP;                  /* ring columns (a power of two): diagonal k lives in column k mod WR */
-    constexpr uint32_t ROWB = WR * 4, BM = ROWB - 1;
+    constexpr int WR = 32 * MAXP;                  /* cells per ring row */
+    constexpr uint32_t ROWB = WR * 4;
     constexpr uint32_t FULL = 0xffffffffu;
     constexpr bool LONGSEQ = SZ == 2;
     typedef SlimCell<SZ> SC;
     typedef typename SC::T CellT;
     constexpr uint32_t HDR_CELLS = sizeof(SlimHdr) / sizeof(CellT);
-    const int lane = threadIdx.x & 31;
+    int lane = threadIdx.x & 31;
+    keep(lane);                                                         /* (not to be re-read from the special register in the loop) */
     const PairDesc pd = P.pairs[pair];
     const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
     const int maxdiff = P.max_dist_diff, min_wf_len = P.min_wf_len;
@@ -130,16 +142,20 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
     /* offsets must fit the cell word, sequences of the short classes the window */
     if ((uint32_t)m > (SZ == 0 ? SLIM_MAX_M10 : SLIM_MAX_M21) || (SZ < 2 && (uint32_t)max(n, m) > SLIM_MAX_SHORT)) { f.status = ST_RING; return f; }
 
-    /* shared memory of the warp: M ring (5 rows: s-4 .. s), I ring, D ring (2 rows each), the two sequence windows */
-    const uint32_t rM = smem_sa, rI = rM + 5 * ROWB, rD = rI + 2 * ROWB;
+    /* shared memory of the warp: M ring (5 rows: s-4 .. s), I|D ring (2 rows, I plane then D plane), the two sequence windows */
+    uint32_t rM = smem_sa;
+    keep(rM);
+    const uint32_t rE = rM + 5 * ROWB;
     SeqWin Q, T;
     __syncwarp();
-    Q.init(P.packed + pd.q_word, (uint32_t)n, rD + 2 * ROWB, lane);
-    T.init(P.packed + pd.t_word, (uint32_t)m, rD + 2 * ROWB + (uint32_t)SLIM_WIN * 8u, lane);
+    Q.init(P.packed + pd.q_word, (uint32_t)n, rE + 4 * ROWB, lane);
+    T.init(P.packed + pd.t_word, (uint32_t)m, rE + 4 * ROWB + (uint32_t)SLIM_WIN * 8u, lane);
     __syncwarp();
 
     SlimHdr *hdrs = reinterpret_cast<SlimHdr *>(slot);                  /* grows up, index s/g */
     CellT   *cells = reinterpret_cast<CellT *>(slot);                   /* rows grow down from the end */
+    CellT   *cells_lane = cells + lane;
+    keep_ptr(cells_lane);
     const uint32_t slot_cells = (uint32_t)min(slot_bytes / sizeof(CellT), (uint64_t)0xfffffff0u);
     uint32_t top = slot_cells;
     uint32_t hdr_limit = 3 * HDR_CELLS + 8;                             /* cells covered by headers incl. the next one + slack */
@@ -183,6 +199,10 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
     /* ranges [lo, hi] (after reduce) of the rows s-1 .. s-4; absent: (NONE_LO, NONE_HI) */
     int lo1 = SLIM_NONE_LO, hi1 = SLIM_NONE_HI, lo2 = SLIM_NONE_LO, hi2 = SLIM_NONE_HI;
     int lo3 = SLIM_NONE_LO, hi3 = SLIM_NONE_HI, lo4 = SLIM_NONE_LO, hi4 = SLIM_NONE_HI;
+    /* where their cell of diagonal 0 would be: ring row address - 4 * (first diagonal stored);
+     * an absent row points at a ring row too, whatever is read there is discarded */
+    uint32_t zM1 = rM, zM2 = rM, zM3 = rM, zM4 = rM, zE1 = rE;
+    const uint32_t lane4 = (uint32_t)lane * 4u;
 
     uint32_t c_cells = 0, c_written = 0, c_steps = 0;
     int status = ST_OK, si = 0;
@@ -193,7 +213,7 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
      * source before that row, so the rows before it do not exist and the row itself is this one cell. */
     const bool first_eq = ((Q.chunk(0u) ^ T.chunk(0u)) & 3u) == 0u;
     const int si_first = first_eq ? 0 : SLIM_XG;
-    int cur = si_first % 5;                                             /* M ring row of score index si */
+    uint32_t recM = rM + (uint32_t)(si_first % 5) * ROWB, recE = rE + (uint32_t)(si_first & 1) * 2u * ROWB;    /* ring rows of score index si */
     {
         const SlimHdr none = {0, 1, 0, 0u};
         for (int j = lane; j < si_first; j += 32) hdrs[j] = none;
@@ -202,127 +222,158 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
         if (LONGSEQ && slow) Mx = extend_global(1u, 0);
         top -= 1;
         if (lane == 0) {
-            sts_u32(rM + (uint32_t)cur * ROWB, Mx); sts_u32(rI + (uint32_t)(si_first & 1) * ROWB, 0u); sts_u32(rD + (uint32_t)(si_first & 1) * ROWB, 0u);
+            sts_u32(recM, Mx); sts_u32(recE, 0u); sts_u32(recE + ROWB, 0u);
             cells[top] = SC::pack(Mx, 0u, 0u);
             const SlimHdr h0 = {0, 0, 0, top};
             hdrs[si_first] = h0;
         }
         __syncwarp();
-        si = si_first; lo1 = hi1 = 0;
+        si = si_first; lo1 = hi1 = 0; zM1 = recM; zE1 = recE;
         c_steps = 1; c_cells = 1; c_written = 1;
         hdr_limit += HDR_CELLS * (uint32_t)(si_first + 1);
         if (Ak == 0 && (int)Mx >= m) { finished = true; minS = (uint32_t)si * P.g; }      /* wfa.go:235-239 */
     }
 
-    while (!finished) {
-        si++; cur = cur == 4 ? 0 : cur + 1;
-        /* loop range of next (wfa.go:557-563): hull of the source rows +- 1, clamped */
-        int lo = min(min(lo1, lo2), lo4) - 1, hi = max(max(hi1, hi2), hi4) + 1;
-        lo = max(lo, -(n - 1)); hi = min(hi, m - 1);
-        int elo = SLIM_NONE_LO, ehi = SLIM_NONE_HI;
-        int4 hc = make_int4(0, 1, 0, 0);
-        bool endhit = false;
-        if (lo <= hi) {
-            const int aw = hi - lo + 1;
-            if (aw > WR) { status = ST_RING; break; }
-            if (top < hdr_limit || top - hdr_limit < (uint32_t)aw) { status = ST_ARENA; break; }
-            const uint32_t off = top - (uint32_t)aw;
-            /* ring rows: sources M[s-o-e] and M[s-x], I[s-e], D[s-e]; destination rows */
-            const int slO = cur == 4 ? 0 : cur + 1, slX = cur >= 2 ? cur - 2 : cur + 3;
-            const uint32_t eS = (uint32_t)((si - 1) & 1) * ROWB, eC = (uint32_t)(si & 1) * ROWB;
-            const uint32_t bO = rM + (uint32_t)slO * ROWB, bX = rM + (uint32_t)slX * ROWB, bC = rM + (uint32_t)cur * ROWB;
-            const uint32_t cb0 = ((uint32_t)(lo + lane) * 4u) & BM;                           /* this lane's column in pass 0 */
-            const uint32_t cntO = (uint32_t)max(hi4 - lo4 + 1, 0), cntE = (uint32_t)max(hi1 - lo1 + 1, 0), cntX = (uint32_t)max(hi2 - lo2 + 1, 0);
-            const int k0 = lo + lane;
-            CellT *grow = cells + off + lane;
-            uint32_t Mn[MAXP]; uint32_t slowmask = 0;
-#pragma unroll
-            for (int p = 0; p < MAXP; p++) {
-                Mn[p] = 0u;
-                if (p * 32 < aw) {
-                    const int k = k0 + 32 * p;
-                    const uint32_t cb = (cb0 + 128u * p) & BM, cbL = (cb - 4u) & BM, cbR = (cb + 4u) & BM;
-                    /* five sources; a row is only valid inside its range (Get, wfa_wavefront.go:153-159) */
-                    const int rO = k - lo4, rE = k - lo1, rX = k - lo2;
-                    uint32_t mo_l = lds_u32(bO + cbL), mo_r = lds_u32(bO + cbR), ie_l = lds_u32(rI + eS + cbL), de_r = lds_u32(rD + eS + cbR), mx = lds_u32(bX + cb);
-                    mo_l = (uint32_t)(rO - 1) < cntO ? mo_l : 0u; mo_r = (uint32_t)(rO + 1) < cntO ? mo_r : 0u;
-                    ie_l = (uint32_t)(rE - 1) < cntE ? ie_l : 0u; de_r = (uint32_t)(rE + 1) < cntE ? de_r : 0u;
-                    mx = (uint32_t)rX < cntX ? mx : 0u;
-                    const bool act = k <= hi;
-                    Cell3O c = next_off3(mo_l, ie_l, mo_r, de_r, mx, act ? (uint32_t)m : 0u, act ? (uint32_t)(n + k) : 0u);
-                    bool slow = false;
-                    c.M = extend(c.M, k, slow);
-                    if (LONGSEQ && slow) slowmask |= 1u << p;
-                    Mn[p] = c.M;
-                    sts_u32(bC + cb, c.M); sts_u32(rI + eC + cb, c.I); sts_u32(rD + eC + cb, c.D);
-                    if (act) grow[32 * p] = SC::pack(c.M, c.I, c.D);
+    /* One row of NP passes of 32 diagonals (GUARD: up to NP passes, the row's width decides).  The
+     * body is instantiated per pass count, so that the common narrow rows run straight-line code:
+     * next + extend + stores per pass, with the lane's Lo/Hi, end test and distance-to-end taken
+     * on the way, then the warp reductions. */
+    int lo = 0, hi = 0, aw = 0, elo = 0, ehi = 0, width = 0;
+    uint32_t off = 0;
+    bool endhit = false, row_exists = false;
+    auto row = [&](auto npc, auto guardc) {
+        constexpr int NP = decltype(npc)::value;
+        constexpr bool GUARD = decltype(guardc)::value;
+        /* this lane's addresses in the source rows M[s-o-e], M[s-x], I|D[s-e] and in the destination
+         * rows, for pass 0: pass p is 128 p bytes on, neighbours are +- 4 bytes */
+        const int k0 = lo + lane;
+        const uint32_t kb = (uint32_t)k0 * 4u;
+        const uint32_t aO = zM4 + kb, aX = zM2 + kb, aE = zE1 + kb, aC = recM + lane4, aF = recE + lane4;
+        const uint32_t cntO = (uint32_t)max(hi4 - lo4 + 1, 0), cntE = (uint32_t)max(hi1 - lo1 + 1, 0), cntX = (uint32_t)max(hi2 - lo2 + 1, 0);
+        CellT *grow = cells_lane + off;
+        uint32_t Mn[NP]; uint32_t slowmask = 0;
+        uint32_t du[NP];                                 /* distance to the end of the lane's cells, 0xffffffff = not counted */
+        int pmin = INT_MAX, pmax = INT_MIN; uint32_t dmin = 0xffffffffu;
+        bool hit = false;
+        auto pass = [&](auto pc) {
+            constexpr int p = decltype(pc)::value;
+            Mn[p] = 0u; du[p] = 0xffffffffu;
+            if (!GUARD || p * 32 < aw) {
+                const int k = k0 + 32 * p;
+                /* five sources; a row is only valid inside its range (Get, wfa_wavefront.go:153-159) */
+                const int rO = k - lo4, rI = k - lo1, rX = k - lo2;
+                uint32_t mo_l = lds32<128 * p - 4>(aO), mo_r = lds32<128 * p + 4>(aO);
+                uint32_t ie_l = lds32<128 * p - 4>(aE), de_r = lds32<128 * p + 4 + (int)ROWB>(aE), mx = lds32<128 * p>(aX);
+                mo_l = (uint32_t)(rO - 1) < cntO ? mo_l : 0u; mo_r = (uint32_t)(rO + 1) < cntO ? mo_r : 0u;
+                ie_l = (uint32_t)(rI - 1) < cntE ? ie_l : 0u; de_r = (uint32_t)(rI + 1) < cntE ? de_r : 0u;
+                mx = (uint32_t)rX < cntX ? mx : 0u;
+                /* only the row's last pass reaches beyond hi */
+                const bool act = (GUARD || p == NP - 1) ? k <= hi : true;
+                const uint32_t ubk = (uint32_t)(n + k);
+                Cell3O c = next_off3(mo_l, ie_l, mo_r, de_r, mx, act ? (uint32_t)m : 0u, act ? ubk : 0u);
+                bool slow = false;
+                c.M = extend(c.M, k, slow);
+                if (LONGSEQ && slow) slowmask |= 1u << p;
+                Mn[p] = c.M;
+                sts32<128 * p>(aC, c.M); sts32<128 * p>(aF, c.I); sts32<128 * p + (int)ROWB>(aF, c.D);
+                if (act) grow[32 * p] = SC::pack(c.M, c.I, c.D);
+                if (!LONGSEQ && c.M != 0u) {
+                    /* M WaveFront.Lo/Hi, end test on diagonal m-n (wfa.go:235-239), distance to the end
+                     * for reduce (wfa.go:474-494; a present cell has v >= 1) */
+                    pmin = min(pmin, k); pmax = k;
+                    const int a = (int)ubk - (int)c.M, b = m - (int)c.M;
+                    hit = hit || (k == Ak && b <= 0);
+                    if (ADAPT && min(a, b) > 0) { du[p] = (uint32_t)max(a, b); dmin = min(dmin, du[p]); }
                 }
             }
-            if (LONGSEQ && __any_sync(FULL, slowmask != 0u)) {
+        };
+        static_for(pass, std::make_integer_sequence<int, NP>{});
+        if (LONGSEQ) {
+            if (__any_sync(FULL, slowmask != 0u)) {
                 /* some compare left the window: finish those cells from the packed pool, then move the windows on */
                 uint32_t wq = 0, wt = 0;
-#pragma unroll
-                for (int p = 0; p < MAXP; p++) if (slowmask >> p & 1u) {
-                    const int k = k0 + 32 * p;
-                    const uint32_t cb = (cb0 + 128u * p) & BM;
-                    Mn[p] = extend_global(Mn[p], k);
-                    sts_u32(bC + cb, Mn[p]);
-                    grow[32 * p] = SC::pack(Mn[p], lds_u32(rI + eC + cb), lds_u32(rD + eC + cb));
-                    wq = max(wq, (uint32_t)((int)Mn[p] - k) >> 4); wt = max(wt, Mn[p] >> 4);
-                }
+                auto fix = [&](auto pc) {
+                    constexpr int p = decltype(pc)::value;
+                    if (slowmask >> p & 1u) {
+                        const int k = k0 + 32 * p;
+                        Mn[p] = extend_global(Mn[p], k);
+                        sts32<128 * p>(aC, Mn[p]);
+                        grow[32 * p] = SC::pack(Mn[p], lds32<128 * p>(aF), lds32<128 * p + (int)ROWB>(aF));
+                        wq = max(wq, (uint32_t)((int)Mn[p] - k) >> 4); wt = max(wt, Mn[p] >> 4);
+                    }
+                };
+                static_for(fix, std::make_integer_sequence<int, NP>{});
                 wq = __reduce_max_sync(FULL, wq); wt = __reduce_max_sync(FULL, wt);
                 Q.advance_to(wq, lane); T.advance_to(wt, lane);
             }
-            /* M WaveFront.Lo/Hi = first / last present cell, end test on diagonal m-n (wfa.go:235-239) */
-            int pmin = INT_MAX, pmax = INT_MIN;
 #pragma unroll
-            for (int p = 0; p < MAXP; p++) if (p * 32 < aw && Mn[p] != 0u) {
+            for (int p = 0; p < NP; p++) if (Mn[p] != 0u) {
                 const int k = k0 + 32 * p;
                 pmin = min(pmin, k); pmax = k;
-                if (k == Ak && (int)Mn[p] >= m) endhit = true;
+                const int a = n + k - (int)Mn[p], b = m - (int)Mn[p];
+                hit = hit || (k == Ak && b <= 0);
+                if (ADAPT && min(a, b) > 0) { du[p] = (uint32_t)max(a, b); dmin = min(dmin, du[p]); }
             }
-            const int wlo = __reduce_min_sync(FULL, pmin), whi = __reduce_max_sync(FULL, pmax);
-            endhit = __any_sync(FULL, endhit);
-            __syncwarp();                                               /* the row is in the ring */
-            if (wlo <= whi) {
+        }
+        const int wlo = __reduce_min_sync(FULL, pmin), whi = __reduce_max_sync(FULL, pmax);
+        const uint32_t mind = ADAPT ? __reduce_min_sync(FULL, dmin) : 0u;
+        endhit = __any_sync(FULL, hit);
+        __syncwarp();                                               /* the row is in the ring */
+        row_exists = wlo <= whi;
+        elo = wlo; ehi = whi; width = whi - wlo + 1;                 /* C counts the row before reduce */
+        if (ADAPT && row_exists && !endhit && whi - wlo + 1 >= min_wf_len) {
+            /* reduce (wfa.go:461-540) as reductions over the lanes' cells: a cell is
+             * near iff it counts and d - min <= MaxDistDiff (an uncounted one wraps to a huge value) */
+            bool anyfar = false; int fk = INT_MAX, Lk = INT_MIN;
+#pragma unroll
+            for (int p = 0; p < NP; p++) {
+                const uint32_t t = du[p] - mind;
+                if (t <= (uint32_t)maxdiff) { fk = min(fk, k0 + 32 * p); Lk = k0 + 32 * p; }
+                else if (du[p] != 0xffffffffu) anyfar = true;
+            }
+            if (__any_sync(FULL, anyfar)) {
+                const int fmin = __reduce_min_sync(FULL, fk);
+                ehi = __reduce_max_sync(FULL, Lk);
+                int lf = INT_MIN;
+#pragma unroll
+                for (int p = 0; p < NP; p++) if (du[p] != 0xffffffffu && k0 + 32 * p < fmin) lf = k0 + 32 * p;
+                lf = __reduce_max_sync(FULL, lf);
+                if (lf != INT_MIN) elo = lf + 1;
+            }
+        }
+    };
+
+    while (!finished) {
+        si++;
+        recM = recM == rM + 4 * ROWB ? rM : recM + ROWB; recE = recE == rE ? rE + 2 * ROWB : rE;
+        /* loop range of next (wfa.go:557-563): hull of the source rows +- 1, clamped */
+        lo = max(min(min(lo1, lo2), lo4) - 1, -(n - 1)); hi = min(max(max(hi1, hi2), hi4) + 1, m - 1);
+        int4 hc = make_int4(0, 1, 0, 0);
+        endhit = false; row_exists = false;
+        if (lo <= hi) {
+            aw = hi - lo + 1;
+            if (aw > WR) { status = ST_RING; break; }
+            if (top < hdr_limit || top - hdr_limit < (uint32_t)aw) { status = ST_ARENA; break; }
+            off = top - (uint32_t)aw;
+            const int np = (aw + 31) >> 5;
+            if (MAXP > 4 && np > 4) row(std::integral_constant<int, MAXP>{}, std::true_type{});
+            else if (np == 1) row(std::integral_constant<int, 1>{}, std::false_type{});
+            else if (np == 2) row(std::integral_constant<int, 2>{}, std::false_type{});
+            else if (np == 3) row(std::integral_constant<int, 3>{}, std::false_type{});
+            else row(std::integral_constant<int, 4>{}, std::false_type{});
+            if (row_exists) {
                 top = off;
-                c_steps++; c_cells += (uint32_t)(whi - wlo + 1); c_written += (uint32_t)aw;
-                elo = wlo; ehi = whi;
-                if (ADAPT && !endhit && whi - wlo + 1 >= min_wf_len) {
-                    /* reduce (wfa.go:461-540) as reductions over the lanes' cells */
-                    int d[MAXP], dmin = INT_MAX;
-#pragma unroll
-                    for (int p = 0; p < MAXP; p++) {
-                        d[p] = -1;
-                        if (p * 32 < aw) {
-                            const int k = k0 + 32 * p, h = (int)Mn[p], a = n - (h - k), b = m - h;
-                            if (Mn[p] != 0u && min(a, b) > 0) { d[p] = max(a, b); dmin = min(dmin, d[p]); }   /* v >= 1 for a present cell */
-                        }
-                    }
-                    const int mind = __reduce_min_sync(FULL, dmin);
-                    bool anyfar = false; int fk = INT_MAX, Lk = INT_MIN;
-#pragma unroll
-                    for (int p = 0; p < MAXP; p++) if (p * 32 < aw && d[p] >= 0) {
-                        if (d[p] - mind > maxdiff) anyfar = true;
-                        else { fk = min(fk, k0 + 32 * p); Lk = k0 + 32 * p; }
-                    }
-                    if (__any_sync(FULL, anyfar)) {
-                        const int fmin = __reduce_min_sync(FULL, fk);
-                        ehi = __reduce_max_sync(FULL, Lk);
-                        int lf = INT_MIN;
-#pragma unroll
-                        for (int p = 0; p < MAXP; p++) if (p * 32 < aw && d[p] >= 0 && k0 + 32 * p < fmin) lf = k0 + 32 * p;
-                        lf = __reduce_max_sync(FULL, lf);
-                        if (lf != INT_MIN) elo = lf + 1;
-                    }
-                }
+                c_steps++; c_cells += (uint32_t)width; c_written += (uint32_t)aw;
                 hc = make_int4(lo, elo, ehi, (int)off);
             }
         }
         if (top < hdr_limit) { status = ST_ARENA; break; }
         if (lane == 0) *reinterpret_cast<int4 *>(hdrs + si) = hc;
         hdr_limit += HDR_CELLS;
-        lo4 = lo3; hi4 = hi3; lo3 = lo2; hi3 = hi2; lo2 = lo1; hi2 = hi1; lo1 = elo; hi1 = ehi;
+        lo4 = lo3; hi4 = hi3; lo3 = lo2; hi3 = hi2; lo2 = lo1; hi2 = hi1;
+        lo1 = row_exists ? elo : SLIM_NONE_LO; hi1 = row_exists ? ehi : SLIM_NONE_HI;
+        zM4 = zM3; zM3 = zM2; zM2 = zM1;
+        zM1 = recM - (row_exists ? (uint32_t)lo * 4u : 0u); zE1 = recE - (row_exists ? (uint32_t)lo * 4u : 0u);
         if (endhit) { minS = (uint32_t)si * P.g; finished = true; }
     }
 
@@ -412,7 +463,7 @@ __device__ __noinline__ void finish_group_slim(const KParams &P, const bool have
 }
 
 #ifndef WFA_SLIM_MINB
-#define WFA_SLIM_MINB 4
+#define WFA_SLIM_MINB 6
 #endif
 template <int MAXP, int SZ, bool ADAPT>
 __global__ void __launch_bounds__(128, WFA_SLIM_MINB)
@@ -420,7 +471,7 @@ slim_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wib = (int)(threadIdx.x >> 5), lane = threadIdx.x & 31;
-    const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)wib * (uint32_t)slim_smem_bytes(MAXP);
+    const uint32_t smem_sa = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)slim_smem_pad(MAXP) + (uint32_t)wib * (uint32_t)slim_smem_bytes(MAXP);
     const uint64_t worker = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib;
     uint8_t *slot = P.arena + worker * P.slot_bytes;
     const uint32_t G = (uint32_t)P.group;

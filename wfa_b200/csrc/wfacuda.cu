@@ -498,7 +498,7 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
     const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
     int wpb, blocks_per_sm = 1;
     if (slim_p) {
-        wpb = 4; lp->threads = 128; lp->ring_cap = 32 * slim_p; lp->smem = slim_smem_bytes(slim_p) * 4;
+        wpb = 4; lp->threads = 128; lp->ring_cap = 32 * slim_p; lp->smem = slim_smem_pad(slim_p) + slim_smem_bytes(slim_p) * 4;
         int &oc = ctx->slim_occ[slim_sz][ctx->cfg.adaptive ? 1 : 0][slim_p];
         if (!oc && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&oc, slim_kernel_ptr(slim_p, slim_sz, ctx->cfg.adaptive != 0), lp->threads, lp->smem) != cudaSuccess) { cudaGetLastError(); oc = 1; }
         blocks_per_sm = std::max(1, oc);
