@@ -158,7 +158,9 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
     keep_ptr(cells_lane);
     const uint32_t slot_cells = (uint32_t)min(slot_bytes / sizeof(CellT), (uint64_t)0xfffffff0u);
     uint32_t top = slot_cells;
-    uint32_t hdr_limit = 3 * HDR_CELLS + 8;                             /* cells covered by headers incl. the next one + slack */
+    /* cells still free between the headers (growing up) and the rows (growing down), after the
+     * headers of the first rows, one spare header and some slack */
+    int room = (int)min(slot_cells, 0x7fffffffu) - (int)(3 * HDR_CELLS + 8);
 
     /* extend (wfa.go:394-455) of a present cell, offset h = M on diagonal k, inside the window;
      * `slow` is raised when the compare has to be finished outside the window */
@@ -204,7 +206,7 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
     uint32_t zM1 = rM, zM2 = rM, zM3 = rM, zM4 = rM, zE1 = rE;
     const uint32_t lane4 = (uint32_t)lane * 4u;
 
-    uint32_t c_cells = 0, c_written = 0, c_steps = 0;
+    uint32_t c_cells = 0, c_steps = 0;
     int status = ST_OK, si = 0;
     uint32_t minS = 0;
     bool finished = false;
@@ -229,8 +231,8 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
         }
         __syncwarp();
         si = si_first; lo1 = hi1 = 0; zM1 = recM; zE1 = recE;
-        c_steps = 1; c_cells = 1; c_written = 1;
-        hdr_limit += HDR_CELLS * (uint32_t)(si_first + 1);
+        c_steps = 1; c_cells = 1;
+        room -= (int)(HDR_CELLS * (uint32_t)(si_first + 1)) + 1;
         if (Ak == 0 && (int)Mx >= m) { finished = true; minS = (uint32_t)si * P.g; }      /* wfa.go:235-239 */
     }
 
@@ -277,13 +279,18 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
                 Mn[p] = c.M;
                 sts32<128 * p>(aC, c.M); sts32<128 * p>(aF, c.I); sts32<128 * p + (int)ROWB>(aF, c.D);
                 if (act) grow[32 * p] = SC::pack(c.M, c.I, c.D);
-                if (!LONGSEQ && c.M != 0u) {
-                    /* M WaveFront.Lo/Hi, end test on diagonal m-n (wfa.go:235-239), distance to the end
-                     * for reduce (wfa.go:474-494; a present cell has v >= 1) */
-                    pmin = min(pmin, k); pmax = k;
-                    const int a = (int)ubk - (int)c.M, b = m - (int)c.M;
-                    hit = hit || (k == Ak && b <= 0);
-                    if (ADAPT && min(a, b) > 0) { du[p] = (uint32_t)max(a, b); dmin = min(dmin, du[p]); }
+                if (!LONGSEQ) {
+                    /* M WaveFront.Lo/Hi (first / last present cell), end test on diagonal m-n (wfa.go:235-239) */
+                    const bool present = c.M != 0u;
+                    pmin = present ? min(pmin, k) : pmin; pmax = present ? k : pmax;
+                    hit = hit || (k == Ak && c.M >= (uint32_t)m);
+                    if (ADAPT) {
+                        /* distance to the end for reduce (wfa.go:474-494): counted iff present, v < n, h < m, i.e.
+                         * 1 <= M < min(n + k, m) (a present cell has v >= 1); then max(m - h, n - v) = max(m, n + k) - M */
+                        const bool counted = c.M - 1u < min(ubk, (uint32_t)m) - 1u;
+                        du[p] = counted ? max(ubk, (uint32_t)m) - c.M : 0xffffffffu;
+                        dmin = min(dmin, du[p]);
+                    }
                 }
             }
         };
@@ -350,10 +357,12 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
         lo = max(min(min(lo1, lo2), lo4) - 1, -(n - 1)); hi = min(max(max(hi1, hi2), hi4) + 1, m - 1);
         int4 hc = make_int4(0, 1, 0, 0);
         endhit = false; row_exists = false;
+        room -= (int)HDR_CELLS;
         if (lo <= hi) {
             aw = hi - lo + 1;
             if (aw > WR) { status = ST_RING; break; }
-            if (top < hdr_limit || top - hdr_limit < (uint32_t)aw) { status = ST_ARENA; break; }
+            room -= aw;
+            if (room < 0) { status = ST_ARENA; break; }
             off = top - (uint32_t)aw;
             const int np = (aw + 31) >> 5;
             if (MAXP > 4 && np > 4) row(std::integral_constant<int, MAXP>{}, std::true_type{});
@@ -363,13 +372,12 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
             else row(std::integral_constant<int, 4>{}, std::false_type{});
             if (row_exists) {
                 top = off;
-                c_steps++; c_cells += (uint32_t)width; c_written += (uint32_t)aw;
+                c_steps++; c_cells += (uint32_t)width;
                 hc = make_int4(lo, elo, ehi, (int)off);
-            }
+            } else room += aw;
         }
-        if (top < hdr_limit) { status = ST_ARENA; break; }
+        if (room < 0) { status = ST_ARENA; break; }
         if (lane == 0) *reinterpret_cast<int4 *>(hdrs + si) = hc;
-        hdr_limit += HDR_CELLS;
         lo4 = lo3; hi4 = hi3; lo3 = lo2; hi3 = hi2; lo2 = lo1; hi2 = hi1;
         lo1 = row_exists ? elo : SLIM_NONE_LO; hi1 = row_exists ? ehi : SLIM_NONE_HI;
         zM4 = zM3; zM3 = zM2; zM2 = zM1;
@@ -378,7 +386,7 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
     }
 
     f.status = status; f.minS = minS; f.lastK = Ak; f.si = si; f.top = (uint64_t)top;
-    f.c_cells = c_cells; f.c_written = c_written; f.c_steps = c_steps;
+    f.c_cells = c_cells; f.c_written = slot_cells - top; f.c_steps = c_steps;     /* every row stays in the slot */
     f.first_eq = first_eq;
     return f;
 }
@@ -416,6 +424,8 @@ template <int SZ> struct SlimView {
     {
         const uint32_t o = SC::get(cached_word(si, k), comp);
         if (o == 0) return 0;
+        /* the walk goes on 1, 2 or 4 rows down: have the headers it will need next on their way */
+        if (si >= 12) asm volatile("prefetch.global.L1 [%0];" :: "l"(hdr + si - 12));
         const CellT wl = word(si - SLIM_OEG, k - 1), el = word(si - SLIM_EG, k - 1);
         const CellT wr = word(si - SLIM_OEG, k + 1), er = word(si - SLIM_EG, k + 1);
         const CellT wx = word(si - SLIM_XG, k);
@@ -466,7 +476,7 @@ __device__ __noinline__ void finish_group_slim(const KParams &P, const bool have
 #define WFA_SLIM_MINB 6
 #endif
 template <int MAXP, int SZ, bool ADAPT>
-__global__ void __launch_bounds__(128, WFA_SLIM_MINB)
+__global__ void __launch_bounds__(128, SZ == 2 ? 4 : WFA_SLIM_MINB)        /* long pairs come in small numbers: registers before residency */
 slim_kernel(const KParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
