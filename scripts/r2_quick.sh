@@ -5,9 +5,10 @@ TAG=${1:-q1}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "slim_worker or synthetic or shard_shape" > $OUT/pytest.log 2>&1; echo "exit $?" >> $OUT/pytest.log; tail -5 $OUT/pytest.log
 WFACUDA_DEBUG=1 timeout 600 python bench.py --workload cfg3_1kbp_e10_global_adaptive --pairs 200000 --steps 3 --warmup 3 --no-cpu-baseline > $OUT/bench_cfg3.json 2> $OUT/bench_cfg3.err
 WFACUDA_DEBUG=1 timeout 600 python bench.py --workload cfg5_100kbp_e15_global_adaptive --pairs 1250 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/bench_cfg5.json 2> $OUT/bench_cfg5.err
+if [ "$2" == "full5" ]; then WFACUDA_DEBUG=1 timeout 900 python bench.py --workload cfg5_100kbp_e15_global_adaptive --pairs 10000 --steps 1 --warmup 2 --no-cpu-baseline > $OUT/bench_cfg5full.json 2> $OUT/bench_cfg5full.err; fi
 python - <<PY
 import json
-for c in ("cfg3","cfg5"):
+for c in ("cfg3","cfg5","cfg5full"):
     try:
         d=json.load(open("$OUT/bench_%s.json" % c))
         print(c, "value %.4gM  ms/step %.3f  kernel_ms %.3f  frac %.3f  e2e %.4gM  launches %d  work %s" % (d["value"]/1e6, d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["e2e"]["value"]/1e6, d["gpu_launches"], d["work"]))

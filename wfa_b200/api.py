@@ -111,9 +111,10 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("WFACUDA_LIB", LIB_PATH)          # development aid: another build of the same library
+    if not os.path.exists(path):
         raise WfaError("libwfacuda.so is not built (run `python -m wfa_b200.build`); there is no CPU fallback")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, u64, u32p = C.c_void_p, C.c_uint64, C.c_void_p
     L.wfacuda_device_count.restype = C.c_int
     L.wfacuda_create.restype = vp

@@ -279,7 +279,7 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
                 Mn[p] = c.M;
                 sts32<128 * p>(aC, c.M); sts32<128 * p>(aF, c.I); sts32<128 * p + (int)ROWB>(aF, c.D);
                 if (act) grow[32 * p] = SC::pack(c.M, c.I, c.D);
-                if (!LONGSEQ) {
+                {
                     /* M WaveFront.Lo/Hi (first / last present cell), end test on diagonal m-n (wfa.go:235-239) */
                     const bool present = c.M != 0u;
                     pmin = present ? min(pmin, k) : pmin; pmax = present ? k : pmax;
@@ -295,32 +295,31 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
             }
         };
         static_for(pass, std::make_integer_sequence<int, NP>{});
-        if (LONGSEQ) {
-            if (__any_sync(FULL, slowmask != 0u)) {
-                /* some compare left the window: finish those cells from the packed pool, then move the windows on */
-                uint32_t wq = 0, wt = 0;
-                auto fix = [&](auto pc) {
-                    constexpr int p = decltype(pc)::value;
-                    if (slowmask >> p & 1u) {
-                        const int k = k0 + 32 * p;
-                        Mn[p] = extend_global(Mn[p], k);
-                        sts32<128 * p>(aC, Mn[p]);
-                        grow[32 * p] = SC::pack(Mn[p], lds32<128 * p>(aF), lds32<128 * p + (int)ROWB>(aF));
-                        wq = max(wq, (uint32_t)((int)Mn[p] - k) >> 4); wt = max(wt, Mn[p] >> 4);
-                    }
-                };
-                static_for(fix, std::make_integer_sequence<int, NP>{});
-                wq = __reduce_max_sync(FULL, wq); wt = __reduce_max_sync(FULL, wt);
-                Q.advance_to(wq, lane); T.advance_to(wt, lane);
-            }
+        if (LONGSEQ && __any_sync(FULL, slowmask != 0u)) {
+            /* some compare left the window: finish those cells from the packed pool (and what was taken
+             * from them on the way), then move the windows on */
+            uint32_t wq = 0, wt = 0;
+            auto fix = [&](auto pc) {
+                constexpr int p = decltype(pc)::value;
+                if (slowmask >> p & 1u) {
+                    const int k = k0 + 32 * p;
+                    const uint32_t M = extend_global(Mn[p], k), ubk = (uint32_t)(n + k);
+                    Mn[p] = M;
+                    sts32<128 * p>(aC, M);
+                    grow[32 * p] = SC::pack(M, lds32<128 * p>(aF), lds32<128 * p + (int)ROWB>(aF));
+                    wq = max(wq, (uint32_t)((int)M - k) >> 4); wt = max(wt, M >> 4);
+                    hit = hit || (k == Ak && M >= (uint32_t)m);
+                    if (ADAPT) du[p] = M - 1u < min(ubk, (uint32_t)m) - 1u ? max(ubk, (uint32_t)m) - M : 0xffffffffu;
+                }
+            };
+            static_for(fix, std::make_integer_sequence<int, NP>{});
+            if (ADAPT) {
+                dmin = 0xffffffffu;
 #pragma unroll
-            for (int p = 0; p < NP; p++) if (Mn[p] != 0u) {
-                const int k = k0 + 32 * p;
-                pmin = min(pmin, k); pmax = k;
-                const int a = n + k - (int)Mn[p], b = m - (int)Mn[p];
-                hit = hit || (k == Ak && b <= 0);
-                if (ADAPT && min(a, b) > 0) { du[p] = (uint32_t)max(a, b); dmin = min(dmin, du[p]); }
+                for (int p = 0; p < NP; p++) dmin = min(dmin, du[p]);
             }
+            wq = __reduce_max_sync(FULL, wq); wt = __reduce_max_sync(FULL, wt);
+            Q.advance_to(wq, lane); T.advance_to(wt, lane);
         }
         const int wlo = __reduce_min_sync(FULL, pmin), whi = __reduce_max_sync(FULL, pmax);
         const uint32_t mind = ADAPT ? __reduce_min_sync(FULL, dmin) : 0u;
@@ -473,7 +472,7 @@ __device__ __noinline__ void finish_group_slim(const KParams &P, const bool have
 }
 
 #ifndef WFA_SLIM_MINB
-#define WFA_SLIM_MINB 6
+#define WFA_SLIM_MINB 7
 #endif
 template <int MAXP, int SZ, bool ADAPT>
 __global__ void __launch_bounds__(128, SZ == 2 ? 4 : WFA_SLIM_MINB)        /* long pairs come in small numbers: registers before residency */
