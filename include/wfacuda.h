@@ -193,8 +193,14 @@ int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len,
                              wfacuda_wavefront *rows, uint32_t rows_capacity, uint32_t *n_rows,
                              uint32_t *cells, uint64_t cells_capacity, uint64_t *n_cells);
 
-/* One host thread per device, work-balanced static sharding, no collective
- * (pairs are independent): the C side of AlignBatch over several GPUs. */
+/* The C side of AlignBatch over several GPUs (north-star item 4; reference contract: one
+ * Aligner per goroutine, wfa.go:73-78): length-binned LPT shards (wfacuda_shard_assign), one host
+ * thread and one ctx per device, every device running the chunked upload / kernels / download
+ * pipeline of wfacuda_align_batch on its shard; no collective, pairs are independent.  Results land
+ * at the caller's indices.  The ops buffer is cut into one region per device, in proportion to
+ * the shards' bases: ops_off[i] is an absolute position in `ops`, the regions are not compacted,
+ * and wfacuda_last_ops_total() returns the extent of the buffer in use (or, after
+ * WFACUDA_E_OPS_CAPACITY, the capacity that makes every region large enough). */
 int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs,
                               const uint8_t *seq_bytes,
                               const uint64_t *q_off, const uint32_t *q_len,
@@ -202,8 +208,16 @@ int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pa
                               wfacuda_result *results,
                               uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off);
 
-/* The sharding rule of wfacuda_align_batch_multi on its own (pure host logic, no GPU):
- * cuts[0..n_shards], shard d owns pairs [cuts[d], cuts[d+1]). */
+/* The sharding rule of wfacuda_align_batch_multi on its own (pure host logic, no GPU): pairs are
+ * binned by length (half octaves of n+m), bins are dealt out longest first, and inside a bin
+ * every shard gets one run of consecutive pairs sized to level the shards' estimated loads
+ * (cost ~ (n+m)^2 without heuristic or semi-global, ~ n+m with wf-adaptive).  shard_of[i] = shard
+ * of pair i; shard_cost (may be NULL) = estimated load per shard. */
+int wfacuda_shard_assign(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
+                         int adaptive, int global_alignment, uint32_t *shard_of, double *shard_cost);
+
+/* Contiguous index ranges of equal estimated cost (what wfacuda_shard_assign yields for reads of
+ * one length class): cuts[0..n_shards], shard d owns pairs [cuts[d], cuts[d+1]). */
 int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
                        int adaptive, uint64_t *cuts);
 

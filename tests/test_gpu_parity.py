@@ -258,15 +258,24 @@ def test_seqs_txt_config1(built_lib):
     assert (r.QBegin, r.QEnd, r.TBegin, r.TEnd, r.AlignLen, r.Matches, r.Gaps, r.GapRegions) == (2, 100, 3, 98, 99, 96, 3, 3)
 
 
-def test_align_batch_multi_two_ctx_same_device(built_lib):
-    """wfacuda_align_batch_multi: two ctxs (both on device 0 here) each take a cost-balanced
-    contiguous shard; results and ops must come back in index order, identical to the oracle."""
-    pairs = _random_pairs(21, 500, maxlen=300)
-    batch = datagen.Batch.from_pairs(pairs)
-    a, b = parity.make_aligner(adaptive=(10, 50)), parity.make_aligner(adaptive=(10, 50))
-    try:
-        gpu = a.AlignBatchMulti([b], batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)
-    finally:
-        a.close(); b.close()
-    ref = parity.oracle_batch(batch, adaptive=(10, 50))
-    parity.assert_same(batch, gpu, ref, "multi")
+def test_align_batch_multi(built_lib):
+    """wfacuda_align_batch_multi: length-binned LPT shards, every device running the chunked
+    pipeline on its shard, results and ops back at the caller's indices, identical to the oracle.
+    One ctx per visible device (two ctxs on device 0 when only one GPU is visible): a mixed-length
+    batch (non-contiguous shards, gather / scatter) and a uniform one big enough to be pipelined
+    (contiguous shards, several chunks per device)."""
+    n_dev = min(api.device_count(), 8)
+    devs = list(range(n_dev)) if n_dev >= 2 else [0, 0]
+    mixed = datagen.Batch.from_pairs(_random_pairs(21, 500, maxlen=300) + _random_pairs(22, 40, maxlen=3000))
+    uniform = datagen.generate(150_000, 150, 0.05, config=2)
+    for batch, ad, what in ((mixed, (10, 50), "multi mixed"), (mixed, None, "multi mixed no heuristic"), (uniform, None, "multi uniform")):
+        algns = [parity.make_aligner(adaptive=ad, device=d) for d in devs]
+        try:
+            gpu = algns[0].AlignBatchMulti(algns[1:], batch.seq_bytes, batch.q_off, batch.q_len, batch.t_off, batch.t_len)
+            pairs_per_dev = [a.stats()["pairs"] for a in algns]
+        finally:
+            for a in algns:
+                a.close()
+        assert sum(pairs_per_dev) == len(batch) and min(pairs_per_dev) > 0, pairs_per_dev
+        ref = parity.oracle_batch(batch, threads=os.cpu_count() or 8, adaptive=ad)
+        parity.assert_same(batch, gpu, ref, what + " on devices %s" % (devs,))

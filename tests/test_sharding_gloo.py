@@ -65,3 +65,35 @@ def test_shard_plan(built_lib):
             per = [cost[int(cuts[i]):int(cuts[i + 1])].sum() for i in range(n)]
             assert max(per) <= 1.05 * (cost.sum() / n) + cost.max()
     assert list(api.shard_plan(3, [], [], 0)) == [0, 0, 0, 0]
+
+
+def test_shard_assign_lpt(built_lib):
+    """wfacuda_shard_assign: length-binned LPT.  Equal-length reads -> contiguous, equal ranges; a
+    mixed batch -> estimated loads within a few percent of each other (a contiguous cut of the same
+    batch by pair count is far off), inside a length bin every shard one run of consecutive pairs."""
+    import numpy as np
+    from wfa_b200 import api
+    rng = np.random.default_rng(5)
+    for n_shards in (2, 4, 8):
+        q = np.full(100_000, 150, np.uint32); t = q + rng.integers(0, 8, len(q)).astype(np.uint32)
+        shard_of, cost = api.shard_assign(n_shards, q, t, False)
+        assert (np.diff(shard_of.astype(np.int64)) >= 0).all()                    # contiguous ranges
+        counts = np.bincount(shard_of, minlength=n_shards)
+        assert counts.max() - counts.min() <= 0.01 * len(q), counts
+        # mixed: 90 % short reads first, then long ones (sorted input: the worst case for contiguous cuts by count)
+        q = np.concatenate([rng.integers(100, 300, 90_000), rng.integers(5_000, 20_000, 9_000), rng.integers(50_000, 100_000, 1_000)]).astype(np.uint32)
+        t = (q * rng.uniform(0.95, 1.05, len(q))).astype(np.uint32)
+        for adaptive in (False, True):
+            shard_of, cost = api.shard_assign(n_shards, q, t, adaptive)
+            assert cost.max() / cost.mean() < 1.05, (n_shards, adaptive, cost)
+            # inside a length bin (half octaves of n+m) every shard owns one run of consecutive pairs
+            nm = q.astype(np.int64) + t
+            lg = np.floor(np.log2(nm)).astype(np.int64)
+            bins = 2 * lg + ((nm >> (lg - 1)) & 1)
+            for b_ in np.unique(bins):
+                assert (np.diff(shard_of[bins == b_].astype(np.int64)) >= 0).all(), b_
+            naive = np.array([c.sum() for c in np.array_split((q.astype(np.float64) + t) ** (1 if adaptive else 2), n_shards)])
+            assert naive.max() / naive.mean() > 1.5
+    assert len(api.shard_assign(3, [], [], 0)[0]) == 0
+    shard_of, _ = api.shard_assign(4, [10], [12], 0)
+    assert len(shard_of) == 1 and shard_of[0] < 4

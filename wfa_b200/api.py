@@ -99,7 +99,7 @@ RESULT_DTYPE = np.dtype([("score", "<u4"), ("tbegin", "<i4"), ("tend", "<i4"), (
 EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda_set_config",
            "wfacuda_align_batch", "wfacuda_last_ops_total", "wfacuda_batch_upload", "wfacuda_batch_run",
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
-           "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_get_stats", "wfacuda_last_error",
+           "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_shard_assign", "wfacuda_get_stats", "wfacuda_last_error",
            "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister",
            "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components", "wfacuda_measure_issue_peak", "wfacuda_chunk_plan"]
 
@@ -148,6 +148,8 @@ def load_library():
     L.wfacuda_chunk_plan.argtypes = [u64, u64, C.c_int, vp, C.c_uint32, vp]
     L.wfacuda_shard_plan.restype = C.c_int
     L.wfacuda_shard_plan.argtypes = [C.c_int, u64, u32p, u32p, C.c_int, vp]
+    L.wfacuda_shard_assign.restype = C.c_int
+    L.wfacuda_shard_assign.argtypes = [C.c_int, u64, u32p, u32p, C.c_int, C.c_int, vp, vp]
     L.wfacuda_get_stats.restype = C.c_int
     L.wfacuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.wfacuda_last_error.restype = C.c_char_p
@@ -204,6 +206,18 @@ def shard_plan(n_shards, q_len, t_len, adaptive):
     if rc != 0:
         raise WfaError("wfacuda_shard_plan failed (%d)" % rc)
     return cuts
+
+
+def shard_assign(n_shards, q_len, t_len, adaptive, global_alignment=True):
+    """(shard of every pair, estimated load per shard) of wfacuda_align_batch_multi's length-binned
+    LPT partition (host logic only)."""
+    q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
+    shard_of = np.zeros(len(q_len), np.uint32); cost = np.zeros(n_shards, np.float64)
+    rc = load_library().wfacuda_shard_assign(n_shards, len(q_len), q_len.ctypes.data, t_len.ctypes.data, int(bool(adaptive)),
+                                            int(bool(global_alignment)), shard_of.ctypes.data, cost.ctypes.data)
+    if rc != 0:
+        raise WfaError("wfacuda_shard_assign failed (%d)" % rc)
+    return shard_of, cost
 
 
 def chunk_plan(n_pairs, chunk_pairs, tail_levels=2):

@@ -1839,51 +1839,148 @@ int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, co
     return 0;
 }
 
+/* Estimated work of one pair: the wavefront band grows with the score without
+ * heuristic and in semi-global mode (cost ~ (n+m)^2), and is bounded by wf-adaptive (~ n+m). */
+static inline double pair_cost(uint32_t n, uint32_t m, bool adaptive, bool global_aln)
+{
+    const double nm = (double)n + m;
+    return ((adaptive && global_aln) ? nm * 64.0 : nm * nm) + 4096.0;
+}
+
+/* Length-binned LPT: pairs are binned by n+m (half-octave bins), bins are dealt out from the
+ * longest to the shortest, and inside a bin every shard gets ONE run of consecutive pairs, sized so
+ * that the shards' estimated loads level out (water-filling).  A batch of equal-length reads ends
+ * up as n_shards contiguous index ranges; a mixed batch as at most 64 runs per shard.  shard_of[i]
+ * = shard of pair i; shard_cost (optional) = estimated load per shard.  Pure host logic. */
+int wfacuda_shard_assign(int n_shards, uint64_t n_pairs, const uint32_t *q_len, const uint32_t *t_len,
+                         int adaptive, int global_alignment, uint32_t *shard_of, double *shard_cost)
+{
+    if (n_shards < 1 || (n_pairs && (!q_len || !t_len || !shard_of))) return WFACUDA_E_INVALID;
+    std::vector<double> load(n_shards, 0.0);
+    auto bin_of = [&](uint64_t i) {
+        const uint64_t nm = (uint64_t)q_len[i] + t_len[i];
+        const int lg = 63 - __builtin_clzll(nm | 1);
+        return 2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1);
+    };
+    double bin_cost[130] = {0.0};
+    uint64_t bin_n[130] = {0};
+    for (uint64_t i = 0; i < n_pairs; i++) {
+        const int b = bin_of(i);
+        bin_cost[b] += pair_cost(q_len[i], t_len[i], adaptive != 0, global_alignment != 0); bin_n[b]++;
+    }
+    /* per bin: which shard is being filled and how much of its share is left */
+    struct Fill { int shard; double left; std::vector<double> share; };
+    std::vector<Fill> fill(130);
+    for (int b = 129; b >= 0; b--) {
+        if (!bin_n[b]) continue;
+        double total = bin_cost[b];
+        for (double l : load) total += l;
+        /* water level: shards above it get nothing from this bin */
+        std::vector<int> order(n_shards);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int a, int c) { return load[a] < load[c]; });
+        double level = 0.0; int used = n_shards;
+        for (;;) {
+            double sum = bin_cost[b];
+            for (int j = 0; j < used; j++) sum += load[order[j]];
+            level = sum / used;
+            if (used > 1 && load[order[used - 1]] > level) used--; else break;
+        }
+        Fill &f = fill[b];
+        f.share.assign(n_shards, 0.0);
+        for (int j = 0; j < used; j++) f.share[order[j]] = std::max(0.0, level - load[order[j]]);
+        for (int d = 0; d < n_shards; d++) load[d] += f.share[d];
+        f.shard = 0;
+        while (f.shard < n_shards - 1 && f.share[f.shard] <= 0.0) f.shard++;
+        f.left = f.share[f.shard];
+    }
+    for (uint64_t i = 0; i < n_pairs; i++) {
+        Fill &f = fill[bin_of(i)];
+        const double c = pair_cost(q_len[i], t_len[i], adaptive != 0, global_alignment != 0);
+        while (f.left < 0.5 * c && f.shard < n_shards - 1) {
+            int nx = f.shard + 1;
+            while (nx < n_shards - 1 && f.share[nx] <= 0.0) nx++;
+            if (f.share[nx] <= 0.0 && nx == n_shards - 1) break;        /* nobody left to take it: stays with this shard */
+            f.shard = nx; f.left += f.share[nx];
+        }
+        shard_of[i] = (uint32_t)f.shard; f.left -= c;
+    }
+    if (shard_cost) {
+        for (int d = 0; d < n_shards; d++) shard_cost[d] = 0.0;
+        for (uint64_t i = 0; i < n_pairs; i++) shard_cost[shard_of[i]] += pair_cost(q_len[i], t_len[i], adaptive != 0, global_alignment != 0);
+    }
+    return 0;
+}
+
+/* One batch over several devices (one ctx each): length-binned LPT shards (wfacuda_shard_assign),
+ * one host thread per device, each running the chunked pipeline of wfacuda_align_batch on its
+ * shard; results come back at the caller's indices.  No collective: pairs are independent
+ * (reference contract: one Aligner per goroutine, wfa.go:73-78).  The ops buffer is cut into one
+ * region per device in proportion to the shards' bases; ops_off[] are absolute positions, so the
+ * regions need not be compacted. */
 int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pairs, const uint8_t *seq_bytes,
                               const uint64_t *q_off, const uint32_t *q_len, const uint64_t *t_off, const uint32_t *t_len,
                               wfacuda_result *results, uint64_t *ops, uint64_t ops_capacity, uint64_t *ops_off)
 {
     if (!ctxs || n_ctx < 1) return fail(nullptr, WFACUDA_E_INVALID, "need at least one ctx");
+    for (int d = 0; d < n_ctx; d++) if (!ctxs[d]) return fail(nullptr, WFACUDA_E_INVALID, "ctx %d is NULL", d);
     if (n_ctx == 1) return wfacuda_align_batch(ctxs[0], n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
-    std::vector<uint64_t> cut(n_ctx + 1, n_pairs);
-    wfacuda_shard_plan(n_ctx, n_pairs, q_len, t_len, ctxs[0]->cfg.adaptive, cut.data());
-    std::vector<wfacuda_batch *> bs(n_ctx, nullptr);
-    std::vector<int> rcs(n_ctx, 0);
-    {
-        std::vector<std::thread> th;
-        for (int d = 0; d < n_ctx; d++)
-            th.emplace_back([&, d]() {
-                const uint64_t a = cut[d], cnt = cut[d + 1] - cut[d];
-                bs[d] = wfacuda_batch_upload(ctxs[d], cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a);
-                rcs[d] = bs[d] ? wfacuda_batch_run(ctxs[d], bs[d]) : WFACUDA_E_CUDA;
-            });
-        for (auto &t : th) t.join();
-    }
-    int rc = 0;
-    for (int d = 0; d < n_ctx; d++) if (rcs[d]) { rc = rcs[d]; g_tls_error = ctxs[d]->err; }
+    if (n_pairs && (!seq_bytes || !q_off || !q_len || !t_off || !t_len || !results)) return fail(ctxs[0], WFACUDA_E_INVALID, "NULL input array");
+    const wfacuda_config &cfg = ctxs[0]->cfg;
+    std::vector<uint32_t> shard_of(n_pairs);
+    wfacuda_shard_assign(n_ctx, n_pairs, q_len, t_len, cfg.adaptive, cfg.global_alignment, shard_of.data(), nullptr);
+    std::vector<std::vector<uint32_t>> idx(n_ctx);
+    std::vector<uint64_t> bases(n_ctx, 0);
+    for (uint64_t i = 0; i < n_pairs; i++) { idx[shard_of[i]].push_back((uint32_t)i); bases[shard_of[i]] += (uint64_t)q_len[i] + t_len[i] + 16; }
+    uint64_t bases_total = 0;
+    for (uint64_t v : bases) bases_total += v;
+    /* ops regions: proportional to the shards' bases */
     std::vector<uint64_t> obase(n_ctx + 1, 0);
-    for (int d = 0; d < n_ctx; d++) obase[d + 1] = obase[d] + (bs[d] ? bs[d]->ops_total : 0);
-    for (int d = 0; d < n_ctx; d++) ctxs[d]->last_ops_total = obase[n_ctx];
-    if (rc == 0 && ops && obase[n_ctx] > ops_capacity)
-        rc = fail(ctxs[0], WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed", (unsigned long long)ops_capacity, (unsigned long long)obase[n_ctx]);
-    const bool want_ops = rc == 0 && ops;
     {
-        std::vector<std::thread> th;
-        for (int d = 0; d < n_ctx; d++)
-            th.emplace_back([&, d]() {
-                if (!bs[d]) return;
-                const uint64_t a = cut[d], cnt = cut[d + 1] - cut[d];
-                if (rcs[d] == 0) {
-                    int r = wfacuda_batch_download(ctxs[d], bs[d], results + a, want_ops ? ops + obase[d] : nullptr,
-                                                   want_ops ? ops_capacity - obase[d] : 0, ops_off ? ops_off + a : nullptr);
-                    if (r) rcs[d] = r;
-                    if (ops_off) for (uint64_t i = 0; i < cnt; i++) ops_off[a + i] += obase[d];
-                }
-                wfacuda_batch_free(ctxs[d], bs[d]);
-            });
-        for (auto &t : th) t.join();
+        uint64_t run = 0;
+        for (int d = 0; d < n_ctx; d++) { obase[d] = bases_total ? (uint64_t)((long double)ops_capacity * run / bases_total) : 0; run += bases[d]; }
+        obase[n_ctx] = ops_capacity;
     }
-    for (int d = 0; d < n_ctx; d++) if (rcs[d] && rc == 0) { rc = rcs[d]; g_tls_error = ctxs[d]->err; }
+    std::vector<int> rcs(n_ctx, 0);
+    std::vector<uint64_t> used(n_ctx, 0);
+    std::vector<std::thread> th;
+    auto work = [&](int d) {
+        const std::vector<uint32_t> &ix = idx[d];
+        const uint64_t cnt = ix.size();
+        if (!cnt) { ctxs[d]->stats = wfacuda_stats{}; return; }
+        uint64_t *ops_d = ops ? ops + obase[d] : nullptr;
+        const uint64_t cap_d = ops ? obase[d + 1] - obase[d] : 0;
+        const bool contiguous = (uint64_t)ix.back() - ix.front() + 1 == cnt;
+        if (contiguous) {
+            const uint64_t a = ix.front();
+            rcs[d] = wfacuda_align_batch(ctxs[d], cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a, results + a, ops_d, cap_d, ops_off ? ops_off + a : nullptr);
+            if (rcs[d] == 0 && ops_off) for (uint64_t j = 0; j < cnt; j++) ops_off[a + j] += obase[d];
+        } else {
+            std::vector<uint64_t> qo(cnt), to(cnt), oo(cnt);
+            std::vector<uint32_t> ql(cnt), tl(cnt);
+            std::vector<wfacuda_result> rr(cnt);
+            for (uint64_t j = 0; j < cnt; j++) { const uint32_t i = ix[j]; qo[j] = q_off[i]; to[j] = t_off[i]; ql[j] = q_len[i]; tl[j] = t_len[i]; }
+            rcs[d] = wfacuda_align_batch(ctxs[d], cnt, seq_bytes, qo.data(), ql.data(), to.data(), tl.data(), rr.data(), ops_d, cap_d, oo.data());
+            if (rcs[d] == 0) for (uint64_t j = 0; j < cnt; j++) { const uint32_t i = ix[j]; results[i] = rr[j]; if (ops_off) ops_off[i] = oo[j] + obase[d]; }
+        }
+        used[d] = ctxs[d]->last_ops_total;
+    };
+    for (int d = 0; d + 1 < n_ctx; d++) th.emplace_back(work, d);
+    work(n_ctx - 1);
+    for (auto &t : th) t.join();
+    int rc = 0;
+    for (int d = 0; d < n_ctx; d++) if (rcs[d] && rcs[d] != WFACUDA_E_OPS_CAPACITY && rc == 0) { rc = rcs[d]; g_tls_error = ctxs[d]->err; }
+    /* capacity: what the whole buffer must hold so that every device's region does (its share is
+     * proportional to its bases); on success, the extent of the buffer in use */
+    uint64_t need = 0, extent = 0; bool short_of = false;
+    for (int d = 0; d < n_ctx; d++) {
+        if (rcs[d] == WFACUDA_E_OPS_CAPACITY) short_of = true;
+        if (bases[d]) need = std::max<uint64_t>(need, (uint64_t)((long double)used[d] * bases_total / bases[d]) + (uint64_t)n_ctx + 64);
+        if (used[d]) extent = std::max(extent, obase[d] + used[d]);
+    }
+    for (int d = 0; d < n_ctx; d++) ctxs[d]->last_ops_total = short_of ? need : extent;
+    if (rc == 0 && short_of && ops)
+        rc = fail(ctxs[0], WFACUDA_E_OPS_CAPACITY, "ops buffer holds %llu words, %llu needed (one region per device)", (unsigned long long)ops_capacity, (unsigned long long)need);
     return rc;
 }
 
