@@ -22,9 +22,35 @@ import (
 )
 
 // cudaAligner is the state the GPU-backed Aligner carries next to p/ad/opt
-// (reference wfa.go:79-87); M, I, D stay nil: the wavefronts live in HBM.
+// (reference wfa.go:79-87); M, I, D stay nil until FillComponents: the wavefronts live in HBM.
+// All buffers that cross the C boundary are page-locked C memory from wfacuda_host_alloc, kept and
+// grown across calls (allocating page-locked memory costs more than aligning a batch): the DMA
+// engines read and write them directly, and no Go pointer is retained by C (cgo pointer rule).
 type cudaAligner struct {
 	ctx *C.wfacuda_ctx
+	buf [8]pinned // pool, qOff, qLen, tOff, tLen, results, opsOff, ops
+}
+
+type pinned struct {
+	p   unsafe.Pointer
+	cap int // bytes
+}
+
+// reserve returns page-locked memory of at least n bytes (contents undefined).
+func (b *pinned) reserve(n int) (unsafe.Pointer, error) {
+	if n > b.cap {
+		if b.p != nil {
+			C.wfacuda_host_free(b.p)
+			b.p, b.cap = nil, 0
+		}
+		want := n + n/4 + 4096
+		b.p = C.wfacuda_host_alloc(C.size_t(want))
+		if b.p == nil {
+			return nil, fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(nil)))
+		}
+		b.cap = want
+	}
+	return b.p, nil
 }
 
 func (algn *Aligner) config() C.wfacuda_config {
@@ -63,6 +89,12 @@ func RecycleAligner(algn *Aligner) {
 	if algn != nil && algn.cuda != nil && algn.cuda.ctx != nil {
 		C.wfacuda_destroy(algn.cuda.ctx)
 		algn.cuda.ctx = nil
+		for i := range algn.cuda.buf {
+			if algn.cuda.buf[i].p != nil {
+				C.wfacuda_host_free(algn.cuda.buf[i].p)
+				algn.cuda.buf[i] = pinned{}
+			}
+		}
 	}
 }
 
@@ -88,9 +120,28 @@ func (algn *Aligner) AlignPointers(q, t *[]byte) (*AlignmentResult, error) {
 // AlignBatch aligns many pairs in one call.  results[i] is nil where errs[i] != nil;
 // errs[i] is ErrEmptySeq / ErrSeqTooLong exactly where Align would return them.
 func (algn *Aligner) AlignBatch(qs, ts [][]byte) ([]*AlignmentResult, []error) {
+	return alignBatchOn([]*Aligner{algn}, qs, ts)
+}
+
+// AlignBatchMulti shards one batch over several devices, one Aligner (ctx) per device: the
+// library cuts length-binned, work-balanced shards and drives every device from its own host
+// thread (wfacuda_align_batch_multi); pairs are independent, there is no collective.  The
+// buffers are those of algns[0].
+func AlignBatchMulti(algns []*Aligner, qs, ts [][]byte) ([]*AlignmentResult, []error) {
+	return alignBatchOn(algns, qs, ts)
+}
+
+func alignBatchOn(algns []*Aligner, qs, ts [][]byte) ([]*AlignmentResult, []error) {
+	algn := algns[0]
 	n := len(qs)
 	results := make([]*AlignmentResult, n)
 	errs := make([]error, n)
+	fail := func(err error) ([]*AlignmentResult, []error) {
+		for i := range errs {
+			errs[i] = err
+		}
+		return results, errs
+	}
 	if n == 0 {
 		return results, errs
 	}
@@ -98,54 +149,75 @@ func (algn *Aligner) AlignBatch(qs, ts [][]byte) ([]*AlignmentResult, []error) {
 	for i := range qs {
 		total += len(qs[i]) + len(ts[i])
 	}
-	// The byte pool lives in page-locked memory from the library (wfacuda_host_alloc): the DMA
-	// engine reads it directly instead of the library staging it through its own pinned buffers,
-	// and it is C memory, so no Go pointer is retained by C (cgo pointer rule).
-	poolPtr := C.wfacuda_host_alloc(C.size_t(total + 16))
-	if poolPtr == nil {
-		err := fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(nil)))
-		for i := range errs {
-			errs[i] = err
+	// page-locked buffers of the Aligner, reused call after call
+	b := &algn.cuda.buf
+	sizes := [7]int{total + 16, 8 * n, 4 * n, 8 * n, 4 * n, int(unsafe.Sizeof(C.wfacuda_result{})) * n, 8 * n}
+	var ptr [8]unsafe.Pointer
+	for i, sz := range sizes {
+		p, err := b[i].reserve(sz)
+		if err != nil {
+			return fail(err)
 		}
-		return results, errs
+		ptr[i] = p
 	}
-	defer C.wfacuda_host_free(poolPtr)
-	pool := unsafe.Slice((*byte)(poolPtr), total+16)[:0]
-	qOff, tOff := make([]C.uint64_t, n), make([]C.uint64_t, n)
-	qLen, tLen := make([]C.uint32_t, n), make([]C.uint32_t, n)
+	opsWords := total/4 + 16*n + 64
+	if b[7].cap/8 > opsWords {
+		opsWords = b[7].cap / 8
+	}
+	p7, err := b[7].reserve(8 * opsWords)
+	if err != nil {
+		return fail(err)
+	}
+	ptr[7] = p7
+	pool := unsafe.Slice((*byte)(ptr[0]), total+16)
+	qOff, qLen := unsafe.Slice((*C.uint64_t)(ptr[1]), n), unsafe.Slice((*C.uint32_t)(ptr[2]), n)
+	tOff, tLen := unsafe.Slice((*C.uint64_t)(ptr[3]), n), unsafe.Slice((*C.uint32_t)(ptr[4]), n)
+	at := 0
 	for i := range qs {
-		qOff[i], qLen[i] = C.uint64_t(len(pool)), C.uint32_t(len(qs[i]))
-		pool = append(pool, qs[i]...)
-		tOff[i], tLen[i] = C.uint64_t(len(pool)), C.uint32_t(len(ts[i]))
-		pool = append(pool, ts[i]...)
+		qOff[i], qLen[i] = C.uint64_t(at), C.uint32_t(len(qs[i]))
+		at += copy(pool[at:], qs[i])
+		tOff[i], tLen[i] = C.uint64_t(at), C.uint32_t(len(ts[i]))
+		at += copy(pool[at:], ts[i])
 	}
-	pool = append(pool, make([]byte, 16)...)
-	res := make([]C.wfacuda_result, n)
-	off := make([]C.uint64_t, n)
-	ops := make([]uint64, total/4+16*n+64)
+	for i := at; i < total+16; i++ {
+		pool[i] = 0
+	}
+	// one ctx per device; the array itself is C memory too
+	ctxs := (*[64]*C.wfacuda_ctx)(C.malloc(C.size_t(len(algns)) * C.size_t(unsafe.Sizeof((*C.wfacuda_ctx)(nil)))))
+	defer C.free(unsafe.Pointer(ctxs))
+	for i, a := range algns {
+		ctxs[i] = a.cuda.ctx
+	}
 	call := func() C.int {
-		return C.wfacuda_align_batch(algn.cuda.ctx, C.uint64_t(n), (*C.uint8_t)(unsafe.Pointer(&pool[0])),
-			&qOff[0], &qLen[0], &tOff[0], &tLen[0], &res[0],
-			(*C.uint64_t)(unsafe.Pointer(&ops[0])), C.uint64_t(len(ops)), &off[0])
+		if len(algns) == 1 {
+			return C.wfacuda_align_batch(algn.cuda.ctx, C.uint64_t(n), (*C.uint8_t)(ptr[0]),
+				&qOff[0], &qLen[0], &tOff[0], &tLen[0], (*C.wfacuda_result)(ptr[5]),
+				(*C.uint64_t)(ptr[7]), C.uint64_t(opsWords), (*C.uint64_t)(ptr[6]))
+		}
+		return C.wfacuda_align_batch_multi(&ctxs[0], C.int(len(algns)), C.uint64_t(n), (*C.uint8_t)(ptr[0]),
+			&qOff[0], &qLen[0], &tOff[0], &tLen[0], (*C.wfacuda_result)(ptr[5]),
+			(*C.uint64_t)(ptr[7]), C.uint64_t(opsWords), (*C.uint64_t)(ptr[6]))
 	}
 	rc := call()
 	if rc == C.WFACUDA_E_OPS_CAPACITY {
-		ops = make([]uint64, uint64(C.wfacuda_last_ops_total(algn.cuda.ctx)))
+		opsWords = int(C.wfacuda_last_ops_total(algn.cuda.ctx))
+		if ptr[7], err = b[7].reserve(8 * opsWords); err != nil {
+			return fail(err)
+		}
 		rc = call()
 	}
 	if rc != 0 {
-		err := fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(algn.cuda.ctx)))
-		for i := range errs {
-			errs[i] = err
-		}
-		return results, errs
+		return fail(fmt.Errorf("wfa: %s", C.GoString(C.wfacuda_last_error(algn.cuda.ctx))))
 	}
+	res := unsafe.Slice((*C.wfacuda_result)(ptr[5]), n)
+	off := unsafe.Slice((*C.uint64_t)(ptr[6]), n)
+	ops := unsafe.Slice((*uint64)(ptr[7]), opsWords)
 	for i := 0; i < n; i++ {
 		switch res[i].status {
 		case C.WFACUDA_OK:
 			r := NewAlignmentResult(algn.opt.GlobalAlignment) // pool, wfa_cigar.go:67-72
-			a := uint64(off[i]) // pairs complete in any order on the GPU: off[i] is where pair i's ops landed
-			r.Ops = append(r.Ops[:0], ops[a:a+uint64(res[i].n_ops)]...) // already reversed + merged
+			a := uint64(off[i])                               // pairs complete in any order on the GPU: off[i] is where pair i's ops landed
+			r.Ops = append(r.Ops[:0], ops[a:a+uint64(res[i].n_ops)]...) // already reversed + merged; copied into Go memory
 			r.Score = uint32(res[i].score)
 			r.TBegin, r.TEnd = int(res[i].tbegin), int(res[i].tend)
 			r.QBegin, r.QEnd = int(res[i].qbegin), int(res[i].qend)
@@ -162,14 +234,6 @@ func (algn *Aligner) AlignBatch(qs, ts [][]byte) ([]*AlignmentResult, []error) {
 		}
 	}
 	return results, errs
-}
-
-// AlignBatchMulti shards one batch over several devices, one goroutine per device
-// inside the library (wfacuda_align_batch_multi): pairs are independent, no collective.
-func AlignBatchMulti(algns []*Aligner, qs, ts [][]byte) ([]*AlignmentResult, []error) {
-	// Same marshalling as AlignBatch with ctxs := []*C.wfacuda_ctx{algns[i].cuda.ctx...}
-	// passed to C.wfacuda_align_batch_multi; omitted here for brevity of the shim.
-	return algns[0].AlignBatch(qs, ts)
 }
 
 // FillComponents aligns one pair and fills algn.M / I / D from the GPU's wavefront store
@@ -202,6 +266,11 @@ func (algn *Aligner) FillComponents(q, t *[]byte) (*AlignmentResult, error) {
 		return nil, ErrEmptySeq
 	case C.WFACUDA_ERR_SEQ_TOO_LONG:
 		return nil, ErrSeqTooLong
+	}
+	// the GPU-backed Aligner has no host-side components until somebody asks for them
+	if algn.M == nil {
+		algn.M, algn.I, algn.D = NewComponent(), NewComponent(), NewComponent()
+		algn.M.IsM = true
 	}
 	algn.M.Reset()
 	algn.I.Reset()

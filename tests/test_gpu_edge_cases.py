@@ -242,3 +242,36 @@ def test_pipeline_graded_chunks_wire_descriptors_and_invalid_pairs(built_lib):
 def batch_slice(batch, a, b):
     pairs = [batch.pair(i) for i in range(a, b)]
     return datagen.Batch.from_pairs(pairs)
+
+
+def test_scattered_pools_are_gathered(built_lib):
+    """Pools where a batch's sequences are NOT one dense range: all queries then all targets, and
+    targets that are windows into one shared reference (65 536 pairs each, so the call is cut
+    into pipeline chunks).  Every chunk gathers its own sequences instead of uploading the range
+    between its first and last byte -- which would be nearly the whole pool per chunk: the
+    host-to-device bytes must stay near the sum of the sequence lengths."""
+    import parity
+    rng = np.random.default_rng(17)
+    n, L = 65_536, 150
+    # (a) queries first, then targets
+    q = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=(n, L))
+    t = q.copy()
+    mut = rng.random((n, L)) < 0.04
+    t[mut] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(mut.sum()))
+    pool = np.concatenate([q.reshape(-1), t.reshape(-1), np.zeros(64, np.uint8)])
+    q_off = (np.arange(n, dtype=np.uint64) * L); t_off = q_off + np.uint64(n * L)
+    lens = np.full(n, L, np.uint32)
+    batch_a = datagen.Batch(pool, q_off, lens, t_off, lens)
+    # (b) reads against windows of one shared reference (windows overlap)
+    ref_len = 1 << 20
+    ref = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=ref_len)
+    starts = rng.integers(0, ref_len - L - 8, n)
+    reads = ref[starts[:, None] + np.arange(L)[None, :]].copy()
+    mut = rng.random((n, L)) < 0.04
+    reads[mut] = rng.choice(np.frombuffer(b"ACGT", np.uint8), size=int(mut.sum()))
+    pool_b = np.concatenate([ref, reads.reshape(-1), np.zeros(64, np.uint8)])
+    batch_b = datagen.Batch(pool_b, np.uint64(ref_len) + np.arange(n, dtype=np.uint64) * L, lens, starts.astype(np.uint64), lens)
+    for batch, what in ((batch_a, "queries then targets"), (batch_b, "shared reference")):
+        gpu, ref_, stats = parity.check(batch, what=what, threads=os.cpu_count() or 8)
+        seq = int(batch.q_len.sum(dtype=np.uint64) + batch.t_len.sum(dtype=np.uint64))
+        assert stats["h2d_bytes"] < 1.5 * seq + 64 * len(batch), (what, stats["h2d_bytes"], seq)

@@ -610,10 +610,15 @@ class Aligner:
         seq_bytes = np.ascontiguousarray(seq_bytes, np.uint8)
         q_off = np.ascontiguousarray(q_off, np.uint64); t_off = np.ascontiguousarray(t_off, np.uint64)
         q_len = np.ascontiguousarray(q_len, np.uint32); t_len = np.ascontiguousarray(t_len, np.uint32)
-        results = np.zeros(n, RESULT_DTYPE); ops_off = np.zeros(n, np.uint64)
-        cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64 if want_ops else 0
+        bufs = getattr(self, "_bufs", None)
+        if not want_ops:
+            cap = 0
+        elif bufs is not None and len(bufs[0]) >= n:
+            cap = len(bufs[2])
+        else:
+            cap = int(q_len.sum(dtype=np.uint64) + t_len.sum(dtype=np.uint64)) // 4 + 16 * n + 64
         while True:
-            ops = np.empty(max(cap, 1), np.uint64)
+            results, ops_off, ops = self._out_buffers(n, cap)        # page-locked, kept across calls
             rc = self._L.wfacuda_align_batch_multi(arr, len(ctxs), n, seq_bytes.ctypes.data, q_off.ctypes.data, q_len.ctypes.data,
                                                    t_off.ctypes.data, t_len.ctypes.data, results.ctypes.data,
                                                    ops.ctypes.data if want_ops else None, cap, ops_off.ctypes.data)

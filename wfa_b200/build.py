@@ -24,10 +24,23 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+def build_host_bench(force=False):
+    """bench_api: the reference's call shape (AlignBatch on per-pair byte strings) through the C++
+    mirror of the Go API -- what bench.py reports as e2e.api_value."""
+    exe = os.path.join(HERE, "host", "bench_api")
+    src = [os.path.join(HERE, "host", "bench_api.cpp"), os.path.join(HERE, "host", "wfa.hpp"), LIB]
+    if force or _stale(exe, src):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", exe, src[0], "-I" + os.path.join(HERE, "host"),
+                               "-L" + HERE, "-lwfacuda", "-lwfagen", "-Wl,-rpath,$ORIGIN/.."])
+    return exe
+
+
 def build_all(force=False):
     from . import datagen
     datagen.build(force)
-    return build_cuda(force)
+    lib = build_cuda(force)
+    build_host_bench(force)
+    return lib
 
 
 if __name__ == "__main__":

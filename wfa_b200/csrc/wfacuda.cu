@@ -193,6 +193,14 @@ struct wfacuda_ctx {
     wfacuda_ctx *h2d_parent = nullptr; /* worker: whose h2d_fifo to use */
     cudaEvent_t ev_h2d = nullptr;      /* worker: completion of its chunk's sequence upload */
     WireDesc *pin_descs = nullptr; size_t pin_descs_cap = 0;   /* worker: page-locked wire descriptors, DMA'd without a staging copy */
+    /* Host waits.  cudaStreamSynchronize spins on a core; a pipeline worker that shares few cores with
+     * many other workers (several ranks on one box) waits on an event created with
+     * cudaEventBlockingSync instead and sleeps. */
+    bool blocking_sync = false; cudaEvent_t ev_block = nullptr;
+    /* the counters as last fetched from the device, valid while nothing was launched since (saves
+     * the second read-back + wait at the end of a run whose last class already fetched them) */
+    Counters hc_cache{}; bool hc_cache_valid = false;
+    uint8_t *pin_pool = nullptr; size_t pin_pool_cap = 0;      /* page-locked copy of a batch's sequences when they are scattered over a much larger pool */
     DevBuf wire_dev;                                           /* their landing place on the device */
     DevBuf render_meta, render_cigar, render_text;             /* wfacuda_batch_render: offsets / lengths / cursors, strings */
     uint64_t render_cigar_total = 0, render_text_total = 0;
@@ -240,6 +248,14 @@ int fail(wfacuda_ctx *ctx, int code, const char *fmt, ...)
             return fail(ctx, e_ == cudaErrorMemoryAllocation ? WFACUDA_E_NOMEM : WFACUDA_E_CUDA, \
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+cudaError_t wait_stream(wfacuda_ctx *ctx, cudaStream_t st)
+{
+    if (!ctx->blocking_sync) return cudaStreamSynchronize(st);
+    if (!ctx->ev_block) { cudaError_t e = cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+    cudaError_t e = cudaEventRecord(ctx->ev_block, st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(ctx->ev_block);
+}
 
 double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec / 1e6; }
 
@@ -371,7 +387,7 @@ int staged_d2h(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes, bool 
 {
     if (bytes >= 65536 && is_pinned(dst)) {
         CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        if (!defer_sync) CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!defer_sync) CU(ctx, wait_stream(ctx, ctx->stream));
         ctx->stats.d2h_bytes += bytes;
         return 0;
     }
@@ -404,7 +420,7 @@ int fetch_small(wfacuda_ctx *ctx, void *dst, const void *src, size_t bytes)
     while (done < bytes) {
         const size_t chunk = std::min(ctx->pinned_cap, bytes - done);
         CU(ctx, cudaMemcpyAsync(ctx->pinned[0], (const char *)src + done, chunk, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, wait_stream(ctx, ctx->stream));
         memcpy((char *)dst + done, ctx->pinned[0], chunk);
         done += chunk;
     }
@@ -598,10 +614,11 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
         else     { if (bits == 2) align_kernel<2, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P);
                    else           align_kernel<8, false><<<lp.blocks, lp.threads, lp.smem, ctx->stream>>>(P); }
         CU(ctx, cudaGetLastError());
-        ctx->stats.kernel_launches++; ctx->stats.align_launches++;
+        ctx->stats.kernel_launches++; ctx->stats.align_launches++; ctx->hc_cache_valid = false;
         ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, lp.slot_bytes * lp.group * lp.workers);
         Counters hc;
         { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
+        ctx->hc_cache = hc; ctx->hc_cache_valid = true;
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   %s kernel: host launch at %.2f, sync returned %.2f ms since call\n", cta ? "cta" : "warp", tk0 - g_dbg_t0, now_ms() - g_dbg_t0);
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch %s bits=%d attempt %d: %zu pairs, %d blocks x %d thr, ring_cap %d, slim passes %d, group %d, smem %zu, slot %.1f KB (scale %.3f), used max %.1f KB, retry %llu\n", slim ? "slim" : cta ? "cta" : "warp", bits, attempt, order.size(), lp.blocks, lp.threads, lp.ring_cap, slim_p, lp.group, lp.smem, lp.slot_bytes / 1024.0, scale, hc.arena_used_max / 1024.0, (unsigned long long)hc.retry_n);
         if (hc.retry_n == 0) {
@@ -894,7 +911,7 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             const int fblocks = (int)std::min<uint64_t>((g1 - g0 + LANE_FINISH_WARPS - 1) / LANE_FINISH_WARPS, (uint64_t)ctx->sm_count * 16);
             lane_finish_kernel<<<fblocks, 32 * LANE_FINISH_WARPS, 0, ctx->stream>>>(P);
             CU(ctx, cudaGetLastError());
-            ctx->stats.kernel_launches += G.n_stages + 1; ctx->stats.align_launches++;
+            ctx->stats.kernel_launches += G.n_stages + 1; ctx->stats.align_launches++; ctx->hc_cache_valid = false;
         }
         if (handover) {
             KParams H = base;
@@ -904,12 +921,13 @@ int run_lane_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
             H.ops_pool = (uint64_t *)ctx->ops_pool.p; H.ops_cap = ctx->ops_pool.cap / 8;
             align_kernel<2, false><<<ho_blocks, 128, ho_smem, ctx->stream>>>(H);
             CU(ctx, cudaGetLastError());
-            ctx->stats.kernel_launches++; ctx->stats.align_launches++;
+            ctx->stats.kernel_launches++; ctx->stats.align_launches++; ctx->hc_cache_valid = false;
         }
         const double tl1 = now_ms();
         ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, total);
         Counters hc;
         { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
+        ctx->hc_cache = hc; ctx->hc_cache_valid = true;
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   lane kernels: host launch at %.2f (took %.2f), sync returned %.2f ms since call; device span %.3f ms\n", tl0 - g_dbg_t0, tl1 - tl0, now_ms() - g_dbg_t0, (hc.t_last - hc.t_first) / 1e6);
         if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch lane attempt %d: %zu pairs, %d stages (ends %d %d %d %d; entered %llu %llu %llu), rows %d, slot0 %.1f KB, %.1f MB device, retry %llu\n", attempt, order.size(), G.n_stages, G.stage_end[0], G.stage_end[1], G.stage_end[2], G.stage_end[3], (unsigned long long)hc.lane_count[1], (unsigned long long)hc.lane_count[2], (unsigned long long)hc.lane_count[3], G.n_rows, G.slot_words[0] / 256.0, total / 1e6, (unsigned long long)hc.retry_n);
         /* learn the next batch's stage boundaries: the score indices by which 40 % and 85 % of
@@ -1064,6 +1082,8 @@ void wfacuda_destroy(wfacuda_ctx *ctx)
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     if (ctx->ev_h2d) cudaEventDestroy(ctx->ev_h2d);
     if (ctx->pin_descs) cudaFreeHost(ctx->pin_descs);
+    if (ctx->pin_pool) cudaFreeHost(ctx->pin_pool);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     if (ctx->h2d_fifo) { cudaStreamSynchronize(ctx->h2d_fifo); cudaStreamDestroy(ctx->h2d_fifo); }
     if (ctx->stream_main) cudaStreamDestroy(ctx->stream_main);
     if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
@@ -1161,11 +1181,13 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         }
         ctx->pin_descs_owner = b;
     }
+    bool fifo_turn_held = false;
+    struct TurnGuard { wfacuda_ctx *c; bool &held; ~TurnGuard() { if (held && c->h2d_turn) c->h2d_turn->release(); } } turn_guard{ctx, fifo_turn_held};
     auto body = [&]() -> int {
         const double t0 = now_ms();
         ctx->stats = wfacuda_stats{};
         /* validation (wfa.go:202-209) + extent of the byte pool actually referenced */
-        uint64_t lo = UINT64_MAX, hi = 0, words = 0;
+        uint64_t lo = UINT64_MAX, hi = 0, words = 0, sum_len = 0;
         for (uint64_t i = 0; i < n_pairs; i++) {
             const uint32_t dn = q_len[i], dm = t_len[i];
             if (dn == 0 || dm == 0) { b->host_status[i] = ST_EMPTY; b->n_invalid++; continue; }
@@ -1173,9 +1195,28 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             lo = std::min(lo, std::min(q_off[i], t_off[i]));
             hi = std::max(hi, std::max(q_off[i] + dn, t_off[i] + dm));
             words += (((uint64_t)((dn + 15) >> 4) + 3) & ~3ull) + (((uint64_t)((dm + 15) >> 4) + 3) & ~3ull);
+            sum_len += (uint64_t)dn + dm;
         }
         if (lo == UINT64_MAX) { lo = 0; hi = 0; }
-        const uint64_t base = lo & ~(uint64_t)15;            /* keep the caller's alignment mod 16 */
+        uint64_t base = lo & ~(uint64_t)15;                  /* keep the caller's alignment mod 16 */
+        /* The batch's sequences are copied as ONE range [base, hi) of the caller's pool -- right for
+         * the usual pool of interleaved pairs.  When they are scattered over a much larger pool (all
+         * queries then all targets cut into chunks, windows into one shared reference, the runs of a
+         * multi-GPU shard) that range would be most of the pool for every chunk: gather them into a
+         * page-locked pool of the ctx instead and address that. */
+        const bool gather = hi - base > 2 * sum_len + (1u << 20);
+        const uint8_t *src = seq_bytes;
+        if (gather) {
+            if (ctx->pin_pool_cap < sum_len + 64) {
+                if (ctx->pin_pool) cudaFreeHost(ctx->pin_pool);
+                ctx->pin_pool = nullptr; ctx->pin_pool_cap = 0;
+                const size_t want = sum_len + sum_len / 8 + 4096;
+                if (cudaHostAlloc((void **)&ctx->pin_pool, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(ctx, WFACUDA_E_NOMEM, "page-locked sequence pool allocation failed"); }
+                ctx->pin_pool_cap = want;
+            }
+            src = ctx->pin_pool; base = 0; hi = sum_len;
+        }
+        uint64_t gcur = 0;
         /* pipeline worker: 20-byte wire descriptors when the chunk's offsets fit 32 bits */
         const bool wire = fifo && hi - base < 0xfffffff0ull && words < 0xfffffff0ull;
         if (!wire) { b->descs_own.resize(n_pairs); b->descs = b->descs_own.data(); }
@@ -1185,7 +1226,12 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         for (uint64_t i = 0; i < n_pairs; i++) {
             const bool ok = !any_invalid || b->host_status[i] == ST_PENDING;
             const uint32_t dn = ok ? q_len[i] : 0, dm = ok ? t_len[i] : 0;
-            const uint64_t qb = ok ? q_off[i] - base : 0, tb = ok ? t_off[i] - base : 0, qw = ok ? words : 0;
+            uint64_t qb = ok ? q_off[i] - base : 0, tb = ok ? t_off[i] - base : 0;
+            const uint64_t qw = ok ? words : 0;
+            if (gather && ok) {
+                qb = gcur; memcpy(ctx->pin_pool + gcur, seq_bytes + q_off[i], dn); gcur += dn;
+                tb = gcur; memcpy(ctx->pin_pool + gcur, seq_bytes + t_off[i], dm); gcur += dm;
+            }
             if (ok) {
                 words += ((uint64_t)((dn + 15) >> 4) + 3) & ~3ull;
                 b->seq_bases += (uint64_t)dn + dm;
@@ -1213,19 +1259,20 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
             if (wire && (rc = ensure(ctx, ctx->wire_dev, n_pairs * sizeof(WireDesc)))) return rc;
             /* bounded queue depth, chunk order: released when this chunk's copies are done */
             if (ctx->h2d_ticket >= 0) ctx->h2d_turn->acquire_ordered((uint64_t)ctx->h2d_ticket); else ctx->h2d_turn->acquire();
+            fifo_turn_held = true;                           /* released when this chunk's copies are done, or by the guard on any early return */
             std::lock_guard<std::mutex> lk(par->h2d_mu);
             if (wire) CU(ctx, cudaMemcpyAsync(ctx->wire_dev.p, ctx->pin_descs, n_pairs * sizeof(WireDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
             else CU(ctx, cudaMemcpyAsync(b->d_descs, b->descs, n_pairs * sizeof(PairDesc), cudaMemcpyHostToDevice, par->h2d_fifo));
-            if (b->raw_bytes) CU(ctx, cudaMemcpyAsync(b->d_raw, seq_bytes + base, b->raw_bytes, cudaMemcpyHostToDevice, par->h2d_fifo));
+            if (b->raw_bytes) CU(ctx, cudaMemcpyAsync(b->d_raw, src + base, b->raw_bytes, cudaMemcpyHostToDevice, par->h2d_fifo));
             CU(ctx, cudaEventRecord(ctx->ev_h2d, par->h2d_fifo));
             ctx->stats.h2d_bytes += b->raw_bytes + n_pairs * (wire ? sizeof(WireDesc) : sizeof(PairDesc));
         } else if (b->raw_bytes) {
-            if (ctx->h2d_turn && b->raw_bytes >= 65536 && is_pinned(seq_bytes + base)) {
+            if (ctx->h2d_turn && b->raw_bytes >= 65536 && is_pinned(src + base)) {
                 struct Turn { wfacuda_ctx::Turns *t; Turn(wfacuda_ctx::Turns *t_) : t(t_) { t->acquire(); } ~Turn() { t->release(); } } turn(ctx->h2d_turn);
-                CU(ctx, cudaMemcpyAsync(b->d_raw, seq_bytes + base, b->raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
-                CU(ctx, cudaStreamSynchronize(ctx->stream));
+                CU(ctx, cudaMemcpyAsync(b->d_raw, src + base, b->raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+                CU(ctx, wait_stream(ctx, ctx->stream));
                 ctx->stats.h2d_bytes += b->raw_bytes;
-            } else if ((rc = staged_h2d(ctx, b->d_raw, seq_bytes + base, b->raw_bytes))) return rc;
+            } else if ((rc = staged_h2d(ctx, b->d_raw, src + base, b->raw_bytes))) return rc;
         }
         if (b->raw_bytes) CU(ctx, dev_fill((char *)b->d_raw + b->raw_bytes, 0, 64, ctx->stream));
         const double t2 = now_ms();
@@ -1285,12 +1332,12 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
         /* FIFO uploads: host-side wait for this chunk's copies (kernels queued behind a device-side
          * event wait were seen to hold up the other workers' streams -- streams share hardware
          * queues); the copies queued behind these are not affected by when this thread wakes up */
-        if (fifo) { const cudaError_t e = cudaEventSynchronize(ctx->ev_h2d); ctx->h2d_turn->release(); CU(ctx, e); }
+        if (fifo) { const cudaError_t e = cudaEventSynchronize(ctx->ev_h2d); ctx->h2d_turn->release(); fifo_turn_held = false; CU(ctx, e); }
         if (b->wire && n_pairs) {
             expand_descs_kernel<<<(int)std::min<uint64_t>((n_pairs + 255) / 256, 1184), 256, 0, ctx->stream>>>((const WireDesc *)ctx->wire_dev.p, (uint32_t)n_pairs, (PairDesc *)b->d_descs);
             CU(ctx, cudaGetLastError());
         }
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!fifo) CU(ctx, wait_stream(ctx, ctx->stream));      /* (FIFO copies were waited for above; the kernels of run() follow on this stream) */
         if (dbg) fprintf(stderr, "[wfacuda] upload: validate+descs %.2f ms, alloc+seq h2d %.2f, descs h2d %.2f, binning %.2f, sync %.2f\n", t1 - t0, t2 - t1, t3 - t2, t4 - t3, now_ms() - t4);
         return 0;
     };
@@ -1317,6 +1364,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     const uint32_t fills0 = g_fill_launches;
     int rc;
     if ((rc = ensure(ctx, ctx->ctr, sizeof(Counters)))) return rc;
+    ctx->hc_cache_valid = false;
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     CU(ctx, dev_fill(ctx->ctr.p, 0, sizeof(Counters), ctx->stream));
     CU(ctx, dev_fill(b->d_flags, 0, b->sz_flags, ctx->stream));
@@ -1327,7 +1375,7 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
         memset(init.data(), 0, n * sizeof(Result));
         for (uint64_t i = 0; i < n; i++) init[i].status = b->host_status[i];
         if ((rc = staged_h2d(ctx, b->d_results, init.data(), n * sizeof(Result)))) return rc;
-        CU(ctx, cudaStreamSynchronize(ctx->stream));     /* init goes out of scope */
+        CU(ctx, wait_stream(ctx, ctx->stream));     /* init goes out of scope */
     } else if (n) CU(ctx, dev_fill(b->d_results, 0xff, n * sizeof(Result), ctx->stream));
     const uint64_t n_valid = b->order_warp.size() + b->order_cta.size() + b->order_lane.size();
     if (n_valid) {
@@ -1403,9 +1451,10 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     /* ops stay where the kernels put them (completion order): pair i's words start at
      * d_where[i] of the pool, and the pool's used prefix is what download() copies */
     Counters hc{};
-    if ((rc = fetch_small(ctx, &hc, ctx->ctr.p, sizeof hc))) return rc;
+    if (ctx->hc_cache_valid) hc = ctx->hc_cache;
+    else if ((rc = fetch_small(ctx, &hc, ctx->ctr.p, sizeof hc))) return rc;
     CU(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, wait_stream(ctx, ctx->stream));
     cudaEventElapsedTime(&ctx->stats.ms_pack, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.ms_align, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->stats.ms_total_device, ctx->ev[0], ctx->ev[3]);
@@ -1441,7 +1490,7 @@ int wfacuda_batch_download(wfacuda_ctx *ctx, wfacuda_batch *b, wfacuda_result *r
         }
         if (b->ops_total) if ((rc = staged_d2h(ctx, ops, ctx->ops_pool.p, b->ops_total * 8, true))) return rc;
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));       /* copies into page-locked caller memory were left in flight */
+    CU(ctx, wait_stream(ctx, ctx->stream));       /* copies into page-locked caller memory were left in flight */
     if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda] download: %.2f ms for %.1f MB\n", now_ms() - t0, ctx->stats.d2h_bytes / 1e6);
     return 0;
 }
@@ -1502,7 +1551,7 @@ int wfacuda_batch_render(wfacuda_ctx *ctx, wfacuda_batch *b, int only_aligned_re
         if ((rc = staged_d2h(ctx, text_len, R.text_len, n * 4))) return rc;
         if (tot[1] && (rc = staged_d2h(ctx, text, R.text, tot[1]))) return rc;
     }
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, wait_stream(ctx, ctx->stream));
     return 0;
 }
 
@@ -1538,7 +1587,7 @@ int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len,
     if (used_hdr == 0 || (uint64_t)used_hdr * sizeof(RowHdr) > ctx->dump_slot_bytes) return fail(ctx, WFACUDA_E_CUDA, "no row headers reported for the pair");
     std::vector<RowHdr> hdr(used_hdr);
     if ((rc = staged_d2h(ctx, hdr.data(), ctx->arena.p, (size_t)used_hdr * sizeof(RowHdr)))) return rc;
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, wait_stream(ctx, ctx->stream));
     uint64_t min_off = slot_words, want_cells = 0; uint32_t want_rows = 0;
     for (uint32_t i = 0; i < used_hdr; i++) {
         const RowHdr &h = hdr[i];
@@ -1569,7 +1618,7 @@ int wfacuda_align_components(wfacuda_ctx *ctx, const uint8_t *q, uint32_t q_len,
     std::vector<uint32_t> slot(slot_words > min_off ? slot_words - min_off : 1);
     if (slot_words > min_off) {
         if ((rc = staged_d2h(ctx, slot.data(), (const uint32_t *)ctx->arena.p + min_off, slot.size() * 4))) return rc;
-        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        CU(ctx, wait_stream(ctx, ctx->stream));
     }
     uint64_t at = 0; uint32_t r = 0;
     for (uint32_t i = 0; i < used_hdr; i++) {
@@ -1751,10 +1800,17 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         if (!sub) return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: %s", g_tls_error.c_str());
         sub->h2d_turn = &ctx->h2d_turns;
         sub->h2d_parent = ctx;
-        if (cudaEventCreateWithFlags(&sub->ev_h2d, cudaEventDisableTiming) != cudaSuccess) { wfacuda_destroy(sub); return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: event creation failed"); }
+        if (cudaEventCreateWithFlags(&sub->ev_h2d, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { wfacuda_destroy(sub); return fail(ctx, WFACUDA_E_CUDA, "pipeline worker: event creation failed"); }
         ctx->subs.push_back(sub);
     }
     if (!ctx->h2d_fifo && cudaStreamCreateWithFlags(&ctx->h2d_fifo, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->h2d_fifo = nullptr; }
+    {
+        /* more workers than this process can expect cores for: sleep in the waits instead of spinning
+         * (WFACUDA_BLOCKING_SYNC=0/1 decides otherwise; a launcher that runs several ranks per box sets it) */
+        bool blocking = (unsigned)K > hw / 2;
+        if (const char *e = getenv("WFACUDA_BLOCKING_SYNC")) blocking = atoi(e) != 0;
+        for (wfacuda_ctx *sub : ctx->subs) sub->blocking_sync = blocking;
+    }
     /* uploads in flight: with the shared FIFO stream two keep the copy engine fed back to back
      * (the next copy is already queued when one completes) without letting chunks arrive late */
     ctx->h2d_turns.free_slots = ctx->h2d_fifo && !getenv("WFACUDA_NO_FIFO") ? 2 : 1;

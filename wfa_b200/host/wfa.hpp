@@ -17,8 +17,11 @@
 #ifndef WFA_HOST_WFA_HPP
 #define WFA_HOST_WFA_HPP
 
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wfacuda.h"
@@ -50,9 +53,24 @@ constexpr uint64_t MaskLower32 = 4294967295ull;
 
 inline void Op(uint64_t op, char *o, uint32_t *n) { *o = (char)(op >> 32); *n = (uint32_t)(op & MaskLower32); } /* :56-58 */
 
+/* The Ops of a result: like a Go slice, a view of words owned elsewhere -- the Aligner's page-locked
+ * output buffer for batch results (valid until the next Align / AlignBatch call on that Aligner
+ * or RecycleAligner), or the result's own copy after Detach(). */
+struct OpsView {
+    const uint64_t *p = nullptr; size_t n = 0;
+    size_t size() const { return n; }
+    const uint64_t &operator[](size_t i) const { return p[i]; }
+    const uint64_t *begin() const { return p; }
+    const uint64_t *end() const { return p + n; }
+};
+
 /* wfa_cigar.go:29-46, as left by process() (:136-214) -- computed on the GPU */
 struct AlignmentResult {
-    std::vector<uint64_t> Ops;
+    OpsView Ops;
+    std::vector<uint64_t> own_;                       /* storage of a detached result */
+    bool pooled_ = false;                             /* lives in its Aligner's result pool (wfa_cigar.go:62-96) */
+    /* copy the ops out of the Aligner's buffer: the result then outlives the next call */
+    void Detach() { if (Ops.p != own_.data() || own_.empty()) { own_.assign(Ops.begin(), Ops.end()); Ops.p = own_.data(); Ops.n = own_.size(); } }
     uint32_t Score = 0;
     int TBegin = 0, TEnd = 0, QBegin = 0, QEnd = 0;
     uint32_t AlignLen = 0, Matches = 0, Gaps = 0, GapRegions = 0;
@@ -111,7 +129,9 @@ public:
         ctx_ = wfacuda_create(device, &c);
         if (!ctx_) err_ = wfacuda_last_error(nullptr);
     }
-    ~Aligner() { if (ctx_) wfacuda_destroy(ctx_); }
+    ~Aligner() { release_buffers(); if (ctx_) wfacuda_destroy(ctx_); }
+    Aligner(const Aligner &) = delete;
+    Aligner &operator=(const Aligner &) = delete;
     bool ok() const { return ctx_ != nullptr; }
     const std::string &error() const { return err_; }
 
@@ -125,54 +145,38 @@ public:
         return nullptr;
     }
 
-    /* wfa.go:196-198 */
+    /* wfa.go:196-198.  The result is detached (owns its ops): free it with RecycleAlignmentResult. */
     Error Align(const std::string &q, const std::string &t, AlignmentResult **out)
     {
         std::vector<AlignmentResult *> rs; std::vector<Error> es;
         Error e = AlignBatch({q}, {t}, &rs, &es);
-        if (e) { *out = nullptr; return e; }
-        *out = rs[0];
+        *out = nullptr;
+        if (e) return e;
+        if (rs[0]) { AlignmentResult *r = new AlignmentResult(*rs[0]); r->pooled_ = false; r->Ops = rs[0]->Ops; r->own_.clear(); r->Detach(); *out = r; }
         return es[0];
     }
 
-    /* New: many pairs per call.  results[i] == nullptr where errors[i] != nil. */
+    /* New: many pairs per call -- the reference's call shape: [][]byte in, []*AlignmentResult out
+     * (wfa.go:196-201, result pool wfa_cigar.go:62-96).  results[i] == nullptr where errors[i] != nil.
+     * The sequences are flattened into one page-locked pool that the Aligner keeps across calls
+     * (the DMA engines read it directly), by several host threads; the result objects come from
+     * the Aligner's pool and their Ops are views of its page-locked output buffer: valid until the
+     * next call on this Aligner (Detach() copies), RecycleAlignmentResult is a no-op for them. */
     Error AlignBatch(const std::vector<std::string> &qs, const std::vector<std::string> &ts,
                      std::vector<AlignmentResult *> *results, std::vector<Error> *errors)
     {
-        const size_t n = qs.size();
-        std::vector<uint8_t> pool; std::vector<uint64_t> qo(n), to(n); std::vector<uint32_t> ql(n), tl(n);
-        size_t total = 0;
-        for (size_t i = 0; i < n; i++) total += qs[i].size() + ts[i].size();
-        pool.reserve(total + 16);
-        for (size_t i = 0; i < n; i++) {
-            qo[i] = pool.size(); ql[i] = (uint32_t)qs[i].size(); pool.insert(pool.end(), qs[i].begin(), qs[i].end());
-            to[i] = pool.size(); tl[i] = (uint32_t)ts[i].size(); pool.insert(pool.end(), ts[i].begin(), ts[i].end());
-        }
-        pool.resize(pool.size() + 16);
-        std::vector<wfacuda_result> res(n); std::vector<uint64_t> off(n);
-        std::vector<uint64_t> ops(total / 4 + 16 * n + 64);
-        int rc = wfacuda_align_batch(ctx_, n, pool.data(), qo.data(), ql.data(), to.data(), tl.data(), res.data(), ops.data(), ops.size(), off.data());
-        if (rc == WFACUDA_E_OPS_CAPACITY) {
-            ops.resize(wfacuda_last_ops_total(ctx_));
-            rc = wfacuda_align_batch(ctx_, n, pool.data(), qo.data(), ql.data(), to.data(), tl.data(), res.data(), ops.data(), ops.size(), off.data());
-        }
-        if (rc != 0) { err_ = wfacuda_last_error(ctx_); return err_.c_str(); }
-        results->assign(n, nullptr); errors->assign(n, nullptr);
-        for (size_t i = 0; i < n; i++) {
-            switch (res[i].status) {
-            case WFACUDA_OK: {
-                AlignmentResult *r = new AlignmentResult();
-                r->Ops.assign(ops.begin() + (long)off[i], ops.begin() + (long)off[i] + res[i].n_ops);
-                r->Score = res[i].score; r->TBegin = res[i].tbegin; r->TEnd = res[i].tend; r->QBegin = res[i].qbegin; r->QEnd = res[i].qend;
-                r->AlignLen = res[i].align_len; r->Matches = res[i].matches; r->Gaps = res[i].gaps; r->GapRegions = res[i].gap_regions;
-                (*results)[i] = r; break;
-            }
-            case WFACUDA_ERR_EMPTY_SEQ: (*errors)[i] = ErrEmptySeq; break;
-            case WFACUDA_ERR_SEQ_TOO_LONG: (*errors)[i] = ErrSeqTooLong; break;
-            default: (*errors)[i] = ErrResources;
-            }
-        }
-        return nullptr;
+        return align_batch_on(&ctx_, 1, qs, ts, results, errors);
+    }
+
+    /* The same over several devices: one Aligner (ctx) per device, sharded inside the library
+     * (wfacuda_align_batch_multi: length-binned LPT, one host thread per device, no collective).
+     * Buffers and result pool are this Aligner's. */
+    Error AlignBatchMulti(const std::vector<Aligner *> &others, const std::vector<std::string> &qs, const std::vector<std::string> &ts,
+                          std::vector<AlignmentResult *> *results, std::vector<Error> *errors)
+    {
+        std::vector<wfacuda_ctx *> ctxs{ctx_};
+        for (Aligner *o : others) ctxs.push_back(o->ctx_);
+        return align_batch_on(ctxs.data(), (int)ctxs.size(), qs, ts, results, errors);
     }
 
     /* CIGAR(onlyAignedRegion) and the AlignmentText lines of every pair of a batch, formatted on the
@@ -251,7 +255,7 @@ public:
         if (res.status != WFACUDA_OK) return ErrResources;
         comps->rows.resize(nr); comps->cells.resize(nc);
         AlignmentResult *r = new AlignmentResult();
-        r->Ops.assign(ops.begin(), ops.begin() + res.n_ops);
+        r->own_.assign(ops.begin(), ops.begin() + res.n_ops); r->Ops.p = r->own_.data(); r->Ops.n = r->own_.size();
         r->Score = res.score; r->TBegin = res.tbegin; r->TEnd = res.tend; r->QBegin = res.qbegin; r->QEnd = res.qend;
         r->AlignLen = res.align_len; r->Matches = res.matches; r->Gaps = res.gaps; r->GapRegions = res.gap_regions;
         *out = r;
@@ -259,6 +263,79 @@ public:
     }
 
 private:
+    /* page-locked, grow-only buffers shared by consecutive calls */
+    template <class T> struct Pinned {
+        T *p = nullptr; size_t cap = 0;
+        bool reserve(size_t n) { if (n <= cap) return true; if (p) wfacuda_host_free(p); cap = n + n / 4 + 64; p = (T *)wfacuda_host_alloc(cap * sizeof(T)); if (!p) cap = 0; return p != nullptr; }
+        void release() { if (p) wfacuda_host_free(p); p = nullptr; cap = 0; }
+    };
+    Pinned<uint8_t> pool_; Pinned<uint64_t> qo_, to_, off_, ops_; Pinned<uint32_t> ql_, tl_; Pinned<wfacuda_result> res_;
+    std::vector<AlignmentResult> objs_;
+    void release_buffers() { pool_.release(); qo_.release(); to_.release(); off_.release(); ops_.release(); ql_.release(); tl_.release(); res_.release(); }
+
+    template <class F> static void parallel(size_t n, F f)
+    {
+        const size_t T = n < 65536 ? 1 : std::max<size_t>(1, std::min<size_t>(16, std::thread::hardware_concurrency() / 2));
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < T; k++) th.emplace_back(f, k, n * k / T, n * (k + 1) / T);
+        f((size_t)0, (size_t)0, n / T);
+        for (auto &t : th) t.join();
+    }
+
+    Error align_batch_on(wfacuda_ctx *const *ctxs, int n_ctx, const std::vector<std::string> &qs, const std::vector<std::string> &ts,
+                         std::vector<AlignmentResult *> *results, std::vector<Error> *errors)
+    {
+        const size_t n = qs.size();
+        if (ts.size() != n) { err_ = "AlignBatch: qs and ts differ in length"; return err_.c_str(); }
+        /* flatten: per-thread byte counts, then every thread copies its range of pairs */
+        size_t part[17] = {0};
+        parallel(n, [&](size_t k, size_t a, size_t b) { size_t s = 0; for (size_t i = a; i < b; i++) s += qs[i].size() + ts[i].size(); part[k + 1] = s; });
+        for (int k = 1; k < 17; k++) part[k] += part[k - 1];
+        const size_t total = part[16];
+        if (!pool_.reserve(total + 64) || !qo_.reserve(n) || !to_.reserve(n) || !ql_.reserve(n) || !tl_.reserve(n) || !res_.reserve(n) || !off_.reserve(n) ||
+            !ops_.reserve(std::max<size_t>(ops_.cap, total / 4 + 16 * n + 64))) { err_ = wfacuda_last_error(nullptr); return err_.c_str(); }
+        parallel(n, [&](size_t k, size_t a, size_t b) {
+            size_t at = part[k];
+            for (size_t i = a; i < b; i++) {
+                qo_.p[i] = at; ql_.p[i] = (uint32_t)qs[i].size(); memcpy(pool_.p + at, qs[i].data(), qs[i].size()); at += qs[i].size();
+                to_.p[i] = at; tl_.p[i] = (uint32_t)ts[i].size(); memcpy(pool_.p + at, ts[i].data(), ts[i].size()); at += ts[i].size();
+            }
+        });
+        memset(pool_.p + total, 0, 16);
+        auto call = [&]() {
+            return n_ctx == 1 ? wfacuda_align_batch(ctxs[0], n, pool_.p, qo_.p, ql_.p, to_.p, tl_.p, res_.p, ops_.p, ops_.cap, off_.p)
+                              : wfacuda_align_batch_multi(ctxs, n_ctx, n, pool_.p, qo_.p, ql_.p, to_.p, tl_.p, res_.p, ops_.p, ops_.cap, off_.p);
+        };
+        int rc = call();
+        if (rc == WFACUDA_E_OPS_CAPACITY) {
+            if (!ops_.reserve(wfacuda_last_ops_total(ctxs[0]))) { err_ = wfacuda_last_error(nullptr); return err_.c_str(); }
+            rc = call();
+        }
+        if (rc != 0) { err_ = wfacuda_last_error(ctxs[0]); return err_.c_str(); }
+        /* result objects from the pool; Ops alias the output buffer (no per-pair allocation) */
+        if (objs_.size() < n) objs_.resize(n);
+        results->assign(n, nullptr); errors->assign(n, nullptr);
+        parallel(n, [&](size_t, size_t a, size_t b) {
+            for (size_t i = a; i < b; i++) {
+                const wfacuda_result &w = res_.p[i];
+                switch (w.status) {
+                case WFACUDA_OK: {
+                    AlignmentResult *r = &objs_[i];
+                    r->pooled_ = true; r->own_.clear();
+                    r->Ops.p = ops_.p + off_.p[i]; r->Ops.n = w.n_ops;
+                    r->Score = w.score; r->TBegin = w.tbegin; r->TEnd = w.tend; r->QBegin = w.qbegin; r->QEnd = w.qend;
+                    r->AlignLen = w.align_len; r->Matches = w.matches; r->Gaps = w.gaps; r->GapRegions = w.gap_regions;
+                    (*results)[i] = r; break;
+                }
+                case WFACUDA_ERR_EMPTY_SEQ: (*errors)[i] = ErrEmptySeq; break;
+                case WFACUDA_ERR_SEQ_TOO_LONG: (*errors)[i] = ErrSeqTooLong; break;
+                default: (*errors)[i] = ErrResources;
+                }
+            }
+        });
+        return nullptr;
+    }
+
     wfacuda_config config() const
     {
         wfacuda_config c{};
@@ -275,7 +352,7 @@ private:
 /* wfa.go:120-131 (ad is reset, unlike the reference's pooled Aligner) / :102-116 / wfa_cigar.go:92-96 */
 inline Aligner *New(const Penalties *p, const Options *opt, int device = 0) { return new Aligner(p, opt, device); }
 inline void RecycleAligner(Aligner *a) { delete a; }
-inline void RecycleAlignmentResult(AlignmentResult *r) { delete r; }
+inline void RecycleAlignmentResult(AlignmentResult *r) { if (r && !r->pooled_) delete r; }      /* pooled results go back with their Aligner */
 
 } // namespace wfa
 #endif
