@@ -124,6 +124,13 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg);
 /* (*Aligner).Align for many pairs (wfa.go:196-268), blocking, host buffers.
  *   seq_bytes            byte pool holding all sequences (arbitrary bytes, case-sensitive)
  *   q_off/q_len, t_off/t_len   per pair, offsets into seq_bytes
+ *                        The usual pool holds the pairs back to back (q0 t0 q1 t1 ...): every
+ *                        pipeline chunk then uploads one dense byte range.  Scattered pools are
+ *                        fine too -- all queries then all targets, windows into one shared
+ *                        reference, even per-pair heap strings addressed relative to the lowest
+ *                        one (seq_bytes = that address): when the range a chunk touches is much
+ *                        larger than its sequences, the library gathers them into a page-locked
+ *                        pool of its own first (one host copy per sequence) and uploads that.
  *   results[n_pairs]     filled for every pair (status says which are valid)
  *   ops / ops_capacity   receives the concatenated AlignmentResult.Ops words
  *                        (op<<32|n, already reversed + merged, wfa_cigar.go:32,123,136-169);

@@ -11,7 +11,7 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_host")
 
 def _build(built_lib):
     libdir = os.path.dirname(built_lib)
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_host.cpp"),
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-o", EXE, os.path.join(ROOT, "tests", "cpp", "test_host.cpp"),
                            "-L" + libdir, "-lwfacuda", "-Wl,-rpath," + libdir])
 
 

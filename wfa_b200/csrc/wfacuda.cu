@@ -1168,19 +1168,8 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
     const bool dbg = getenv("WFACUDA_DEBUG") != nullptr;
     /* pipeline worker with page-locked caller memory: sequence bytes and descriptors go through
      * the parent's FIFO upload stream */
-    const bool fifo = ctx->h2d_parent && ctx->h2d_parent->h2d_fifo && n_pairs && is_pinned(seq_bytes) &&
-                      ctx->pin_descs_owner == nullptr && !getenv("WFACUDA_NO_FIFO");
-    if (fifo) {
-        if (ctx->pin_descs_cap < n_pairs) {
-            if (ctx->pin_descs) cudaFreeHost(ctx->pin_descs);
-            ctx->pin_descs = nullptr; ctx->pin_descs_cap = 0;
-            if (cudaHostAlloc((void **)&ctx->pin_descs, (n_pairs + n_pairs / 8) * sizeof(WireDesc), cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError(); fail(ctx, WFACUDA_E_NOMEM, "page-locked descriptor buffer allocation failed"); delete b; return nullptr;
-            }
-            ctx->pin_descs_cap = n_pairs + n_pairs / 8;
-        }
-        ctx->pin_descs_owner = b;
-    }
+    const bool fifo_possible = ctx->h2d_parent && ctx->h2d_parent->h2d_fifo && n_pairs && ctx->pin_descs_owner == nullptr && !getenv("WFACUDA_NO_FIFO");
+    bool fifo = false;        /* decided in body(): the bytes to upload must sit in page-locked memory (the caller's, or the gathered pool) */
     bool fifo_turn_held = false;
     struct TurnGuard { wfacuda_ctx *c; bool &held; ~TurnGuard() { if (held && c->h2d_turn) c->h2d_turn->release(); } } turn_guard{ctx, fifo_turn_held};
     auto body = [&]() -> int {
@@ -1215,6 +1204,32 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
                 ctx->pin_pool_cap = want;
             }
             src = ctx->pin_pool; base = 0; hi = sum_len;
+        }
+        /* a pipeline worker stages a dense range of pageable caller memory the same way: one copy into
+         * its page-locked pool, which then goes through the FIFO like page-locked caller memory does */
+        const bool caller_pinned = is_pinned(seq_bytes);
+        if (!gather && fifo_possible && !caller_pinned && hi > base) {
+            const size_t want = hi - base + 64;
+            if (ctx->pin_pool_cap < want) {
+                if (ctx->pin_pool) cudaFreeHost(ctx->pin_pool);
+                ctx->pin_pool = nullptr; ctx->pin_pool_cap = 0;
+                if (cudaHostAlloc((void **)&ctx->pin_pool, want + want / 8, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return fail(ctx, WFACUDA_E_NOMEM, "page-locked sequence pool allocation failed"); }
+                ctx->pin_pool_cap = want + want / 8;
+            }
+            memcpy(ctx->pin_pool, seq_bytes + base, hi - base);
+            src = ctx->pin_pool - base;                      /* src + base is the staged copy */
+        }
+        fifo = fifo_possible && (gather || src != seq_bytes || caller_pinned);
+        if (fifo) {
+            if (ctx->pin_descs_cap < n_pairs) {
+                if (ctx->pin_descs) cudaFreeHost(ctx->pin_descs);
+                ctx->pin_descs = nullptr; ctx->pin_descs_cap = 0;
+                if (cudaHostAlloc((void **)&ctx->pin_descs, (n_pairs + n_pairs / 8) * sizeof(WireDesc), cudaHostAllocDefault) != cudaSuccess) {
+                    cudaGetLastError(); return fail(ctx, WFACUDA_E_NOMEM, "page-locked descriptor buffer allocation failed");
+                }
+                ctx->pin_descs_cap = n_pairs + n_pairs / 8;
+            }
+            ctx->pin_descs_owner = b;
         }
         uint64_t gcur = 0;
         /* pipeline worker: 20-byte wire descriptors when the chunk's offsets fit 32 bits */
@@ -1773,7 +1788,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
     /* one worker per chunk in flight: enough of them that uploads (PCIe-bound, taken in turns)
      * never wait for a worker that is still computing or downloading */
-    unsigned kmax = src_pinned ? std::min<unsigned>(16, std::max(2u, hw - 2)) : std::min<unsigned>(8, hw / 2);
+    unsigned kmax = std::min<unsigned>(16, std::max(2u, hw - 2));     /* (pageable memory is staged by the workers: host copies, one core each) */
     if (const char *e = getenv("WFACUDA_PIPE_WORKERS")) kmax = std::max(1, atoi(e));
     const int K = (int)std::min<uint64_t>(kmax, n_chunks);
     if ((int)ctx->subs.size() < K && ctx->arena.p) {
@@ -1807,7 +1822,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     {
         /* more workers than this process can expect cores for: sleep in the waits instead of spinning
          * (WFACUDA_BLOCKING_SYNC=0/1 decides otherwise; a launcher that runs several ranks per box sets it) */
-        bool blocking = (unsigned)K > hw / 2;
+        bool blocking = (unsigned)K > hw;
         if (const char *e = getenv("WFACUDA_BLOCKING_SYNC")) blocking = atoi(e) != 0;
         for (wfacuda_ctx *sub : ctx->subs) sub->blocking_sync = blocking;
     }

@@ -40,19 +40,19 @@ int main(int argc, char **argv)
     wfa::AdaptiveReductionOption ad = {10, 50, 1};
     if (adaptive && algn->AdaptiveReduction(&ad) != nullptr) return 3;
     std::vector<wfa::AlignmentResult *> rs; std::vector<wfa::Error> es;
-    double best = 1e30, sum = 0.0; uint64_t checksum = 0;
+    double best = 1e30, sum = 0.0, fl = 0.0, cl = 0.0, ob = 0.0; uint64_t checksum = 0;
     for (int it = 0; it < warmup + steps; it++) {
         const auto t0 = std::chrono::steady_clock::now();
         wfa::Error e = algn->AlignBatch(qs, ts, &rs, &es);
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (e) { std::fprintf(stderr, "AlignBatch failed: %s\n", e); return 4; }
-        if (it >= warmup) { sum += ms; best = ms < best ? ms : best; }
+        if (it >= warmup) { sum += ms; best = ms < best ? ms : best; fl += algn->last_flatten_ms; cl += algn->last_call_ms; ob += algn->last_objects_ms; }
     }
     uint64_t ok = 0;
     for (uint64_t i = 0; i < n; i++) if (rs[i]) { ok++; checksum += rs[i]->Score + rs[i]->Ops.size() * 31u + (rs[i]->Ops.size() ? rs[i]->Ops[0] : 0); }
-    std::printf("{\"api_value\": %.1f, \"ms_per_call_mean\": %.4f, \"ms_per_call_min\": %.4f, \"pairs\": %llu, \"pairs_ok\": %llu, \"steps\": %d, \"checksum\": %llu, "
+    std::printf("{\"api_value\": %.1f, \"ms_per_call_mean\": %.4f, \"ms_per_call_min\": %.4f, \"pairs\": %llu, \"pairs_ok\": %llu, \"steps\": %d, \"checksum\": %llu, \"flatten_ms\": %.3f, \"c_abi_calls_ms\": %.3f, \"objects_ms\": %.3f, "
                 "\"call\": \"wfa::Aligner::AlignBatch(vector<string>, vector<string>) -> vector<AlignmentResult*> (wfa.hpp, mirror of the Go API)\"}\n",
-                (double)n / (sum / steps / 1e3), sum / steps, best, (unsigned long long)n, (unsigned long long)ok, steps, (unsigned long long)checksum);
+                (double)n / (sum / steps / 1e3), sum / steps, best, (unsigned long long)n, (unsigned long long)ok, steps, (unsigned long long)checksum, fl / steps, cl / steps, ob / steps);
     wfa::RecycleAligner(algn);
     return 0;
 }

@@ -18,6 +18,7 @@
 #define WFA_HOST_WFA_HPP
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -269,42 +270,63 @@ private:
         bool reserve(size_t n) { if (n <= cap) return true; if (p) wfacuda_host_free(p); cap = n + n / 4 + 64; p = (T *)wfacuda_host_alloc(cap * sizeof(T)); if (!p) cap = 0; return p != nullptr; }
         void release() { if (p) wfacuda_host_free(p); p = nullptr; cap = 0; }
     };
-    Pinned<uint8_t> pool_; Pinned<uint64_t> qo_, to_, off_, ops_; Pinned<uint32_t> ql_, tl_; Pinned<wfacuda_result> res_;
+    Pinned<uint64_t> qo_, to_, off_, ops_; Pinned<uint32_t> ql_, tl_; Pinned<wfacuda_result> res_;
     std::vector<AlignmentResult> objs_;
-    void release_buffers() { pool_.release(); qo_.release(); to_.release(); off_.release(); ops_.release(); ql_.release(); tl_.release(); res_.release(); }
+    void release_buffers() { qo_.release(); to_.release(); off_.release(); ops_.release(); ql_.release(); tl_.release(); res_.release(); }
 
-    template <class F> static void parallel(size_t n, F f)
+    /* f(chunk) for chunk in [c0, c1) on up to 16 host threads */
+    template <class F> static void parallel_chunks(size_t c0, size_t c1, size_t threads, F f)
     {
-        const size_t T = n < 65536 ? 1 : std::max<size_t>(1, std::min<size_t>(16, std::thread::hardware_concurrency() / 2));
         std::vector<std::thread> th;
-        for (size_t k = 1; k < T; k++) th.emplace_back(f, k, n * k / T, n * (k + 1) / T);
-        f((size_t)0, (size_t)0, n / T);
+        const size_t T = std::max<size_t>(1, std::min(threads, c1 - c0));
+        for (size_t k = 1; k < T; k++) th.emplace_back([=] { for (size_t c = c0 + k; c < c1; c += T) f(c); });
+        for (size_t c = c0; c < c1; c += T) f(c);
         for (auto &t : th) t.join();
     }
+
+public:
+    double last_flatten_ms = 0, last_call_ms = 0, last_objects_ms = 0;      /* where the last AlignBatch spent its time */
+private:
+    static double now_ms_() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
     Error align_batch_on(wfacuda_ctx *const *ctxs, int n_ctx, const std::vector<std::string> &qs, const std::vector<std::string> &ts,
                          std::vector<AlignmentResult *> *results, std::vector<Error> *errors)
     {
         const size_t n = qs.size();
         if (ts.size() != n) { err_ = "AlignBatch: qs and ts differ in length"; return err_.c_str(); }
-        /* flatten: per-thread byte counts, then every thread copies its range of pairs */
-        size_t part[17] = {0};
-        parallel(n, [&](size_t k, size_t a, size_t b) { size_t s = 0; for (size_t i = a; i < b; i++) s += qs[i].size() + ts[i].size(); part[k + 1] = s; });
-        for (int k = 1; k < 17; k++) part[k] += part[k - 1];
-        const size_t total = part[16];
-        if (!pool_.reserve(total + 64) || !qo_.reserve(n) || !to_.reserve(n) || !ql_.reserve(n) || !tl_.reserve(n) || !res_.reserve(n) || !off_.reserve(n) ||
-            !ops_.reserve(std::max<size_t>(ops_.cap, total / 4 + 16 * n + 64))) { err_ = wfacuda_last_error(nullptr); return err_.c_str(); }
-        parallel(n, [&](size_t k, size_t a, size_t b) {
-            size_t at = part[k];
-            for (size_t i = a; i < b; i++) {
-                qo_.p[i] = at; ql_.p[i] = (uint32_t)qs[i].size(); memcpy(pool_.p + at, qs[i].data(), qs[i].size()); at += qs[i].size();
-                to_.p[i] = at; tl_.p[i] = (uint32_t)ts[i].size(); memcpy(pool_.p + at, ts[i].data(), ts[i].size()); at += ts[i].size();
+        /* The per-pair byte strings are scattered over the heap.  They are NOT copied together here:
+         * the C ABI takes offsets into one address range, so the range is the heap span of the
+         * strings and the offsets are their addresses relative to the lowest one; the library's
+         * pipeline workers gather every chunk's sequences into their page-locked pools themselves
+         * (wfacuda.h: scattered pools), overlapped with the copies and kernels of the other chunks. */
+        const double t_begin = now_ms_();
+        const size_t T = n < 65536 ? 1 : std::max<size_t>(1, std::min<size_t>(16, std::thread::hardware_concurrency())), C = T * 2;
+        if (!qo_.reserve(n) || !to_.reserve(n) || !ql_.reserve(n) || !tl_.reserve(n) || !res_.reserve(n) || !off_.reserve(n)) { err_ = wfacuda_last_error(nullptr); return err_.c_str(); }
+        std::vector<size_t> cut(C + 1), bytes(C, 0);
+        std::vector<uintptr_t> lowest(C, ~(uintptr_t)0);
+        for (size_t c = 0; c <= C; c++) cut[c] = n * c / C;
+        parallel_chunks(0, C, T, [&](size_t c) {
+            uintptr_t lo = ~(uintptr_t)0; size_t s_ = 0;
+            for (size_t i = cut[c]; i < cut[c + 1]; i++) {
+                lo = std::min(lo, std::min((uintptr_t)qs[i].data(), (uintptr_t)ts[i].data())); s_ += qs[i].size() + ts[i].size();
+            }
+            lowest[c] = lo; bytes[c] = s_;
+        });
+        uintptr_t base = ~(uintptr_t)0; size_t total = 0;
+        for (size_t c = 0; c < C; c++) { base = std::min(base, lowest[c]); total += bytes[c]; }
+        if (n == 0) base = 0;
+        if (!ops_.reserve(std::max<size_t>(ops_.cap, total / 4 + 16 * n + 64))) { err_ = wfacuda_last_error(nullptr); return err_.c_str(); }
+        parallel_chunks(0, C, T, [&](size_t c) {
+            for (size_t i = cut[c]; i < cut[c + 1]; i++) {
+                qo_.p[i] = (uintptr_t)qs[i].data() - base; ql_.p[i] = (uint32_t)qs[i].size();
+                to_.p[i] = (uintptr_t)ts[i].data() - base; tl_.p[i] = (uint32_t)ts[i].size();
             }
         });
-        memset(pool_.p + total, 0, 16);
+        last_flatten_ms = now_ms_() - t_begin;
+        const double c0 = now_ms_();
         auto call = [&]() {
-            return n_ctx == 1 ? wfacuda_align_batch(ctxs[0], n, pool_.p, qo_.p, ql_.p, to_.p, tl_.p, res_.p, ops_.p, ops_.cap, off_.p)
-                              : wfacuda_align_batch_multi(ctxs, n_ctx, n, pool_.p, qo_.p, ql_.p, to_.p, tl_.p, res_.p, ops_.p, ops_.cap, off_.p);
+            return n_ctx == 1 ? wfacuda_align_batch(ctxs[0], n, (const uint8_t *)base, qo_.p, ql_.p, to_.p, tl_.p, res_.p, ops_.p, ops_.cap, off_.p)
+                              : wfacuda_align_batch_multi(ctxs, n_ctx, n, (const uint8_t *)base, qo_.p, ql_.p, to_.p, tl_.p, res_.p, ops_.p, ops_.cap, off_.p);
         };
         int rc = call();
         if (rc == WFACUDA_E_OPS_CAPACITY) {
@@ -312,12 +334,15 @@ private:
             rc = call();
         }
         if (rc != 0) { err_ = wfacuda_last_error(ctxs[0]); return err_.c_str(); }
+        last_call_ms = now_ms_() - c0;
         /* result objects from the pool; Ops alias the output buffer (no per-pair allocation) */
+        const double o0 = now_ms_();
         if (objs_.size() < n) objs_.resize(n);
-        results->assign(n, nullptr); errors->assign(n, nullptr);
-        parallel(n, [&](size_t, size_t a, size_t b) {
-            for (size_t i = a; i < b; i++) {
+        results->resize(n); errors->resize(n);
+        parallel_chunks(0, C, T, [&](size_t c) {
+            for (size_t i = cut[c]; i < cut[c + 1]; i++) {
                 const wfacuda_result &w = res_.p[i];
+                (*results)[i] = nullptr; (*errors)[i] = nullptr;
                 switch (w.status) {
                 case WFACUDA_OK: {
                     AlignmentResult *r = &objs_[i];
@@ -333,6 +358,7 @@ private:
                 }
             }
         });
+        last_objects_ms = now_ms_() - o0;
         return nullptr;
     }
 
