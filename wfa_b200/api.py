@@ -492,7 +492,7 @@ class Aligner:
                      max(grow(bufs[2] if bufs else None, cap), 1))
             self._bufs = bufs = None
             # large result arrays live in page-locked memory: D2H lands in them directly
-            big = self._pinned_out and sizes[0] * RESULT_DTYPE.itemsize >= (1 << 20)
+            big = self._pinned_out and (sizes[0] * RESULT_DTYPE.itemsize >= (1 << 20) or sizes[2] * 8 >= (1 << 20))
             mk = (lambda k, dt: pinned_empty(k, dt)) if big else (lambda k, dt: np.zeros(k, dt))
             bufs = (mk(sizes[0], RESULT_DTYPE), mk(sizes[1], np.uint64), mk(sizes[2], np.uint64))
             if big:

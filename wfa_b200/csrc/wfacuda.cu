@@ -197,6 +197,7 @@ struct wfacuda_ctx {
      * many other workers (several ranks on one box) waits on an event created with
      * cudaEventBlockingSync instead and sleeps. */
     bool blocking_sync = false; cudaEvent_t ev_block = nullptr;
+    unsigned core_share = 0;           /* host cores this ctx's pipeline may count on (0: all of them) */
     /* the counters as last fetched from the device, valid while nothing was launched since (saves
      * the second read-back + wait at the end of a run whose last class already fetched them) */
     Counters hc_cache{}; bool hc_cache_valid = false;
@@ -1785,10 +1786,12 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     if (const char *e = getenv("WFACUDA_TAIL_LEVELS")) tail_levels = std::max(0, std::min(5, atoi(e)));
     const std::vector<uint64_t> cuts = plan_chunks(n_pairs, chunk_pairs, getenv("WFACUDA_UNIFORM_CHUNKS") ? -1 : tail_levels);
     const uint64_t n_chunks = cuts.size() - 1;
-    const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+    const unsigned hw = ctx->core_share ? ctx->core_share : std::max(2u, std::thread::hardware_concurrency());
     /* one worker per chunk in flight: enough of them that uploads (PCIe-bound, taken in turns)
      * never wait for a worker that is still computing or downloading */
-    unsigned kmax = std::min<unsigned>(16, std::max(2u, hw - 2));     /* (pageable memory is staged by the workers: host copies, one core each) */
+    /* (pageable memory is staged by the workers: host copies, one core each; with few cores per device
+     * still enough workers to overlap copies and kernels -- they then sleep in their waits, see below) */
+    unsigned kmax = std::min<unsigned>(16, std::max(6u, hw - 2));
     if (const char *e = getenv("WFACUDA_PIPE_WORKERS")) kmax = std::max(1, atoi(e));
     const int K = (int)std::min<uint64_t>(kmax, n_chunks);
     if ((int)ctx->subs.size() < K && ctx->arena.p) {
@@ -1822,7 +1825,7 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     {
         /* more workers than this process can expect cores for: sleep in the waits instead of spinning
          * (WFACUDA_BLOCKING_SYNC=0/1 decides otherwise; a launcher that runs several ranks per box sets it) */
-        bool blocking = (unsigned)K > hw;
+        bool blocking = (unsigned)K + 1 > hw;
         if (const char *e = getenv("WFACUDA_BLOCKING_SYNC")) blocking = atoi(e) != 0;
         for (wfacuda_ctx *sub : ctx->subs) sub->blocking_sync = blocking;
     }
@@ -1998,11 +2001,49 @@ int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pa
     if (n_ctx == 1) return wfacuda_align_batch(ctxs[0], n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
     if (n_pairs && (!seq_bytes || !q_off || !q_len || !t_off || !t_len || !results)) return fail(ctxs[0], WFACUDA_E_INVALID, "NULL input array");
     const wfacuda_config &cfg = ctxs[0]->cfg;
-    std::vector<uint32_t> shard_of(n_pairs);
-    wfacuda_shard_assign(n_ctx, n_pairs, q_len, t_len, cfg.adaptive, cfg.global_alignment, shard_of.data(), nullptr);
     std::vector<std::vector<uint32_t>> idx(n_ctx);
-    std::vector<uint64_t> bases(n_ctx, 0);
-    for (uint64_t i = 0; i < n_pairs; i++) { idx[shard_of[i]].push_back((uint32_t)i); bases[shard_of[i]] += (uint64_t)q_len[i] + t_len[i] + 16; }
+    std::vector<uint64_t> bases(n_ctx, 0), range_a(n_ctx, 0), range_n(n_ctx, 0);
+    /* Reads of one length class (the usual batch): the LPT of wfacuda_shard_assign is n_ctx equal,
+     * contiguous index ranges -- found with one cheap pass over the lengths (a few host threads),
+     * no per-pair shard table, no index lists. */
+    bool one_bin = n_pairs > 0;
+    {
+        const unsigned T = n_pairs < 200000 ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+        std::vector<int> lo_bin(T, 1 << 30), hi_bin(T, -1);
+        std::vector<uint64_t> sum(T * (size_t)n_ctx, 0);
+        auto scan = [&](unsigned k) {
+            for (int d = 0; d < n_ctx; d++) {
+                /* thread k scans its part of every shard's range, so that the per-shard byte sums fall out too */
+                const uint64_t a = n_pairs * d / n_ctx & ~31ull, e = d + 1 == n_ctx ? n_pairs : (n_pairs * (d + 1) / n_ctx & ~31ull);
+                uint64_t s_ = 0; int lo = lo_bin[k], hi = hi_bin[k];
+                for (uint64_t i = a + (e - a) * k / T; i < a + (e - a) * (k + 1) / T; i++) {
+                    const uint64_t nm = (uint64_t)q_len[i] + t_len[i];
+                    const int lg = 63 - __builtin_clzll(nm | 1), b = 2 * lg + (int)((nm >> (lg > 0 ? lg - 1 : 0)) & 1);
+                    lo = std::min(lo, b); hi = std::max(hi, b); s_ += nm + 16;
+                }
+                lo_bin[k] = lo; hi_bin[k] = hi; sum[k * (size_t)n_ctx + d] = s_;
+            }
+        };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < T; k++) th.emplace_back(scan, k);
+        scan(0);
+        for (auto &t : th) t.join();
+        for (unsigned k = 0; k < T; k++) if (lo_bin[k] != lo_bin[0] || hi_bin[k] != hi_bin[0] || lo_bin[k] != hi_bin[k]) one_bin = false;
+        if (one_bin) for (int d = 0; d < n_ctx; d++) {
+            range_a[d] = n_pairs * d / n_ctx & ~31ull;
+            range_n[d] = (d + 1 == n_ctx ? n_pairs : (n_pairs * (d + 1) / n_ctx & ~31ull)) - range_a[d];
+            for (unsigned k = 0; k < T; k++) bases[d] += sum[k * (size_t)n_ctx + d];
+        }
+    }
+    if (!one_bin) {
+        std::vector<uint32_t> shard_of(n_pairs);
+        wfacuda_shard_assign(n_ctx, n_pairs, q_len, t_len, cfg.adaptive, cfg.global_alignment, shard_of.data(), nullptr);
+        for (uint64_t i = 0; i < n_pairs; i++) { idx[shard_of[i]].push_back((uint32_t)i); bases[shard_of[i]] += (uint64_t)q_len[i] + t_len[i] + 16; }
+        for (int d = 0; d < n_ctx; d++) {
+            range_n[d] = idx[d].size();
+            if (range_n[d] && (uint64_t)idx[d].back() - idx[d].front() + 1 == range_n[d]) { range_a[d] = idx[d].front(); idx[d].clear(); }   /* one run: no gather needed */
+        }
+    }
     uint64_t bases_total = 0;
     for (uint64_t v : bases) bases_total += v;
     /* ops regions: proportional to the shards' bases */
@@ -2017,13 +2058,15 @@ int wfacuda_align_batch_multi(wfacuda_ctx *const *ctxs, int n_ctx, uint64_t n_pa
     std::vector<std::thread> th;
     auto work = [&](int d) {
         const std::vector<uint32_t> &ix = idx[d];
-        const uint64_t cnt = ix.size();
+        const uint64_t cnt = range_n[d];
         if (!cnt) { ctxs[d]->stats = wfacuda_stats{}; return; }
         uint64_t *ops_d = ops ? ops + obase[d] : nullptr;
         const uint64_t cap_d = ops ? obase[d + 1] - obase[d] : 0;
-        const bool contiguous = (uint64_t)ix.back() - ix.front() + 1 == cnt;
-        if (contiguous) {
-            const uint64_t a = ix.front();
+        /* the devices of one process share its cores: each pipeline gets its share of them */
+        ctxs[d]->core_share = std::max(2u, std::thread::hardware_concurrency() / (unsigned)n_ctx);
+        struct Share { wfacuda_ctx *c; ~Share() { c->core_share = 0; } } share{ctxs[d]};
+        if (ix.empty()) {
+            const uint64_t a = range_a[d];
             rcs[d] = wfacuda_align_batch(ctxs[d], cnt, seq_bytes, q_off + a, q_len + a, t_off + a, t_len + a, results + a, ops_d, cap_d, ops_off ? ops_off + a : nullptr);
             if (rcs[d] == 0 && ops_off) for (uint64_t j = 0; j < cnt; j++) ops_off[a + j] += obase[d];
         } else {
