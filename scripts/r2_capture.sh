@@ -1,0 +1,19 @@
+#!/bin/bash
+# Final captures of the round: launch lists + traffic / instruction counters of the headline kernels (cheap metric set,
+# every launch of one short bench run), and one `--set full` report per SLIM workload.
+cd "$(dirname "$0")/.."
+TAG=${1:-c1}; OUT=gpurun_out/$TAG; mkdir -p $OUT
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__thread_inst_executed_per_inst_executed.ratio
+run() { # name workload pairs
+  WFACUDA_NO_PIPELINE=1 timeout 900 ncu --metrics $M --clock-control none --csv --log-file $OUT/launches_$1.csv python bench.py --workload $2 --pairs $3 --steps 1 --warmup 3 --only-headline --no-cpu-baseline > $OUT/ncu_$1.log 2>&1
+}
+run cfg2 cfg2_150bp_e5_global 1000000
+run cfg3 cfg3_1kbp_e10_global_adaptive 1000000
+run cfg5 cfg5_100kbp_e15_global_adaptive 1250
+run cfg5full cfg5_100kbp_e15_global_adaptive 10000
+run cfg4 cfg4_10kbp_in_12kbp_e5_semiglobal 296
+if [ "$2" == "full" ]; then
+WFACUDA_NO_PIPELINE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:slim_kernel -s 3 -c 1 -f -o $OUT/prof_cfg3 python bench.py --workload cfg3_1kbp_e10_global_adaptive --pairs 100000 --steps 1 --warmup 3 --only-headline --no-cpu-baseline > $OUT/ncu_full_cfg3.log 2>&1
+WFACUDA_NO_PIPELINE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:slim_kernel -s 3 -c 1 -f -o $OUT/prof_cfg5 python bench.py --workload cfg5_100kbp_e15_global_adaptive --pairs 1250 --steps 1 --warmup 3 --only-headline --no-cpu-baseline > $OUT/ncu_full_cfg5.log 2>&1
+fi
+ls -la $OUT

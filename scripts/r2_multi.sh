@@ -6,7 +6,8 @@ nvidia-smi --query-gpu=index,name --format=csv > $OUT/gpu.txt 2>&1; nproc >> $OU
 timeout 300 python scripts/pcie_ceiling.py > $OUT/pcie_ceiling.jsonl 2> $OUT/pcie.err; cat $OUT/pcie_ceiling.jsonl
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "multi" > $OUT/pytest_multi.log 2>&1; tail -3 $OUT/pytest_multi.log
 for n in $3; do
-( time timeout 1700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n --steps 5 --warmup 3 $4 > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err ) 2>&1 | grep real
+EXTRA=""; if [ "$n" != "$N" ]; then EXTRA="--only-headline --no-cpu-baseline"; fi
+( time timeout 1700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n --steps 5 --warmup 3 $EXTRA > $OUT/bench_n$n.json 2> $OUT/bench_n$n.err ) 2>&1 | grep real
 python - <<PY
 import json
 try:
