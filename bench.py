@@ -228,7 +228,7 @@ def report(workload, m, steps, world, sm_count, clocks, int32_peaks):
     achieved = B / k_sec / 1e9
     int_ops = 50 * stats["cells"]                            # O = 32 C + 10 V + 8 W with V, W ~ C
     kname = max((stats["pairs_lane"], "lane_kernel"), (stats["pairs_warp"], "align_kernel<warp>"), (stats["pairs_cta"], "align_kernel<cta>"),
-                (stats.get("pairs_slim", 0), "slim_kernel"))[1]
+                (stats.get("pairs_slim", 0), "slim_kernel"), (stats.get("pairs_wide", 0), "wide_kernel"))[1]
     cap, why = ncu_capture(workload, m["n_pairs"])
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     issue_peak = sm_count * 4 * 32 * sm_mhz * 1e6
@@ -262,7 +262,7 @@ def report(workload, m, steps, world, sm_count, clocks, int32_peaks):
                            "executed_warp_instructions": cap["warp_instructions"] if cap else None,
                            "executed_frac": (cap["warp_instructions"] * 32 / k_sec) / issue_peak if cap else None},
         "device_ms_per_step": m["ms_dev"] / steps,
-        "work": {k: int(stats.get(k, 0)) for k in ("cells", "cells_written", "score_steps", "ops", "retries", "pairs_lane", "pairs_slim", "pairs_warp", "pairs_cta")},
+        "work": {k: int(stats.get(k, 0)) for k in ("cells", "cells_written", "score_steps", "ops", "retries", "pairs_lane", "pairs_slim", "pairs_wide", "pairs_warp", "pairs_cta")},
     }
 
 

@@ -74,6 +74,8 @@ typedef struct wfacuda_config {
 #define WFACUDA_FLAG_NO_LANE            8u
 /* Keep pairs off the SLIM kernel (one warp per pair, offsets-only cells); testing / comparison. */
 #define WFACUDA_FLAG_NO_SLIM            16u
+/* Keep pairs off the WIDE kernel (one thread-block cluster per pair, live rows in shared memory); testing / comparison. */
+#define WFACUDA_FLAG_NO_WIDE            32u
 
 /* AlignmentResult (wfa_cigar.go:29-46) after process() (wfa_cigar.go:136-214).
  * tend/qend are 0 when the alignment has no match run (the reference leaves
@@ -105,6 +107,7 @@ typedef struct wfacuda_stats {
     float    ms_pack, ms_align, ms_total_device;   /* CUDA-event times on the ctx stream */
     uint32_t pairs_lane;         /* pairs aligned by the LANE kernel (not counted in pairs_warp) */
     uint32_t pairs_slim;         /* pairs aligned by the SLIM kernel (not counted in pairs_warp) */
+    uint32_t pairs_wide;         /* pairs aligned by the WIDE kernel (not counted in pairs_cta) */
 } wfacuda_stats;
 
 typedef struct wfacuda_ctx   wfacuda_ctx;

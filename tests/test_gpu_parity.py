@@ -178,6 +178,8 @@ def test_synthetic_configs(built_lib, name, count):
         assert stats["cells"] == ref[3]["cells"], (stats, ref[3])
     if c["adaptive"]:
         assert stats["pairs_slim"] > 0.9 * count, stats           # configs 3 and 5 run on the SLIM worker
+    if not c["global_alignment"]:
+        assert stats["pairs_wide"] == count, stats                # config 4 runs on the WIDE worker (2-CTA clusters)
 
 
 def test_config5_shard_shape(built_lib):
@@ -242,6 +244,47 @@ def test_slim_worker_boundaries(built_lib):
     finally:
         os.environ.pop("WFACUDA_SLIM_P", None)
     parity.check(batch, what="slim boundaries, SLIM off", adaptive=(10, 50), gpu_kw=dict(flags=api.FLAG_NO_SLIM))
+
+
+def test_wide_worker(built_lib):
+    """WIDE worker (wfa_wide.cuh): one thread-block cluster per pair, the live rows as 16-bit offsets in
+    the (distributed) shared memory of the cluster, halo cells pushed to the neighbouring CTA, the row's
+    reductions through per-CTA mailboxes and one cluster barrier per score; backtraces in their own kernel.
+    Cluster sizes 1 .. 8 forced on small pairs (segments of 64 diagonals upwards, so that rows cross CTA
+    boundaries and halos matter), global and semi-global, every penalty set of the default shape; pairs with
+    a non-ACGT byte (8-bit hand-over to the CTA worker); and the worker switched off (CTA worker) as a control."""
+    rng = random.Random(53)
+    rnd = lambda n, al=b"ACGT": bytes(rng.choice(al) for _ in range(n))
+    pairs = _random_pairs(51, 120, maxlen=300)
+    for L in (63, 64, 65, 127, 128, 129, 255, 256, 257, 500, 700):
+        q = rnd(L)
+        pairs += [(q, q), (q, _mutate(rng, q, 0.05, b"ACGT")), (q, _mutate(rng, q, 0.25, b"ACGT")), (q[:L - 3], q), (q, q[5:]),
+                  (rnd(L // 2 + 1) + q, q), (q, rnd(L // 3 + 1) + _mutate(rng, q, 0.1, b"ACGT") + rnd(L // 3 + 1)), (q, rnd(L))]
+    for _ in range(6):
+        q = rnd(200)
+        t = bytearray(q); t[rng.randrange(200)] = ord("N")
+        pairs.append((q, bytes(t)))
+    pairs += [(b"A", b"A"), (b"A", b"C"), (b"AC", b"A"), (b"A", b"ACGTACGT"), (b"ACGTACGTAC", b"A")]
+    rng.shuffle(pairs)
+    batch = datagen.Batch.from_pairs(pairs)
+    try:
+        for cl in ("1", "2", "4", "8", None):
+            if cl is None:
+                os.environ.pop("WFACUDA_WIDE_CLUSTER", None)
+            else:
+                os.environ["WFACUDA_WIDE_CLUSTER"] = cl
+            for glob in (True, False):
+                for pen in ((4, 6, 2), (2, 3, 1), (8, 12, 4)):
+                    gpu, ref, stats = parity.check(batch, what="wide cluster=%s glob=%s pen=%s" % (cl, glob, pen), global_alignment=glob,
+                                                   mismatch=pen[0], gap_open=pen[1], gap_ext=pen[2], gpu_kw=dict(flags=api.FLAG_FORCE_CTA))
+                    assert stats["pairs_wide"] > 0.9 * len(batch) and stats["pairs_8bit"] > 0, stats
+                    if glob:
+                        assert stats["cells"] == ref[3]["cells"], (cl, pen, stats, ref[3])
+    finally:
+        os.environ.pop("WFACUDA_WIDE_CLUSTER", None)
+    for glob in (True, False):
+        gpu, ref, stats = parity.check(batch, what="wide off glob=%s" % glob, global_alignment=glob, gpu_kw=dict(flags=api.FLAG_FORCE_CTA | api.FLAG_NO_WIDE))
+        assert stats["pairs_wide"] == 0 and stats["pairs_cta"] > 0, stats
 
 
 def test_seqs_txt_config1(built_lib):

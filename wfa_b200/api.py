@@ -70,6 +70,7 @@ FLAG_FORCE_CTA = 2
 FLAG_FORCE_8BIT = 4
 FLAG_NO_LANE = 8
 FLAG_NO_SLIM = 16
+FLAG_NO_WIDE = 32
 
 
 class _Config(C.Structure):
@@ -86,7 +87,7 @@ class Stats(C.Structure):
                 ("kernel_launches", C.c_uint32), ("align_launches", C.c_uint32), ("retries", C.c_uint32),
                 ("pairs_warp", C.c_uint32), ("pairs_cta", C.c_uint32), ("pairs_8bit", C.c_uint32),
                 ("ms_pack", C.c_float), ("ms_align", C.c_float), ("ms_total_device", C.c_float),
-                ("pairs_lane", C.c_uint32), ("pairs_slim", C.c_uint32)]
+                ("pairs_lane", C.c_uint32), ("pairs_slim", C.c_uint32), ("pairs_wide", C.c_uint32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

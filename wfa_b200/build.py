@@ -16,7 +16,7 @@ def _stale(target, sources):
 
 
 def build_cuda(force=False, verbose=False):
-    src = [os.path.join(CSRC, f) for f in ("wfacuda.cu", "wfa_kernels.cuh", "wfa_lane.cuh", "wfa_slim.cuh", "wfa_render.cuh")] + \
+    src = [os.path.join(CSRC, f) for f in ("wfacuda.cu", "wfa_kernels.cuh", "wfa_lane.cuh", "wfa_slim.cuh", "wfa_wide.cuh", "wfa_render.cuh")] + \
           [os.path.join(os.path.dirname(HERE), "include", "wfacuda.h")]
     if force or _stale(LIB, src):
         cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, src[0]]

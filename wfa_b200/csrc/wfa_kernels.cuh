@@ -128,6 +128,10 @@ struct KParams {
     int32_t  min_wf_len, max_dist_diff;
     LaneGeom lg;               /* LANE kernels only */
     LaneAux  la;
+    /* WIDE kernels only (wfa_wide.cuh): diagonals per CTA of the cluster, 8-byte entries of shared memory for
+     * the two sequence windows, where the forward pass leaves item i's outcome for the finish kernel */
+    int32_t  wide_seg; uint32_t wide_seq_cap;
+    struct FwdOut *wide_rec;
 };
 
 /* ------------------------------------------------------------------ sequences

@@ -434,7 +434,7 @@ template <int SZ> struct SlimView {
         uint32_t code;
         if (comp == 1) code = T_INS_OPEN + ((c.code >> 3) & 1u);
         else if (comp == 2) code = T_DEL_OPEN + ((c.code >> 4) & 1u);
-        else code = c.M ? (c.code & 7u) : (first_eq ? T_MATCH : T_MISMATCH);
+        else code = c.M ? (c.code & 7u) : (si == 0 ? T_MATCH : T_MISMATCH);      /* init cell: M[0] holds the matching start cells, M[x] the others (wfa.go:155-183) */
         return o << T_BITS | code;
     }
 };

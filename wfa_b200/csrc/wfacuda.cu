@@ -16,6 +16,7 @@
 #include "wfa_kernels.cuh"
 #include "wfa_lane.cuh"
 #include "wfa_slim.cuh"
+#include "wfa_wide.cuh"
 #include "wfa_render.cuh"
 
 #include <algorithm>
@@ -148,6 +149,8 @@ struct wfacuda_ctx {
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     double arena_scale = 1.0;      /* learned: observed / estimated arena need */
     double arena_scale_slim = 1.0;  /* the same for the REG worker's slots */
+    double arena_scale_wide = 1.0;  /* the same for the WIDE worker's slots */
+    DevBuf wide_rec;                /* WIDE class: FwdOut of every item of a launch, read by its finish kernel */
     int slim_p_learned = 0;         /* learned: cells per lane (row capacity / 32) the REG worker needed */
     int slim_occ[3][2][9] = {};    /* [size class][adaptive][MAXP]: resident blocks per SM, 0 = unknown */
     /* LANE class: sampled histogram of the score index at which the previous batch's pairs
@@ -699,6 +702,161 @@ int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &o
 }
 
 
+/* ---- WIDE class: one thread-block cluster per pair, live rows in (distributed) shared memory (wfa_wide.cuh) ---- */
+
+bool wide_class_enabled(const wfacuda_ctx *ctx)
+{
+    const wfacuda_config &c = ctx->cfg;
+    if (c.adaptive || ctx->dump_mode) return false;
+    if (c.flags & (WFACUDA_FLAG_FORCE_8BIT | WFACUDA_FLAG_SEMIGLOBAL_LITERAL | WFACUDA_FLAG_NO_WIDE)) return false;
+    if (getenv("WFACUDA_NO_WIDE")) return false;
+    return ctx->xg == SLIM_XG && ctx->oeg == SLIM_OEG && ctx->eg == SLIM_EG;
+}
+
+/* Pairs of `order0` through the WIDE worker: forward launch (clusters) + finish launch (backtraces) per
+ * sub-batch of as many pairs as the arena holds slots.  Pairs it cannot take (too wide for eight CTAs'
+ * shared memory, target beyond 16-bit offsets) go to *to_cta, pairs with a non-ACGT byte to *to_8bit. */
+int run_wide_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &order0, KParams base,
+                   std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit)
+{
+    if (order0.empty()) return 0;
+    const bool semi = !ctx->cfg.global_alignment;
+    const void *kfn = semi ? (const void *)wide_kernel<true> : (const void *)wide_kernel<false>;
+    double boost = 1.0;
+    std::vector<uint32_t> requeued;
+    for (int attempt = 0; ; attempt++) {
+        const std::vector<uint32_t> &order = attempt == 0 ? order0 : requeued;
+        if (order.empty()) break;
+        if (attempt > 24) return fail(ctx, WFACUDA_E_NOMEM, "pairs still out of resources after %d retries", attempt);
+        /* geometry of the launch: widest pair decides cluster size and segment, the longest sequences the windows */
+        uint64_t wmax = 1, need_max = 0; uint32_t seq_ent = 4;
+        std::vector<uint32_t> fit, too_wide;
+        const uint32_t head = (uint32_t)WIDE_HEAD_BYTES + 64;
+        for (uint32_t pr : order) {
+            const uint32_t dn = b->n_of(pr), dm = b->m_of(pr);
+            const uint64_t w = (uint64_t)dn + dm - 1;
+            const uint32_t ent = ((dn + 15) >> 4) + ((dm + 15) >> 4) + 2;
+            /* fits eight CTAs?  (9 rows of 16-bit offsets + the windows, per CTA) */
+            const uint64_t seg8 = ((w + 7) / 8 + 63) & ~63ull;
+            if (dm > WIDE_MAX_M || wide_smem_bytes((uint32_t)seg8, ent) + head > ctx->smem_optin) { too_wide.push_back(pr); continue; }
+            fit.push_back(pr);
+            wmax = std::max(wmax, w); seq_ent = std::max(seq_ent, ent);
+            need_max = std::max(need_max, estimate(ctx, dn, dm).arena);
+        }
+        if (to_cta) to_cta->insert(to_cta->end(), too_wide.begin(), too_wide.end());
+        else if (!too_wide.empty()) return fail(ctx, WFACUDA_E_INVALID, "internal: WIDE class without a fallback");
+        if (fit.empty()) break;
+        int C = 1; uint32_t seg = 0;
+        for (;; C *= 2) {
+            seg = (uint32_t)(((wmax + C - 1) / C + 63) & ~63ull);
+            if (wide_smem_bytes(seg, seq_ent) + head <= ctx->smem_optin || C == WIDE_MAX_CLUSTER) break;
+        }
+        if (const char *e = getenv("WFACUDA_WIDE_CLUSTER")) {         /* testing: small pairs over several CTAs */
+            C = std::max(1, std::min(WIDE_MAX_CLUSTER, atoi(e)));
+            seg = (uint32_t)(((wmax + C - 1) / C + 63) & ~63ull);
+        }
+        const size_t smem = wide_smem_bytes(seg, seq_ent);
+        int threads = (int)std::min<uint32_t>(1024, std::max<uint32_t>(128, ((seg / 2 + 31) / 32) * 32));
+        if (const char *e = getenv("WFACUDA_WIDE_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+        /* slots: 8-byte cells instead of the estimate's 12, one slot per pair of a sub-batch */
+        uint64_t slot = (uint64_t)((double)need_max * (8.0 / 12.0) * ctx->arena_scale_wide / std::max(ctx->arena_scale, 1e-9) * boost);
+        slot = (std::max<uint64_t>(slot, 65536) + 255) & ~255ull;
+        const uint64_t budget = arena_budget(ctx, ctx->arena.cap == 0 || boost > 1.0);
+        bool slot_at_max = false;
+        if (slot > budget) { slot = budget & ~255ull; slot_at_max = true; }
+        const uint64_t kWideSlotMax = 30ull << 30;                   /* 32-bit cell indices */
+        if (slot > kWideSlotMax) { slot = kWideSlotMax; slot_at_max = true; }
+        const size_t cap = (size_t)std::max<uint64_t>(1, std::min<uint64_t>(fit.size(), budget / slot));
+        int rc;
+        if ((rc = ensure(ctx, ctx->arena, slot * cap))) return rc;
+        if ((rc = ensure(ctx, ctx->work, fit.size() * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->retry, fit.size() * 8 + 16))) return rc;
+        if ((rc = ensure(ctx, ctx->wide_rec, cap * sizeof(FwdOut)))) return rc;
+        if ((rc = staged_h2d(ctx, ctx->work.p, fit.data(), fit.size() * 4))) return rc;
+        CU(ctx, cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t lc{};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.blockDim = dim3((unsigned)threads); lc.dynamicSmemBytes = smem; lc.stream = ctx->stream; lc.attrs = at; lc.numAttrs = 1;
+        lc.gridDim = dim3((unsigned)C);
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &lc) != cudaSuccess || max_clusters < 1) {
+            cudaGetLastError();
+            return fail(ctx, WFACUDA_E_CUDA, "WIDE kernel: a cluster of %d CTAs x %d threads with %zu bytes of shared memory cannot be resident", C, threads, smem);
+        }
+        std::vector<uint32_t> again;
+        bool ops_full = false, arena_full = false;
+        uint64_t used_max = 0;
+        Counters *dc = (Counters *)ctx->ctr.p;
+        for (size_t i0 = 0; i0 < fit.size(); i0 += cap) {
+            const size_t cnt = std::min(cap, fit.size() - i0);
+            CU(ctx, dev_fill(&dc->retry_n, 0, (size_t)((char *)&dc->launch_end - (char *)&dc->retry_n), ctx->stream));
+            KParams P = base;
+            P.work = (const uint32_t *)ctx->work.p + i0; P.n_work = (uint32_t)cnt;
+            P.arena = (uint8_t *)ctx->arena.p; P.slot_bytes = slot; P.group = 1;
+            P.retry = (uint64_t *)ctx->retry.p; P.ctr = dc; P.retry_ctr = &dc->retry_n;
+            P.ops_pool = (uint64_t *)ctx->ops_pool.p; P.ops_cap = ctx->ops_pool.cap / 8;
+            P.wide_seg = (int32_t)seg; P.wide_seq_cap = seq_ent; P.wide_rec = (FwdOut *)ctx->wide_rec.p;
+            lc.gridDim = dim3((unsigned)(std::min<size_t>(cnt, (size_t)max_clusters) * C));
+            void *args[1] = {&P};
+            CU(ctx, cudaLaunchKernelExC(&lc, kfn, args));
+            wide_finish_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, ctx->stream>>>(P);
+            CU(ctx, cudaGetLastError());
+            ctx->stats.kernel_launches += 2; ctx->stats.align_launches += 2; ctx->hc_cache_valid = false;
+            ctx->stats.arena_bytes = std::max<uint64_t>(ctx->stats.arena_bytes, slot * cap);
+            Counters hc;
+            { int rc2 = fetch_small(ctx, &hc, dc, sizeof hc); if (rc2) return rc2; }
+            ctx->hc_cache = hc; ctx->hc_cache_valid = true;
+            used_max = std::max<uint64_t>(used_max, hc.arena_used_max);
+            if (getenv("WFACUDA_DEBUG")) fprintf(stderr, "[wfacuda]   launch wide attempt %d: %zu pairs (of %zu), %d clusters of %d x %d thr, seg %u, smem %zu, slot %.1f MB (scale %.3f), used max %.1f MB, retry %llu\n",
+                                                 attempt, cnt, fit.size(), (int)std::min<size_t>(cnt, (size_t)max_clusters), C, threads, seg, smem, slot / 1048576.0, ctx->arena_scale_wide, hc.arena_used_max / 1048576.0, (unsigned long long)hc.retry_n);
+            if (hc.retry_n) {
+                std::vector<uint64_t> rl(hc.retry_n);
+                { int rc2 = fetch_small(ctx, rl.data(), ctx->retry.p, hc.retry_n * 8); if (rc2) return rc2; }
+                for (uint64_t r : rl) {
+                    const uint32_t st = (uint32_t)(r >> 32), pair = (uint32_t)r;
+                    if (st == ST_RING) { if (to_cta) to_cta->push_back(pair); }
+                    else if (st == ST_NEED8) { if (to_8bit) to_8bit->push_back(pair); }
+                    else { again.push_back(pair); if (st == ST_OPS) ops_full = true; else arena_full = true; }
+                }
+                if (ops_full) {
+                    /* grow the completion-order pool before the next sub-batch; what successful pairs wrote stays valid */
+                    const uint64_t old_cap = ctx->ops_pool.cap / 8;
+                    const uint64_t new_cap = std::max<uint64_t>(2 * old_cap, 2 * hc.ops_cursor + (1u << 20));
+                    DevBuf nb;
+                    if ((rc = ensure(ctx, nb, new_cap * 8))) return rc;
+                    CU(ctx, cudaMemcpy(nb.p, ctx->ops_pool.p, std::min<uint64_t>(old_cap, hc.ops_cursor) * 8, cudaMemcpyDeviceToDevice));
+                    cudaFree(ctx->ops_pool.p);
+                    ctx->ops_pool = nb;
+                    ops_full = false;
+                }
+            }
+        }
+        ctx->stats.retries += (uint32_t)again.size();
+        if (again.empty()) {
+            if (boost == 1.0 && !slot_at_max && slot > 65536 && used_max) {
+                const double r = 1.5 * (double)used_max / (double)slot;
+                ctx->arena_scale_wide = std::min(64.0, std::max(1.0 / 64, ctx->arena_scale_wide * std::min(1.0, std::max(r, 0.25))));
+            }
+            break;
+        }
+        if (arena_full) {
+            if (slot_at_max && cap <= 1) {
+                /* one pair already owns the whole budget: cannot be aligned on this device */
+                for (uint32_t pair : again) {
+                    Result res; memset(&res, 0, sizeof res); res.status = ST_RESOURCES;
+                    CU(ctx, cudaMemcpy((Result *)b->d_results + pair, &res, sizeof res, cudaMemcpyHostToDevice));
+                }
+                again.clear();
+            } else boost *= 4.0;
+            ctx->arena_scale_wide = std::min(64.0, ctx->arena_scale_wide * 2.0);
+        }
+        requeued.swap(again);
+    }
+    return 0;
+}
+
+
 /* ---- LANE class: 32 short pairs per warp in lockstep (wfa_lane.cuh) ---------------------- */
 
 constexpr int kLaneW = 64;                       /* ring columns: diagonals -32..31 */
@@ -1123,7 +1281,7 @@ int wfacuda_set_config(wfacuda_ctx *ctx, const wfacuda_config *cfg)
     wfacuda_config old = ctx->cfg;
     int rc = apply_config(ctx, cfg);
     if (rc == 0 && memcmp(&old, cfg, sizeof old) != 0) {
-        ctx->arena_scale = 1.0; ctx->arena_scale_slim = 1.0; ctx->slim_p_learned = 0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = ctx->lane_occ[2] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
+        ctx->arena_scale = 1.0; ctx->arena_scale_slim = 1.0; ctx->arena_scale_wide = 1.0; ctx->slim_p_learned = 0; ctx->lane_hist_n = 0; ctx->lane_n_bounds = 0; ctx->lane_occ[0] = ctx->lane_occ[1] = ctx->lane_occ[2] = 0; ctx->lane_occ_sw = 0; ctx->ring_cap_learned = 0; memset(ctx->occ_cache, 0, sizeof ctx->occ_cache);
         for (wfacuda_ctx *c : ctx->subs) wfacuda_destroy(c);      /* re-created with the new config on demand */
         ctx->subs.clear();
     }
@@ -1458,8 +1616,17 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     if (!to_cta.empty()) { cta_extra = b->order_cta; cta_extra.insert(cta_extra.end(), to_cta.begin(), to_cta.end()); }
     const std::vector<uint32_t> &cta_order = to_cta.empty() ? b->order_cta : cta_extra;
     ctx->stats.pairs_warp = (uint32_t)(warp_order.size() + warp8.size() - to_cta.size() + ctx->lane_handed) - ctx->stats.pairs_slim;
-    ctx->stats.pairs_cta = (uint32_t)cta_order.size();
-    if ((rc = run_class(ctx, b, cta_order, b->identity_cls == 1 && to_cta.empty(), true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
+    /* WIDE worker first (no heuristic, penalties of the default shape: clusters with the live rows on chip);
+     * what it cannot hold goes on to the CTA worker */
+    std::vector<uint32_t> wide_left;
+    const bool use_wide = wide_class_enabled(ctx) && !cta_order.empty();
+    if (use_wide) {
+        if ((rc = run_wide_class(ctx, b, cta_order, P, &wide_left, &cta8))) return rc;
+        ctx->stats.pairs_wide = (uint32_t)(cta_order.size() - wide_left.size() - cta8.size());
+    }
+    const std::vector<uint32_t> &cta_rest = use_wide ? wide_left : cta_order;
+    ctx->stats.pairs_cta = (uint32_t)cta_rest.size();
+    if ((rc = run_class(ctx, b, cta_rest, !use_wide && b->identity_cls == 1 && to_cta.empty(), true, force8 ? 8 : 2, P, nullptr, &cta8))) return rc;
     if ((rc = run_class(ctx, b, cta8, false, true, 8, P, nullptr, nullptr))) return rc;
     ctx->stats.pairs_8bit = force8 ? (uint32_t)n_valid : (uint32_t)(warp8.size() + cta8.size());
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1751,7 +1918,7 @@ static void add_stats(wfacuda_stats &a, const wfacuda_stats &s)
     a.ops += s.ops; a.seq_bases += s.seq_bases; a.arena_bytes = std::max(a.arena_bytes, s.arena_bytes);
     a.h2d_bytes += s.h2d_bytes; a.d2h_bytes += s.d2h_bytes; a.kernel_launches += s.kernel_launches;
     a.align_launches += s.align_launches; a.retries += s.retries; a.pairs_warp += s.pairs_warp;
-    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.pairs_lane += s.pairs_lane; a.pairs_slim += s.pairs_slim; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
+    a.pairs_cta += s.pairs_cta; a.pairs_8bit += s.pairs_8bit; a.pairs_lane += s.pairs_lane; a.pairs_slim += s.pairs_slim; a.pairs_wide += s.pairs_wide; a.ms_pack += s.ms_pack; a.ms_align += s.ms_align;
     a.ms_total_device += s.ms_total_device;
 }
 
