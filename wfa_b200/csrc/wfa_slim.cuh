@@ -48,9 +48,10 @@ struct SlimHdr { int32_t alo, lo, hi; uint32_t off; };
 template <int SZ> struct SlimCell {
     static constexpr bool WIDE = SZ != 0;
     typedef typename std::conditional<WIDE, uint64_t, uint32_t>::type T;
-    static constexpr int BITS = WIDE ? 21 : 10;
+    static constexpr int BITS = SZ == 3 ? 16 : WIDE ? 21 : 10;            /* SZ 3: the WIDE worker's cells (16-bit offsets: M | I << 16 in one half, D in the other) */
     __device__ static __forceinline__ T pack(uint32_t M, uint32_t I, uint32_t D)
     {
+        if (SZ == 3) return (uint64_t)(M | I << 16) | (uint64_t)D << 32;
         if (WIDE) return (uint64_t)(M | I << 21) | (uint64_t)(I >> 11 | D << 10) << 32;
         return (T)(M | I << 10 | D << 20);
     }

@@ -46,7 +46,7 @@ constexpr int WIDE_MAX_CLUSTER = 8;
  * side keep the rows word aligned), the two sequence windows (8 bytes per 16 bases + 1 entry each) */
 __host__ __device__ inline size_t wide_smem_bytes(uint32_t seg, uint32_t seq_entries)
 {
-    return WIDE_HEAD_BYTES + 9 * (size_t)(seg + 4) * 2 + 8 + (size_t)seq_entries * 8;
+    return WIDE_HEAD_BYTES + 9 * (size_t)(seg + 4) * 2 + 8 + (size_t)seq_entries * 8;      /* (seg / 2 + 2) x (5 x 4 + 2 x 8) bytes of rings */
 }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -65,6 +65,12 @@ __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+/* The per-row barrier: only a handful of threads have written to other CTAs (halo cells, mailboxes); they
+ * fence their stores themselves (cluster_fence) and nobody else pays a release fence that would wait for
+ * the thread's arena stores to drain. */
+__device__ __forceinline__ void cluster_fence() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 /* a whole 2-bit sequence in shared memory: entry j holds words j and j + 1 */
@@ -80,19 +86,30 @@ struct SeqAll {
 
 /* Forward pass of one pair by the whole cluster: wfa.go:228-251 with next + extend fused per cell.
  * Every thread of every CTA keeps the same row bookkeeping in registers (the reductions are combined
- * identically everywhere).  Returns what the finish kernel needs (valid in all threads). */
+ * identically everywhere).  Returns what the finish kernel needs (valid in all threads).
+ *
+ * Rows and ranges.  Row si (score si * g) is computed over a range that depends on si alone: all
+ * n + m - 1 diagonals for semi-global alignment (the init cells span them, wfa.go:160-183), [-si, si]
+ * (clamped) for global alignment -- a superset of the reference's loop range (wfa.go:557-563: the hull
+ * of the source rows' ranges +- 1 grows by at most one diagonal per row), and a cell outside the
+ * reference's range has no source and comes out absent.  So the loop never waits for a reduction:
+ * what the reductions deliver (M WaveFront.Lo/Hi for the header and the work counter, the end test,
+ * the start-cell test) is consumed ONE ROW LATER, in the middle of the next row, which is what lets the
+ * cluster barrier of row si overlap the first cells of row si + 1.  The row computed past the final
+ * one is discarded (its arena cells lie beyond `top`, nobody reads them). */
 template <bool SEMI>
 __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t pair, const uint32_t sbase, uint8_t *slot, const uint64_t slot_bytes,
                                                const uint32_t rank, const uint32_t C)
 {
-    typedef SlimCell<1> SC;
-    typedef uint64_t CellT;
+    typedef uint64_t CellT;                                    /* SlimCell<3>: M | I << 16 | D << 32 */
     constexpr uint32_t HDR_CELLS = sizeof(SlimHdr) / sizeof(CellT);
     const uint32_t tid = threadIdx.x, T = blockDim.x, lane = tid & 31u, wid = tid >> 5, nw = T >> 5;
-    const uint32_t SEG = (uint32_t)P.wide_seg, RS = (SEG + 4u) * 2u, HALF = SEG >> 1;
+    const uint32_t SEG = (uint32_t)P.wide_seg, HALF = SEG >> 1;
+    const uint32_t RSM = (HALF + 2u) * 4u, RSE = (HALF + 2u) * 8u;           /* row strides: M ring (one word per column pair), I|D ring ({I, D} words per column pair) */
     const uint32_t sMail = sbase, sRed = sbase + 512u;
-    const uint32_t sRing = sbase + WIDE_HEAD_BYTES;
-    const uint32_t sSeq = (sRing + 9u * RS + 7u) & ~7u;
+    const uint32_t sRingE = sbase + WIDE_HEAD_BYTES;                          /* 2 rows of {I pair, D pair} */
+    const uint32_t sRingM = sRingE + 2u * RSE;                                /* 5 rows */
+    const uint32_t sSeq = (sRingM + 5u * RSM + 7u) & ~7u;
 
     const PairDesc pd = P.pairs[pair];
     const int n = (int)pd.n, m = (int)pd.m, Ak = m - n;
@@ -104,8 +121,8 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
     f.c_cells = f.c_written = f.c_steps = 0; f.first_eq = false;
     if (pd.m > WIDE_MAX_M || W > C * SEG || qent + tent + 2u > P.wide_seq_cap) { f.status = ST_RING; return f; }
 
-    /* ---- per-pair set-up: ring zeroed (absent everywhere), the sequences in their windows */
-    for (uint32_t a = tid * 4u; a < 9u * RS; a += T * 4u) sts_u32(sRing + a, 0u);
+    /* ---- per-pair set-up: rings zeroed (absent everywhere), the sequences in their windows */
+    for (uint32_t a = tid * 4u; a < 2u * RSE + 5u * RSM; a += T * 4u) sts_u32(sRingE + a, 0u);
     SeqAll Q, Tq;
     Q.sa = sSeq; Tq.sa = sSeq + (qent + 1u) * 8u;
     {
@@ -119,6 +136,7 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(Tq.sa + j * 8u), "r"(a), "r"(b) : "memory");
         }
     }
+    keep(Q.sa); keep(Tq.sa);                                   /* (opaque: not to be re-derived from the kernel parameters inside the cell loop) */
     cluster_sync_all();                                        /* nobody pushes a halo cell into a ring that is still being cleared */
 
     SlimHdr *hdrs = reinterpret_cast<SlimHdr *>(slot);         /* grows up, index s/g */
@@ -128,181 +146,216 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
     long long room = (long long)slot_cells - (long long)(3 * HDR_CELLS + 8);
 
     const int nm1 = n - 1;
-    const uint32_t base_j = rank * SEG;                        /* first column of this CTA's segment */
+    uint32_t base_j = rank * SEG;                              /* first column of this CTA's segment */
+    keep(base_j);
     const int ilo = SEMI ? -nm1 : 0, ihi = SEMI ? m - 1 : 0;   /* init cells, wfa.go:155-183 */
+    const bool edgeL = rank > 0, edgeR = rank + 1u < C;        /* the segment has a neighbour on that side: its first / last column pair needs halo cells */
 
-    /* present ranges [lo, hi] of the rows s-1 .. s-5 (s-5: what the M slot being overwritten still holds) */
-    int lo1 = SLIM_NONE_LO, hi1 = SLIM_NONE_HI, lo2 = SLIM_NONE_LO, hi2 = SLIM_NONE_HI, lo3 = SLIM_NONE_LO, hi3 = SLIM_NONE_HI;
-    int lo4 = SLIM_NONE_LO, hi4 = SLIM_NONE_HI, lo5 = SLIM_NONE_LO, hi5 = SLIM_NONE_HI;
     unsigned long long c_cells = 0, c_written = 0, c_steps = 0;
-    int status = ST_OK, si = -1, lastK = Ak;
-    uint32_t minS = 0, parity = 0;
+    int status = ST_OK, si = -1, lastK = Ak, si_final = 0;
+    uint32_t minS = 0, top_final = slot_cells;
     uint32_t slotM = 4;                                        /* ring slot of row si (si mod 5), advanced incrementally */
+    /* the previous row, whose reductions are still on their way */
+    bool pending = false; uint32_t p_off = 0, p_ja = 0, p_aw = 0;
 
     for (;;) {
         si++;
         slotM = slotM == 4u ? 0u : slotM + 1u;
         const bool has_init = si == 0 || si == SLIM_XG;
-        int lo = min(min(lo1, lo2), lo4), hi = max(max(hi1, hi2), hi4);
-        if (lo <= hi) { lo = max(lo - 1, -nm1); hi = min(hi + 1, m - 1); }       /* wfa.go:557-563 */
-        if (has_init) { lo = min(lo, ilo); hi = max(hi, ihi); }
-        lo = min(lo, lo5); hi = max(hi, hi5);                                     /* cells the destination slot still holds are recomputed (to absent) */
-        int4 hc = make_int4(0, 1, 0, 0);
-        room -= (long long)HDR_CELLS;
-        bool exists = false, endhit = false, hit = false;
-        int wlo = SLIM_NONE_LO, whi = SLIM_NONE_HI, hitK = Ak;
-        if (lo <= hi) {
-            const uint32_t ja = (uint32_t)(lo + nm1) & ~1u, jb = (uint32_t)(hi + nm1) | 1u;   /* even / odd: whole column pairs */
-            const uint32_t aw = jb - ja + 1u;
-            room -= (long long)aw;
-            if (room < 0) { status = ST_ARENA; break; }
-            const uint32_t off = top - aw;
-            /* this CTA's share: column pairs c (columns base_j + 2c, + 1), c in [cl, ch] */
-            const int gl = (int)(ja >> 1) - (int)(base_j >> 1), gh = (int)(jb >> 1) - (int)(base_j >> 1);
-            const int cl = max(gl, 0), ch = min(gh, (int)HALF - 1);
-            /* source and destination rows */
-            uint32_t s4 = slotM + 1u; s4 = s4 >= 5u ? s4 - 5u : s4;             /* row si-4 = slot (si+1) mod 5 */
-            uint32_t s2 = slotM + 3u; s2 = s2 >= 5u ? s2 - 5u : s2;             /* row si-2 */
-            const uint32_t pe = (uint32_t)(si & 1);
-            const uint32_t bM4 = sRing + s4 * RS, bM2 = sRing + s2 * RS, bI1 = sRing + (5u + (pe ^ 1u)) * RS, bD1 = sRing + (7u + (pe ^ 1u)) * RS;
-            const uint32_t bMc = sRing + slotM * RS, bIc = sRing + (5u + pe) * RS, bDc = sRing + (7u + pe) * RS;
-            CellT *grow = cells + off - ja;                                     /* cell of column j at grow[j] */
-            int pmin = INT_MAX, pmax = INT_MIN, ka = INT_MIN, kb = INT_MAX;
-            auto body = [&](auto initc) {
-                constexpr bool INIT = decltype(initc)::value;
-                for (int c = cl + (int)tid; c <= ch; c += (int)T) {
-                    const uint32_t wa = 4u * (uint32_t)c + 4u;
-                    const uint32_t a = lds_u32(bM4 + wa - 4u), b = lds_u32(bM4 + wa), d = lds_u32(bM4 + wa + 4u);
-                    const uint32_t ia = lds_u32(bI1 + wa - 4u), ib = lds_u32(bI1 + wa);
-                    const uint32_t db = lds_u32(bD1 + wa), dd = lds_u32(bD1 + wa + 4u);
-                    const uint32_t xm = lds_u32(bM2 + wa);
-                    const uint32_t j0 = base_j + 2u * (uint32_t)c;              /* columns j0, j0 + 1; n + k = j + 1 */
-                    const bool act1 = j0 + 1u < W;                              /* the padding column past the last diagonal stays absent */
-                    const uint32_t um = (uint32_t)m;
-                    Cell3O c0 = next_off3(a >> 16, ia >> 16, b >> 16, db >> 16, xm & 0xffffu, um, j0 + 1u);
-                    Cell3O c1 = next_off3(b & 0xffffu, ib & 0xffffu, d & 0xffffu, dd & 0xffffu, xm >> 16, act1 ? um : 0u, act1 ? j0 + 2u : 0u);
-                    const int k0 = (int)j0 - nm1;
-                    if (INIT) {
-                        /* initComponents (wfa.go:155-183): cell k of the first row / column; next's Set wins when both write */
-                        auto seed = [&](Cell3O &cc, const int k, const bool act) {
-                            if (cc.M == 0u && act && k >= ilo && k <= ihi) {
-                                const bool eq = ((Q.chunk((uint32_t)(k < 0 ? -k : 0)) ^ Tq.chunk((uint32_t)(k > 0 ? k : 0))) & 3u) == 0u;
-                                if (eq ? (si == 0) : (si == SLIM_XG)) cc.M = (uint32_t)((k > 0 ? k : 0) + 1);
-                            }
-                        };
-                        seed(c0, k0, true); seed(c1, k0 + 1, act1);
+        const int lo = SEMI ? -nm1 : max(-si, -nm1), hi = SEMI ? m - 1 : min(si, m - 1);
+        const uint32_t ja = (uint32_t)(lo + nm1) & ~1u, jb = (uint32_t)(hi + nm1) | 1u;       /* even / odd: whole column pairs */
+        const uint32_t aw = jb - ja + 1u;
+        room -= (long long)(HDR_CELLS + aw);
+        if (room < 0) { if (pending) cluster_wait(); status = ST_ARENA; break; }
+        const uint32_t off = top - aw;
+        /* this CTA's share: column pairs c (columns base_j + 2c, + 1), c in [cl, ch]; the pairs next to a
+         * neighbouring segment wait for the halo cells (after the barrier of the previous row) */
+        const int gl = (int)(ja >> 1) - (int)(base_j >> 1), gh = (int)(jb >> 1) - (int)(base_j >> 1);
+        const int cl = max(gl, 0), ch = min(gh, (int)HALF - 1);
+        const bool doL = edgeL && cl == 0 && cl <= ch, doR = edgeR && ch == (int)HALF - 1 && cl <= ch;      /* (a segment has at least 32 column pairs) */
+        const int c_first = cl + (doL ? 1 : 0), c_last = ch - (doR ? 1 : 0);
+        /* source and destination rows */
+        uint32_t s4 = slotM + 1u; s4 = s4 >= 5u ? s4 - 5u : s4;                 /* row si-4 = slot (si+1) mod 5 */
+        uint32_t s2 = slotM + 3u; s2 = s2 >= 5u ? s2 - 5u : s2;                 /* row si-2 */
+        const uint32_t pe = (uint32_t)(si & 1);
+        uint32_t bM4 = sRingM + s4 * RSM, bM2 = sRingM + s2 * RSM, bMc = sRingM + slotM * RSM;
+        uint32_t bE1 = sRingE + (pe ^ 1u) * RSE, bEc = sRingE + pe * RSE;
+        keep(bM4); keep(bM2); keep(bMc); keep(bE1); keep(bEc);                 /* (not to be re-derived inside the cell loop) */
+        uint4 *grow = reinterpret_cast<uint4 *>(cells + off - ja + base_j);     /* column pair c of this CTA at grow[c] */
+        keep_ptr(grow);
+        int pmin = INT_MAX, pmax = INT_MIN, ka = INT_MIN, kb = INT_MAX;         /* pmin / pmax: first / last column PAIR with a present cell */
+
+        /* one column pair: next (wfa.go:572-699) + extend (wfa.go:394-455) of its two cells, stores */
+        auto cellpair = [&](const int c, auto initc) {
+            constexpr bool INIT = decltype(initc)::value;
+            const uint32_t wa = 4u * (uint32_t)c + 4u;
+            const uint32_t pM4 = bM4 + wa, pE1 = bE1 + 2u * wa;
+            const uint32_t a = lds32<-4>(pM4), b = lds32<0>(pM4), d = lds32<4>(pM4);
+            const uint32_t ia = lds32<-8>(pE1), dd = lds32<12>(pE1);
+            uint32_t ib, db;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(ib), "=r"(db) : "r"(pE1));
+            const uint32_t xm = lds32<0>(bM2 + wa);
+            const uint32_t j0 = base_j + 2u * (uint32_t)c;                      /* columns j0, j0 + 1; n + k = j + 1 */
+            const bool act1 = j0 + 1u < W;                                      /* the padding column past the last diagonal stays absent */
+            const uint32_t um = (uint32_t)m;
+            Cell3O c0 = next_off3(a >> 16, ia >> 16, b >> 16, db >> 16, xm & 0xffffu, um, j0 + 1u);
+            Cell3O c1 = next_off3(b & 0xffffu, ib & 0xffffu, d & 0xffffu, dd & 0xffffu, xm >> 16, act1 ? um : 0u, act1 ? j0 + 2u : 0u);
+            const int k0 = (int)j0 - nm1;
+            if (INIT) {
+                /* initComponents (wfa.go:155-183): cell k of the first row / column; next's Set wins when both write */
+                auto seed = [&](Cell3O &cc, const int k, const bool act) {
+                    if (cc.M == 0u && act && k >= ilo && k <= ihi) {
+                        const bool eq = ((Q.chunk((uint32_t)(k < 0 ? -k : 0)) ^ Tq.chunk((uint32_t)(k > 0 ? k : 0))) & 3u) == 0u;
+                        if (eq ? (si == 0) : (si == SLIM_XG)) cc.M = (uint32_t)((k > 0 ? k : 0) + 1);
                     }
-                    /* extend (wfa.go:394-455): a present cell has v >= 1, so it applies iff min(n - v, m - h) > 0 */
-                    auto extend = [&](uint32_t M, const uint32_t j, const int k) -> uint32_t {
-                        const int ext = (int)min(j + 1u, um) - (int)M;          /* min(n + k, m) - M */
-                        if (M == 0u) return M;
-                        if (ext > 0) {
-                            const uint32_t v = (uint32_t)((int)M - k);
-                            int l = 0;
-                            do {
-                                const uint32_t xx = Q.chunk(v + (uint32_t)l) ^ Tq.chunk(M + (uint32_t)l);
-                                if (xx) { l += __clz((int)__brev(xx)) >> 1; break; }
-                                l += 16;
-                            } while (l < ext);
-                            M += (uint32_t)min(l, ext);
-                            if (l < ext) return M;
-                        }
-                        if (SEMI) {
-                            /* a cell at the end of a sequence: start-cell classification (wfa.go:306-323 / :341-358) */
-                            const int h = (int)M, v = h - k;
-                            int cls = 0;
-                            if (v <= 0 || v > n || h > m) cls = 1;
-                            else if ((v == n && h >= n) || (h == m && v >= m)) cls = 2;
-                            if (cls) {
-                                const int key = (k + n) * 2 + (cls == 2);
-                                if (k <= Ak) ka = max(ka, key); else kb = min(kb, key);
-                            }
-                        }
-                        return M;
-                    };
-                    c0.M = extend(c0.M, j0, k0);
-                    c1.M = extend(c1.M, j0 + 1u, k0 + 1);
-                    sts_u32(bMc + wa, c0.M | c1.M << 16); sts_u32(bIc + wa, c0.I | c1.I << 16); sts_u32(bDc + wa, c0.D | c1.D << 16);
-                    const CellT w0 = SC::pack(c0.M, c0.I, c0.D), w1 = SC::pack(c1.M, c1.I, c1.D);
-                    *reinterpret_cast<ulonglong2 *>(grow + j0) = make_ulonglong2(w0, w1);
-                    /* M WaveFront.Lo/Hi: first / last present cell */
-                    if (c0.M) { pmin = min(pmin, (int)j0); pmax = max(pmax, (int)j0); }
-                    if (c1.M) { pmin = min(pmin, (int)j0 + 1); pmax = max(pmax, (int)j0 + 1); }
+                };
+                seed(c0, k0, true); seed(c1, k0 + 1, act1);
+            }
+            /* extend: a present cell has v >= 1, so it applies iff ext = min(n - v, m - h) > 0.  The first 16
+             * bases are compared whatever the cell (an absent cell or one at the end of a sequence compares
+             * clamped positions and advances by 0): the common case is straight-line code */
+            auto extend = [&](const uint32_t M, const uint32_t j, const int k) -> uint32_t {
+                const int ext = (int)min(j + 1u, um) - (int)M;                  /* min(n + k, m) - M */
+                const uint32_t v = min((uint32_t)((int)M - k), (uint32_t)nm1);
+                const uint32_t xx = Q.chunk(v) ^ Tq.chunk(M);
+                int l = __clz((int)__brev(xx)) >> 1;                            /* 16 when all 16 bases agree */
+                if (l >= 16 && ext > 16) {
+                    do {
+                        const uint32_t x2 = Q.chunk(v + (uint32_t)l) ^ Tq.chunk(M + (uint32_t)l);
+                        if (x2) { l += __clz((int)__brev(x2)) >> 1; break; }
+                        l += 16;
+                    } while (l < ext);
                 }
+                const uint32_t Mn = M ? M + (uint32_t)max(min(l, ext), 0) : 0u;
+                if (SEMI && M != 0u && l >= ext) {
+                    /* the cell has reached the end of a sequence: start-cell classification (wfa.go:306-323 / :341-358) */
+                    const int h = (int)Mn, vv = h - k;
+                    int cls = 0;
+                    if (vv <= 0 || vv > n || h > m) cls = 1;
+                    else if ((vv == n && h >= n) || (h == m && vv >= m)) cls = 2;
+                    if (cls) {
+                        const int key = (k + n) * 2 + (cls == 2);
+                        if (k <= Ak) ka = max(ka, key); else kb = min(kb, key);
+                    }
+                }
+                return Mn;
             };
-            if (has_init) body(std::true_type{}); else body(std::false_type{});
-            /* halo: the first / last column of the segment goes to the neighbour that reads it as k + 1 / k - 1 */
-            if (cl <= ch) {
-                if (rank > 0 && cl == 0 && tid == 0) {
-                    const uint32_t left = rank - 1u;
-                    st_cluster_u16(cluster_map(bMc + 4u + SEG * 2u, left), lds_u16(bMc + 4u));          /* M -> column SEG of the left CTA */
-                    st_cluster_u16(cluster_map(bDc + 4u + SEG * 2u, left), lds_u16(bDc + 4u));
-                }
-                if (rank + 1u < C && ch == (int)HALF - 1 && tid == (uint32_t)(ch - cl) % T) {
-                    const uint32_t right = rank + 1u;
-                    st_cluster_u16(cluster_map(bMc + 2u, right), lds_u16(bMc + 2u + SEG * 2u));          /* M -> column -1 of the right CTA */
-                    st_cluster_u16(cluster_map(bIc + 2u, right), lds_u16(bIc + 2u + SEG * 2u));
-                }
-                /* end test on diagonal m - n = column m - 1 (wfa.go:235-239), by the thread that wrote it */
-                const int cA = (int)(((uint32_t)m - 1u) >> 1) - (int)(base_j >> 1);
-                if (cA >= cl && cA <= ch && tid == (uint32_t)(cA - cl) % T)
-                    endhit = lds_u16(bMc + 4u + ((uint32_t)m - 1u - base_j) * 2u) >= (uint32_t)m;
-            }
-            /* reductions: warp, block, then every CTA's partial result into every CTA's mailbox */
-            pmin = __reduce_min_sync(0xffffffffu, pmin); pmax = __reduce_max_sync(0xffffffffu, pmax);
-            const uint32_t eh = __any_sync(0xffffffffu, endhit) ? 1u : 0u;
-            if (SEMI) { ka = __reduce_max_sync(0xffffffffu, ka); kb = __reduce_min_sync(0xffffffffu, kb); }
-            if (lane == 0) {
-                sts_u32(sRed + wid * 4u, (uint32_t)pmin); sts_u32(sRed + 128u + wid * 4u, (uint32_t)pmax); sts_u32(sRed + 256u + wid * 4u, eh);
-                if (SEMI) { sts_u32(sRed + 384u + wid * 4u, (uint32_t)ka); sts_u32(sRed + 512u + wid * 4u, (uint32_t)kb); }
-            }
-            __syncthreads();
-            if (wid == 0) {
-                int a0 = lane < nw ? (int)lds_u32(sRed + lane * 4u) : INT_MAX, a1 = lane < nw ? (int)lds_u32(sRed + 128u + lane * 4u) : INT_MIN;
-                uint32_t a2 = lane < nw ? lds_u32(sRed + 256u + lane * 4u) : 0u;
-                int a3 = INT_MIN, a4 = INT_MAX;
-                if (SEMI) { a3 = lane < nw ? (int)lds_u32(sRed + 384u + lane * 4u) : INT_MIN; a4 = lane < nw ? (int)lds_u32(sRed + 512u + lane * 4u) : INT_MAX; }
-                a0 = __reduce_min_sync(0xffffffffu, a0); a1 = __reduce_max_sync(0xffffffffu, a1); a2 = __reduce_or_sync(0xffffffffu, a2);
-                if (SEMI) { a3 = __reduce_max_sync(0xffffffffu, a3); a4 = __reduce_min_sync(0xffffffffu, a4); }
-                if (lane < C) {
-                    const uint32_t dst = cluster_map(sMail + parity * 256u + rank * 32u, lane);
-                    st_cluster_u32(dst, (uint32_t)a0); st_cluster_u32(dst + 4u, (uint32_t)a1); st_cluster_u32(dst + 8u, a2);
-                    st_cluster_u32(dst + 12u, (uint32_t)a3); st_cluster_u32(dst + 16u, (uint32_t)a4);
-                }
-            }
-            cluster_sync_all();                                 /* row, halos and mailboxes are in place everywhere */
-            {
+            c0.M = extend(c0.M, j0, k0);
+            c1.M = extend(c1.M, j0 + 1u, k0 + 1);
+            const uint32_t Mw = c0.M | c1.M << 16, Iw = c0.I | c1.I << 16, Dw = c0.D | c1.D << 16;
+            sts_u32(bMc + wa, Mw);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(bEc + 2u * wa), "r"(Iw), "r"(Dw) : "memory");
+            /* arena: two 8-byte cells {M | I << 16, D}, one 128-bit store */
+            grow[c] = make_uint4(__byte_perm(Mw, Iw, 0x5410), Dw & 0xffffu, __byte_perm(Mw, Iw, 0x7632), Dw >> 16);
+            if (Mw) { pmin = min(pmin, c); pmax = max(pmax, c); }
+        };
+        auto run = [&](auto initc) {
+            int c = c_first + (int)tid;
+            if (c <= c_last) { cellpair(c, initc); c += (int)T; }
+            if (pending) {
+                /* ---- the previous row: its barrier has had a column pair's worth of time to complete */
+                cluster_wait();
+                pending = false;
+                const uint32_t mbase = sMail + (uint32_t)((si - 1) & 1) * 256u;
                 int g0 = INT_MAX, g1 = INT_MIN, g3 = INT_MIN, g4 = INT_MAX; uint32_t g2 = 0;
                 for (uint32_t r = 0; r < C; r++) {
-                    const uint32_t mb = sMail + parity * 256u + r * 32u;
+                    const uint32_t mb = mbase + r * 32u;
                     g0 = min(g0, (int)lds_u32(mb)); g1 = max(g1, (int)lds_u32(mb + 4u)); g2 |= lds_u32(mb + 8u);
                     if (SEMI) { g3 = max(g3, (int)lds_u32(mb + 12u)); g4 = min(g4, (int)lds_u32(mb + 16u)); }
                 }
-                parity ^= 1u;
-                exists = g0 <= g1;
-                wlo = g0 - nm1; whi = g1 - nm1; endhit = g2 != 0u;
+                const bool exists = g0 <= g1, endhit = g2 != 0u;
+                const int wlo = g0 - nm1, whi = g1 - nm1;
+                bool hit = false; int hitK = Ak;
                 if (SEMI) {
                     /* backtraceStartPosistion (wfa.go:270-375) for this one score: scan (a) runs from the end
                      * diagonal downwards, scan (b) upwards from the one above it; (b) overrides (a) */
                     if (g3 != INT_MIN && (g3 & 1)) { hit = true; hitK = (g3 >> 1) - n; }
                     if (g4 != INT_MAX && (g4 & 1)) { hit = true; hitK = (g4 >> 1) - n; }
                 }
+                int4 hc = make_int4(0, 1, 0, 0);
+                c_written += p_aw;
+                if (exists) {
+                    c_steps++; c_cells += (unsigned long long)(whi - wlo + 1);
+                    hc = make_int4((int)p_ja - nm1, wlo, whi, (int)p_off);
+                    top_final = p_off;
+                }
+                if (rank == 0 && tid == 0) *reinterpret_cast<int4 *>(hdrs + (si - 1)) = hc;
+                si_final = si - 1;
+                if (exists && endhit) { minS = (uint32_t)(si - 1) * P.g; lastK = SEMI && hit ? hitK : Ak; return true; }
+                if (SEMI && exists && hit) { minS = (uint32_t)(si - 1) * P.g; lastK = hitK; return true; }
             }
-            if (exists) {
-                top = off;
-                c_steps++; c_cells += (unsigned long long)(whi - wlo + 1); c_written += aw;
-                hc = make_int4((int)ja - nm1, wlo, whi, (int)off);
-            } else room += (long long)aw;
+            /* the column pairs next to the neighbouring segments, now that their halo cells are here; their
+             * outermost cells go on to the neighbour that reads them as k + 1 / k - 1 */
+            if (wid == nw - 1u) {
+                if (lane == 0 && doL) {
+                    cellpair(0, initc);
+                    const uint32_t left = rank - 1u;
+                    st_cluster_u16(cluster_map(bMc + 4u * (HALF + 1u), left), lds_u16(bMc + 4u));             /* M -> column SEG of the left CTA */
+                    st_cluster_u16(cluster_map(bEc + 8u * (HALF + 1u) + 4u, left), lds_u16(bEc + 8u + 4u));   /* D */
+                    cluster_fence();
+                }
+                if (lane == 1 && doR) {
+                    cellpair((int)HALF - 1, initc);
+                    const uint32_t right = rank + 1u;
+                    st_cluster_u16(cluster_map(bMc + 2u, right), lds_u16(bMc + 4u * HALF + 2u));              /* M -> column -1 of the right CTA */
+                    st_cluster_u16(cluster_map(bEc + 2u, right), lds_u16(bEc + 8u * HALF + 2u));              /* I */
+                    cluster_fence();
+                }
+            }
+            for (; c <= c_last; c += (int)T) cellpair(c, initc);
+            return false;
+        };
+        const bool done = has_init ? run(std::true_type{}) : run(std::false_type{});
+        if (done) break;
+
+        /* ---- this row's reductions: exact first / last present column from the thread's own pair words,
+         * end test on diagonal m - n = column m - 1 (wfa.go:235-239) by the thread that wrote it */
+        int cmin = INT_MAX, cmax = INT_MIN;
+        if (pmin <= pmax) {
+            const uint32_t w0 = lds_u32(bMc + 4u * (uint32_t)pmin + 4u), w1 = lds_u32(bMc + 4u * (uint32_t)pmax + 4u);
+            cmin = (int)base_j + 2 * pmin + ((w0 & 0xffffu) ? 0 : 1);
+            cmax = (int)base_j + 2 * pmax + ((w1 >> 16) ? 1 : 0);
         }
-        if (room < 0) { status = ST_ARENA; break; }
-        if (rank == 0 && tid == 0) *reinterpret_cast<int4 *>(hdrs + si) = hc;
-        lo5 = lo4; hi5 = hi4; lo4 = lo3; hi4 = hi3; lo3 = lo2; hi3 = hi2; lo2 = lo1; hi2 = hi1;
-        lo1 = exists ? wlo : SLIM_NONE_LO; hi1 = exists ? whi : SLIM_NONE_HI;
-        if (exists && endhit) { minS = (uint32_t)si * P.g; lastK = SEMI && hit ? hitK : Ak; break; }
-        if (SEMI && exists && hit) { minS = (uint32_t)si * P.g; lastK = hitK; break; }
+        bool endhit = false;
+        {
+            /* the thread that computed column m - 1 reads its own store */
+            const int cA = (int)(((uint32_t)m - 1u) >> 1) - (int)(base_j >> 1);
+            bool mine;
+            if (doL && cA == 0) mine = wid == nw - 1u && lane == 0;
+            else if (doR && cA == (int)HALF - 1) mine = wid == nw - 1u && lane == 1;
+            else mine = cA >= c_first && cA <= c_last && tid == (uint32_t)(cA - c_first) % T;
+            if (mine) endhit = lds_u16(bMc + 4u + ((uint32_t)m - 1u - base_j) * 2u) >= (uint32_t)m;
+        }
+        cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
+        const uint32_t eh = __any_sync(0xffffffffu, endhit) ? 1u : 0u;
+        if (SEMI) { ka = __reduce_max_sync(0xffffffffu, ka); kb = __reduce_min_sync(0xffffffffu, kb); }
+        if (lane == 0) {
+            sts_u32(sRed + wid * 4u, (uint32_t)cmin); sts_u32(sRed + 128u + wid * 4u, (uint32_t)cmax); sts_u32(sRed + 256u + wid * 4u, eh);
+            if (SEMI) { sts_u32(sRed + 384u + wid * 4u, (uint32_t)ka); sts_u32(sRed + 512u + wid * 4u, (uint32_t)kb); }
+        }
+        __syncthreads();
+        if (wid == 0) {
+            int a0 = lane < nw ? (int)lds_u32(sRed + lane * 4u) : INT_MAX, a1 = lane < nw ? (int)lds_u32(sRed + 128u + lane * 4u) : INT_MIN;
+            uint32_t a2 = lane < nw ? lds_u32(sRed + 256u + lane * 4u) : 0u;
+            int a3 = INT_MIN, a4 = INT_MAX;
+            if (SEMI) { a3 = lane < nw ? (int)lds_u32(sRed + 384u + lane * 4u) : INT_MIN; a4 = lane < nw ? (int)lds_u32(sRed + 512u + lane * 4u) : INT_MAX; }
+            a0 = __reduce_min_sync(0xffffffffu, a0); a1 = __reduce_max_sync(0xffffffffu, a1); a2 = __reduce_or_sync(0xffffffffu, a2);
+            if (SEMI) { a3 = __reduce_max_sync(0xffffffffu, a3); a4 = __reduce_min_sync(0xffffffffu, a4); }
+            if (lane < C) {
+                const uint32_t dst = cluster_map(sMail + (uint32_t)(si & 1) * 256u + rank * 32u, lane);
+                st_cluster_u32(dst, (uint32_t)a0); st_cluster_u32(dst + 4u, (uint32_t)a1); st_cluster_u32(dst + 8u, a2);
+                st_cluster_u32(dst + 12u, (uint32_t)a3); st_cluster_u32(dst + 16u, (uint32_t)a4);
+                cluster_fence();
+            }
+        }
+        /* arrive now, wait in the middle of the next row: halos (their writers' fences) and mailboxes are
+         * in place everywhere once the barrier completes */
+        cluster_arrive_relaxed();
+        pending = true; p_off = off; p_ja = ja; p_aw = aw;
+        top = off;
     }
 
-    f.status = status; f.minS = minS; f.lastK = lastK; f.si = si; f.top = (uint64_t)top;
+    f.status = status; f.minS = minS; f.lastK = lastK; f.si = si_final; f.top = (uint64_t)top_final;
     f.c_cells = c_cells; f.c_written = c_written; f.c_steps = c_steps;
     return f;
 }
@@ -349,7 +402,7 @@ wide_finish_kernel(const KParams P)
     f.status = ST_PENDING; f.minS = 0; f.lastK = 0; f.si = 0; f.n = f.m = 0; f.top = 0; f.c_cells = f.c_written = f.c_steps = 0; f.first_eq = false;
     uint32_t pair = 0;
     if (have) { f = P.wide_rec[item]; pair = P.work ? P.work[item] : item; }
-    finish_group_slim<1>(P, have, pair, f, P.arena + (uint64_t)(have ? item : 0u) * P.slot_bytes, P.slot_bytes);
+    finish_group_slim<3>(P, have, pair, f, P.arena + (uint64_t)(have ? item : 0u) * P.slot_bytes, P.slot_bytes);
 }
 
 } /* namespace wfak */
