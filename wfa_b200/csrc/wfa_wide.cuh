@@ -86,7 +86,7 @@ struct SeqAll {
 
 /* Forward pass of one pair by the whole cluster: wfa.go:228-251 with next + extend fused per cell.
  * Every thread of every CTA keeps the same row bookkeeping in registers (the reductions are combined
- * identically everywhere).  Returns what the finish kernel needs (valid in all threads).
+ * identically everywhere).  Returns what the finish kernel needs (complete in thread 0 of CTA 0, the record keeper).
  *
  * Rows and ranges.  Row si (score si * g) is computed over a range that depends on si alone: all
  * n + m - 1 diagonals for semi-global alignment (the init cells span them, wfa.go:160-183), [-si, si]
@@ -264,7 +264,6 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
                     if (SEMI) { g3 = max(g3, (int)lds_u32(mb + 12u)); g4 = min(g4, (int)lds_u32(mb + 16u)); }
                 }
                 const bool exists = g0 <= g1, endhit = g2 != 0u;
-                const int wlo = g0 - nm1, whi = g1 - nm1;
                 bool hit = false; int hitK = Ak;
                 if (SEMI) {
                     /* backtraceStartPosistion (wfa.go:270-375) for this one score: scan (a) runs from the end
@@ -272,35 +271,37 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
                     if (g3 != INT_MIN && (g3 & 1)) { hit = true; hitK = (g3 >> 1) - n; }
                     if (g4 != INT_MAX && (g4 & 1)) { hit = true; hitK = (g4 >> 1) - n; }
                 }
-                int4 hc = make_int4(0, 1, 0, 0);
-                c_written += p_aw;
-                if (exists) {
-                    c_steps++; c_cells += (unsigned long long)(whi - wlo + 1);
-                    hc = make_int4((int)p_ja - nm1, wlo, whi, (int)p_off);
-                    top_final = p_off;
+                if (rank == 0 && tid == 0) {
+                    /* the record keeper: header of the row, work counters, where the backtrace starts */
+                    const int wlo = g0 - nm1, whi = g1 - nm1;
+                    int4 hc = make_int4(0, 1, 0, 0);
+                    c_written += p_aw;
+                    if (exists) {
+                        c_steps++; c_cells += (unsigned long long)(whi - wlo + 1);
+                        hc = make_int4((int)p_ja - nm1, wlo, whi, (int)p_off);
+                        top_final = p_off;
+                    }
+                    *reinterpret_cast<int4 *>(hdrs + (si - 1)) = hc;
+                    si_final = si - 1;
+                    if (exists && (endhit || hit)) { minS = (uint32_t)(si - 1) * P.g; lastK = SEMI && hit ? hitK : Ak; }
                 }
-                if (rank == 0 && tid == 0) *reinterpret_cast<int4 *>(hdrs + (si - 1)) = hc;
-                si_final = si - 1;
-                if (exists && endhit) { minS = (uint32_t)(si - 1) * P.g; lastK = SEMI && hit ? hitK : Ak; return true; }
-                if (SEMI && exists && hit) { minS = (uint32_t)(si - 1) * P.g; lastK = hitK; return true; }
+                if (exists && (endhit || (SEMI && hit))) return true;
             }
             /* the column pairs next to the neighbouring segments, now that their halo cells are here; their
              * outermost cells go on to the neighbour that reads them as k + 1 / k - 1 */
-            if (wid == nw - 1u) {
-                if (lane == 0 && doL) {
-                    cellpair(0, initc);
+            if (wid == nw - 1u && lane < 2u && (lane == 0 ? doL : doR)) {
+                /* (both in one pass: the warp with the fewest column pairs of its own takes one more) */
+                cellpair(lane == 0 ? 0 : (int)HALF - 1, initc);
+                if (lane == 0) {
                     const uint32_t left = rank - 1u;
                     st_cluster_u16(cluster_map(bMc + 4u * (HALF + 1u), left), lds_u16(bMc + 4u));             /* M -> column SEG of the left CTA */
                     st_cluster_u16(cluster_map(bEc + 8u * (HALF + 1u) + 4u, left), lds_u16(bEc + 8u + 4u));   /* D */
-                    cluster_fence();
-                }
-                if (lane == 1 && doR) {
-                    cellpair((int)HALF - 1, initc);
+                } else {
                     const uint32_t right = rank + 1u;
                     st_cluster_u16(cluster_map(bMc + 2u, right), lds_u16(bMc + 4u * HALF + 2u));              /* M -> column -1 of the right CTA */
                     st_cluster_u16(cluster_map(bEc + 2u, right), lds_u16(bEc + 8u * HALF + 2u));              /* I */
-                    cluster_fence();
                 }
+                cluster_fence();
             }
             for (; c <= c_last; c += (int)T) cellpair(c, initc);
             return false;
