@@ -320,6 +320,7 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
             uint32_t *gp = cells + off + lane;
             keep(pO); keep(pX); keep(pM); keep(pI); keep(pD); keep_ptr(gp);
             const uint32_t um = (uint32_t)m;
+            const uint32_t pos_max = (uint32_t)(SW - 1) * 16u - 1u;      /* last base whose 16-base chunk lies inside the SW words of a sequence */
 
             struct Pend { Cell3O c; int ext; uint32_t xr; };
             /* phase A of one cell: next (wfa.go:572-699) -> first 16-base compare of extend.  CLAMP
@@ -335,8 +336,9 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
                  * keeps or raises v -- so the test is "exists and min(n - v, m - h) > 0". */
                 const int h = (int)q.c.M, v = h - k;
                 q.ext = q.c.M != 0u ? max(min(n - v, m - h), 0) : 0;
-                /* positions are only meaningful when ex; masked so that the loads stay inside the block */
-                q.xr = lane_chunk(sQ, v & 255) ^ lane_chunk(sT, h);
+                /* positions are only meaningful when ext > 0; clamped so that the loads stay inside the lane's own
+                 * sequence words (an absent cell or one at the end of a sequence compares something and advances by 0) */
+                q.xr = lane_chunk(sQ, (int)min((uint32_t)v, pos_max)) ^ lane_chunk(sT, (int)min((uint32_t)h, pos_max));
                 return q;
             };
             /* phase B: rest of extend (wfa.go:411-454) */

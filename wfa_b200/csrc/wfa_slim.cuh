@@ -169,20 +169,37 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
         const int h = (int)M, v = h - k;
         /* a present cell has v >= 1, so "v > 0, v < n, h < m" is "min(n-v, m-h) > 0" */
         const int ext = min(n - v, m - h);
-        if (M == 0u || ext <= 0) return M;
-        int lim = ext;
-        if (LONGSEQ) {
-            if ((uint32_t)v < Q.wbase * 16u || (uint32_t)h < T.wbase * 16u) { slow = true; return M; }
-            lim = min(ext, min((int)(Q.wend * 16u) - v, (int)(T.wend * 16u) - h));       /* > 0 only if both chunks start inside */
-            if (lim <= 0) { slow = true; return M; }
+        if (!LONGSEQ) {
+            /* whole sequences in the window: the first 16 bases are compared whatever the cell (the window
+             * addresses wrap inside the ring; an absent cell or one at the end of a sequence advances by 0),
+             * so the common case is straight-line code for all lanes */
+            const uint32_t xx = Q.chunk((uint32_t)v) ^ T.chunk((uint32_t)h);
+            int l = __clz((int)__brev(xx)) >> 1;                                /* 16 when all 16 bases agree */
+            if (l >= 16 && ext > 16) {
+                do {
+                    const uint32_t x2 = Q.chunk((uint32_t)(v + l)) ^ T.chunk((uint32_t)(h + l));
+                    if (x2) { l += __clz((int)__brev(x2)) >> 1; break; }
+                    l += 16;
+                } while (l < ext);
+            }
+            return M ? M + (uint32_t)max(min(l, ext), 0) : 0u;
         }
-        int l = 0;
-        do {
-            const uint32_t xx = Q.chunk((uint32_t)(v + l)) ^ T.chunk((uint32_t)(h + l));
-            if (xx) { l += __clz((int)__brev(xx)) >> 1; break; }
-            l += 16;
-        } while (l < lim);
-        if (LONGSEQ && l >= lim && lim < ext) slow = true;
+        /* moving window: the first 16 bases are compared before anything is known about the cell (the window
+         * addresses wrap inside the ring), the tests that decide what the compare is worth follow */
+        const uint32_t xx = Q.chunk((uint32_t)v) ^ T.chunk((uint32_t)h);
+        if (M == 0u || ext <= 0) return M;
+        if ((uint32_t)v < Q.wbase * 16u || (uint32_t)h < T.wbase * 16u) { slow = true; return M; }
+        const int lim = min(ext, min((int)(Q.wend * 16u) - v, (int)(T.wend * 16u) - h));       /* > 0 only if both chunks start inside */
+        if (lim <= 0) { slow = true; return M; }
+        int l = __clz((int)__brev(xx)) >> 1;                                    /* 16 when all 16 bases agree */
+        if (l >= 16 && lim > 16) {
+            do {
+                const uint32_t x2 = Q.chunk((uint32_t)(v + l)) ^ T.chunk((uint32_t)(h + l));
+                if (x2) { l += __clz((int)__brev(x2)) >> 1; break; }
+                l += 16;
+            } while (l < lim);
+        }
+        if (l >= lim && lim < ext) slow = true;
         return M + (uint32_t)min(l, lim);
     };
     /* the same from the packed pool (idempotent on an already extended cell) */

@@ -218,6 +218,7 @@ struct wfacuda_batch {
     uint64_t n_pairs = 0;
     std::vector<uint8_t> host_status;       /* EMPTY / TOO_LONG decided on the host */
     std::vector<uint32_t> order_warp, order_cta, order_lane;
+    std::vector<uint32_t> order_slim_small, order_slim_rest;   /* order_warp split by SLIM cell word (reads of about 1 kbp), see wfacuda_batch_run */
     int identity_cls = -1;                  /* class (0 warp, 1 cta, 2 lane) whose order is 0..n-1: no work list needed */
     uint32_t lane_maxlen = 1;               /* longest sequence of the LANE class */
     PairDesc *descs = nullptr;              /* descs_own's storage; nullptr when the batch was uploaded with wire descriptors */
@@ -569,11 +570,11 @@ int plan_launch(wfacuda_ctx *ctx, const wfacuda_batch *b, const std::vector<uint
  * ring width (WARP kernel -> wider ring or the CTA kernel through *to_cta),
  * arena (4x slot) or ops pool (pool doubled). */
 int run_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_t> &order0, bool identity, bool cta, int bits, KParams base,
-              std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit, bool slim = false)
+              std::vector<uint32_t> *to_cta, std::vector<uint32_t> *to_8bit, bool slim = false, int slim_sz_force = -1)
 {
     /* SLIM worker: `to_cta` takes the pairs whose rows outgrow its widest instantiation (the WARP
      * worker places them); passes per row start from what earlier batches needed */
-    const int slim_sz = slim_size_class(b->max_len);
+    const int slim_sz = slim_sz_force >= 0 ? slim_sz_force : slim_size_class(b->max_len);
     int slim_li = 0;
     if (slim) {
         int p0 = ctx->slim_p_learned;
@@ -1502,6 +1503,13 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
                 (*ords[cls])[counts[cls][bk]++] = (uint32_t)i;
             }
         }
+        if (slim_class_enabled(ctx) && slim_size_class(b->max_len) == 1 && b->order_warp.size() >= 100000) {      /* (a second launch per pipeline chunk would cost more than it saves) */
+            /* reads of about 1 kbp: the pairs whose target fits the SLIM worker's 10-bit fields will take its 32-bit
+             * cell word (half the arena bytes, cheaper packing), only the few longer ones the 64-bit word */
+            b->order_slim_small.reserve(b->order_warp.size());
+            for (uint32_t pr : b->order_warp) (b->m_of(pr) <= SLIM_MAX_M10 && b->n_of(pr) <= SLIM_MAX_SHORT ? b->order_slim_small : b->order_slim_rest).push_back(pr);
+            if (b->order_slim_small.size() < 3 * b->order_slim_rest.size()) { b->order_slim_small.clear(); b->order_slim_rest.clear(); }
+        }
         const double t4 = now_ms();
         /* FIFO uploads: host-side wait for this chunk's copies (kernels queued behind a device-side
          * event wait were seen to hold up the other workers' streams -- streams share hardware
@@ -1604,7 +1612,13 @@ int wfacuda_batch_run(wfacuda_ctx *ctx, wfacuda_batch *b)
     bool use_slim = slim_class_enabled(ctx) && b->max_len <= SLIM_MAX_M21 && !force8 && !warp_order.empty();
     /* without heuristic a row is as wide as the score allows: not worth a try beyond the ring's reach */
     if (use_slim && !ctx->cfg.adaptive && !ctx->slim_p_learned && estimate_slim(ctx, b->max_len, b->max_len, false).width > 32 * kSlimLadder[kSlimLadderN - 1]) use_slim = false;
-    if (use_slim) {
+    if (use_slim && !b->order_slim_small.empty() && to_warp.empty()) {
+        /* (split by cell word at upload time) */
+        if ((rc = run_class(ctx, b, b->order_slim_small, false, false, 2, P, &slim_left, &warp8, true, 0))) return rc;
+        if ((rc = run_class(ctx, b, b->order_slim_rest, false, false, 2, P, &slim_left, &warp8, true, 1))) return rc;
+        ctx->stats.pairs_slim = (uint32_t)(warp_order.size() - slim_left.size() - warp8.size());
+        if ((rc = run_class(ctx, b, slim_left, false, false, 2, P, &to_cta, &warp8))) return rc;
+    } else if (use_slim) {
         if ((rc = run_class(ctx, b, warp_order, b->identity_cls == 0 && to_warp.empty(), false, 2, P, &slim_left, &warp8, true))) return rc;
         ctx->stats.pairs_slim = (uint32_t)(warp_order.size() - slim_left.size() - warp8.size());
         if ((rc = run_class(ctx, b, slim_left, false, false, 2, P, &to_cta, &warp8))) return rc;
