@@ -53,7 +53,7 @@ CPU_SAMPLE = {"cfg2_150bp_e5_global": 400_000, "cfg3_1kbp_e10_global_adaptive": 
 # config 4 needs 0.4 GB of backtrace arena per pair, config 5 is one config cut into N shards)
 SIDE_PAIRS = {"cfg3_1kbp_e10_global_adaptive": None, "cfg4_10kbp_in_12kbp_e5_semiglobal": 296,
               "cfg5_100kbp_e15_global_adaptive": "strong"}
-KERNEL_SOURCES = ("wfa_kernels.cuh", "wfa_lane.cuh", "wfa_slim.cuh")
+KERNEL_SOURCES = ("wfa_kernels.cuh", "wfa_lane.cuh", "wfa_slim.cuh", "wfa_wide.cuh")
 
 
 def peaks():

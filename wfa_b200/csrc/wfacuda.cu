@@ -1948,21 +1948,27 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
     if (n_pairs && !results) return fail(ctx, WFACUDA_E_INVALID, "results is NULL");
     if (n_pairs && (!seq_bytes || !q_off || !q_len || !t_off || !t_len)) return fail(ctx, WFACUDA_E_INVALID, "NULL input array");
     const uint64_t kMinChunk = 32768;
-    if (n_pairs < 2 * kMinChunk || getenv("WFACUDA_NO_PIPELINE")) {
+    uint64_t sample_bytes = 0;
+    const uint64_t sample_n = std::max<uint64_t>(1, std::min<uint64_t>(n_pairs, 4096));
+    for (uint64_t i = 0; i < sample_n && n_pairs; i++) sample_bytes += (uint64_t)q_len[i * (n_pairs / sample_n)] + t_len[i * (n_pairs / sample_n)];
+    const double mean_bytes = std::max(1.0, (double)sample_bytes / (double)sample_n);
+    /* A few hundred LONG pairs (config 5 as one GPU of eight sees it: 1 250 pairs of 100 kbp, 250 MB in, 230 MB of
+     * ops out): one warp per pair, every pair's 40 k dependent score steps decide the kernel time, and the device
+     * is far from full -- so four chunks whose kernels run side by side cost no more kernel time than one, while
+     * their uploads and downloads overlap the other chunks' kernels. */
+    const bool long_pairs = n_pairs >= 256 && mean_bytes >= 32768.0 && !getenv("WFACUDA_NO_LONG_PIPELINE");
+    if ((n_pairs < 2 * kMinChunk && !long_pairs) || getenv("WFACUDA_NO_PIPELINE")) {
         int rc = align_batch_single(ctx, n_pairs, seq_bytes, q_off, q_len, t_off, t_len, results, ops, ops_capacity, ops_off);
         if (rc == 0 || rc == WFACUDA_E_OPS_CAPACITY) return rc;
         return rc;
     }
     /* chunk size: about 20 MB of sequence (0.45 ms of PCIe; ~one full wave of the LANE kernel for 150 bp reads), at least kMinChunk pairs */
-    uint64_t sample_bytes = 0;
-    const uint64_t sample_n = std::min<uint64_t>(n_pairs, 4096);
-    for (uint64_t i = 0; i < sample_n; i++) sample_bytes += (uint64_t)q_len[i * (n_pairs / sample_n)] + t_len[i * (n_pairs / sample_n)];
-    const double mean_bytes = std::max(1.0, (double)sample_bytes / (double)sample_n);
     /* pageable caller memory is staged by the workers themselves (host memcpy, memory-bound):
      * fewer, larger chunks there */
     const bool src_pinned = is_pinned(seq_bytes);
     uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 20e6 : 24e6) / mean_bytes)));
-    if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
+    if (long_pairs) chunk_pairs = std::max<uint64_t>(32, (((n_pairs + 3) / 4 + 31) / 32) * 32);
+    if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(long_pairs ? 32 : 1024, strtoull(e, nullptr, 10));
     int tail_levels = 2;
     if (const char *e = getenv("WFACUDA_TAIL_LEVELS")) tail_levels = std::max(0, std::min(5, atoi(e)));
     const std::vector<uint64_t> cuts = plan_chunks(n_pairs, chunk_pairs, getenv("WFACUDA_UNIFORM_CHUNKS") ? -1 : tail_levels);
