@@ -198,8 +198,26 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
             const uint32_t j0 = base_j + 2u * (uint32_t)c;                      /* columns j0, j0 + 1; n + k = j + 1 */
             const bool act1 = j0 + 1u < W;                                      /* the padding column past the last diagonal stays absent */
             const uint32_t um = (uint32_t)m;
-            Cell3O c0 = next_off3(a >> 16, ia >> 16, b >> 16, db >> 16, xm & 0xffffu, um, j0 + 1u);
-            Cell3O c1 = next_off3(b & 0xffffu, ib & 0xffffu, d & 0xffffu, dd & 0xffffu, xm >> 16, act1 ? um : 0u, act1 ? j0 + 2u : 0u);
+            /* next (wfa.go:572-699) of both cells.  The sources as pairs of 16-bit offsets (low half: column j0):
+             * when none of them reaches a bound -- every cell away from the ends of the sequences -- all validity
+             * tests pass and the recurrence is I = max + 1, D = max, M = max(M[s-x] + 1, I, D) on present sources,
+             * which sm_100a does on both halves at once (VIMNMX.U16x2, VIADD.16x2); otherwise cell by cell. */
+            Cell3O c0, c1;
+            {
+                const uint32_t L2 = __byte_perm(a, b, 0x5432), I2 = __byte_perm(ia, ib, 0x5432);      /* M[s-o-e][k-1], I[s-e][k-1] */
+                const uint32_t R2 = __byte_perm(b, d, 0x5432), D2 = __byte_perm(db, dd, 0x5432);      /* M[s-o-e][k+1], D[s-e][k+1] */
+                const uint32_t mi = __vmaxu2(L2, I2), md = __vmaxu2(R2, D2);
+                const uint32_t all = __vmaxu2(__vmaxu2(mi, md), xm);
+                if (max(all & 0xffffu, all >> 16) <= min(um, j0 + 1u) && act1) {
+                    const uint32_t Iw2 = __vadd2(mi, __vminu2(mi, 0x00010001u));                        /* + 1 where present */
+                    const uint32_t Ew2 = __vadd2(xm, __vminu2(xm, 0x00010001u));
+                    const uint32_t Mw2 = __vmaxu2(__vmaxu2(Ew2, Iw2), md);
+                    c0.M = Mw2 & 0xffffu; c1.M = Mw2 >> 16; c0.I = Iw2 & 0xffffu; c1.I = Iw2 >> 16; c0.D = md & 0xffffu; c1.D = md >> 16;
+                } else {
+                    c0 = next_off3(a >> 16, ia >> 16, b >> 16, db >> 16, xm & 0xffffu, um, j0 + 1u);
+                    c1 = next_off3(b & 0xffffu, ib & 0xffffu, d & 0xffffu, dd & 0xffffu, xm >> 16, act1 ? um : 0u, act1 ? j0 + 2u : 0u);
+                }
+            }
             const int k0 = (int)j0 - nm1;
             if (INIT) {
                 /* initComponents (wfa.go:155-183): cell k of the first row / column; next's Set wins when both write */
