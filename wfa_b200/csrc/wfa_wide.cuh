@@ -408,6 +408,81 @@ wide_kernel(const KParams P)
     }
 }
 
+/* Component.Get on a WIDE slot of a SEMI-GLOBAL pair: every row spans the same columns (all n + m - 1 diagonals,
+ * padded to whole column pairs) and every computed row has its cells in the slot (absent ones as zeros), so the cell of
+ * (score index, diagonal) sits at an address that is arithmetic in both -- the backtrace's dependent chain is one arena
+ * read per step instead of header + cell.  Otherwise SlimView<3>. */
+struct WideSemiView {
+    typedef SlimCell<3> SC;
+    const uint64_t *cells;
+    uint32_t slot_cells, aw; int alo;
+    int si_last, n, m;
+    int c_si, c_k; uint64_t c_w[5];
+    __device__ __forceinline__ uint64_t word(int si, int k) const
+    {
+        const uint32_t col = (uint32_t)(k - alo);
+        if (si < 0 || si > si_last || col >= aw) return 0;
+        return __ldg(cells + (slot_cells - (uint32_t)(si + 1) * aw + col));
+    }
+    __device__ __forceinline__ uint64_t cached_word(int si, int k) const
+    {
+        const int dk = k - c_k, ds = c_si - si;
+        if (c_si >= 0) {
+            if (dk == -1) { if (ds == SLIM_OEG) return c_w[0]; if (ds == SLIM_EG) return c_w[1]; }
+            else if (dk == 1) { if (ds == SLIM_OEG) return c_w[2]; if (ds == SLIM_EG) return c_w[3]; }
+            else if (dk == 0 && ds == SLIM_XG) return c_w[4];
+        }
+        return word(si, k);
+    }
+    __device__ __forceinline__ uint32_t get(int comp, int si, int k) const { return SC::get(cached_word(si, k), comp) << T_BITS; }
+    __device__ __forceinline__ uint32_t get_typed(int comp, int si, int k)
+    {
+        const uint32_t o = SC::get(cached_word(si, k), comp);
+        if (o == 0) return 0;
+        const uint64_t wl = word(si - SLIM_OEG, k - 1), el = word(si - SLIM_EG, k - 1);
+        const uint64_t wr = word(si - SLIM_OEG, k + 1), er = word(si - SLIM_EG, k + 1);
+        const uint64_t wx = word(si - SLIM_XG, k);
+        c_si = si; c_k = k; c_w[0] = wl; c_w[1] = el; c_w[2] = wr; c_w[3] = er; c_w[4] = wx;
+        const CellO c = next_off(SC::get(wl, 0), SC::get(el, 1), SC::get(wr, 0), SC::get(er, 2), SC::get(wx, 0),
+                                 (uint32_t)m, (uint32_t)(n + k));
+        uint32_t code;
+        if (comp == 1) code = T_INS_OPEN + ((c.code >> 3) & 1u);
+        else if (comp == 2) code = T_DEL_OPEN + ((c.code >> 4) & 1u);
+        else code = c.M ? (c.code & 7u) : (si == 0 ? T_MATCH : T_MISMATCH);          /* init cell (wfa.go:160-183) */
+        return o << T_BITS | code;
+    }
+};
+
+__device__ __noinline__ void finish_group_wide_semi(const KParams &P, const bool have, const uint32_t pair, const FwdOut &f, uint8_t *slot, const uint64_t slot_bytes)
+{
+    uint32_t *words = reinterpret_cast<uint32_t *>(slot);
+    const uint64_t slot_words = slot_bytes >> 2, top_w = f.top * 2;
+    const uint64_t scratch_w = (((uint64_t)(f.si + 1) * sizeof(SlimHdr) + 7) / 8) * 2;
+    uint64_t *scratch = reinterpret_cast<uint64_t *>(words + scratch_w);
+    int status = have ? f.status : ST_PENDING;
+    Result res;
+    res.score = 0; res.tbegin = res.tend = res.qbegin = res.qend = 0;
+    res.align_len = res.matches = res.gaps = res.gap_regions = 0; res.n_ops = 0;
+    res.status = (uint8_t)status; res.pad_[0] = res.pad_[1] = res.pad_[2] = 0;
+    uint32_t n_ops = 0;
+    __syncwarp();
+    if (status == ST_OK) {
+        WideSemiView A; A.cells = reinterpret_cast<const uint64_t *>(slot);
+        A.slot_cells = (uint32_t)min(slot_bytes / 8, (uint64_t)0xfffffff0u) & ~1u;
+        A.alo = -(f.n - 1); A.aw = (((uint32_t)(f.n + f.m - 2)) | 1u) + 1u;          /* columns 0 .. (W - 1) | 1, as the forward pass laid them out */
+        A.si_last = f.si; A.n = f.n; A.m = f.m; A.c_si = -1; A.c_k = 0;
+        A.c_w[0] = A.c_w[1] = A.c_w[2] = A.c_w[3] = A.c_w[4] = 0;
+        OpSink sink; sink.buf = scratch; sink.cap = (uint32_t)min((uint64_t)0x7fffffff, top_w > scratch_w ? (top_w - scratch_w) / 2 : 0);
+        sink.n = 0; sink.cur_op = 0; sink.cur_n = 0; sink.overflow = false; sink.stride = 1;
+        back_trace_inl(A, P, f.n, f.m, f.minS, f.lastK, res, sink);
+        n_ops = sink.n;
+        if (sink.overflow) { status = ST_ARENA; n_ops = 0; }
+    }
+    __syncwarp();
+    group_emit(P, have, pair, status, res, n_ops, ScratchOps{scratch, 1u},
+               (unsigned long long)((slot_words - top_w + scratch_w) * 4 + 8ull * n_ops), f.c_cells, f.c_written, f.c_steps);
+}
+
 /* Backtraces (wfa.go:703-983) and results of the items of a WIDE launch, lane-parallel. */
 __global__ void __launch_bounds__(128)
 wide_finish_kernel(const KParams P)
@@ -421,7 +496,9 @@ wide_finish_kernel(const KParams P)
     f.status = ST_PENDING; f.minS = 0; f.lastK = 0; f.si = 0; f.n = f.m = 0; f.top = 0; f.c_cells = f.c_written = f.c_steps = 0; f.first_eq = false;
     uint32_t pair = 0;
     if (have) { f = P.wide_rec[item]; pair = P.work ? P.work[item] : item; }
-    finish_group_slim<3>(P, have, pair, f, P.arena + (uint64_t)(have ? item : 0u) * P.slot_bytes, P.slot_bytes);
+    uint8_t *slot = P.arena + (uint64_t)(have ? item : 0u) * P.slot_bytes;
+    if (!P.global_aln) finish_group_wide_semi(P, have, pair, f, slot, P.slot_bytes);
+    else finish_group_slim<3>(P, have, pair, f, slot, P.slot_bytes);
 }
 
 } /* namespace wfak */
