@@ -8,7 +8,8 @@ from wfa_b200 import api
 
 @pytest.mark.parametrize("n,c,levels", [(1_000_000, 66_674, 2), (340_000, 53_333, 2), (1_000_003, 66_674, 3),
                                          (2_000_000, 100_000, 1), (399_999, 53_333, 0), (1_000_000, 66_674, -1),
-                                         (150_000, 53_333, 2), (70_000, 32_768, 2), (5, 66_674, 2), (0, 66_674, 2)])
+                                         (150_000, 53_333, 2), (70_000, 32_768, 2), (5, 66_674, 2), (0, 66_674, 2),
+                                         (1_250, 320, 2), (10_000, 2_528, 2), (256, 64, 2)])      # a few hundred long pairs: four chunks side by side
 def test_chunk_plan_properties(built_lib, n, c, levels):
     cuts = api.chunk_plan(n, c, levels).astype(np.int64)
     assert cuts[0] == 0 and cuts[-1] == n
@@ -30,3 +31,5 @@ def test_chunk_plan_properties(built_lib, n, c, levels):
         assert mid.max() - mid.min() <= 64                                                  # equal middle chunks
     else:
         assert sizes.max() - sizes.min() <= 64 or len(sizes) == 1
+    if c < 32768 and n >= 256:
+        assert len(sizes) == 4, sizes                              # the long-pair rule of wfacuda_align_batch: chunk = ceil(n / 4) rounded up to 32
