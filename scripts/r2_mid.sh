@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 TAG=${1:-mid1}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -4 $OUT/pytest_gpu.log
-for c in "cfg2_150bp_e5_global 1000000" "cfg3_1kbp_e10_global_adaptive 1000000" "cfg5_100kbp_e15_global_adaptive 1250"; do set -- $c
+for c in "cfg2_150bp_e5_global 1000000" "cfg3_1kbp_e10_global_adaptive 1000000" "cfg5_100kbp_e15_global_adaptive 1250" "cfg4_10kbp_in_12kbp_e5_semiglobal 296"; do set -- $c
 timeout 600 python bench.py --workload $1 --pairs $2 --steps 3 --warmup 3 --only-headline --no-cpu-baseline > $OUT/bench_$1.json 2> $OUT/bench_$1.err
 python - <<PY
 import json

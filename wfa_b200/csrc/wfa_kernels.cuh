@@ -175,6 +175,17 @@ __device__ __forceinline__ int lcp(const SeqView<BITS, SM> &Q, const SeqView<BIT
     return l < maxl ? l : maxl;
 }
 
+/* Bases matched by a 16-base compare: half the number of trailing zero bits of the XOR of the two chunks, 16 when they
+ * agree.  popc((x - 1) & ~x) counts the trailing zeros and is 32 for x = 0 by itself; the decrement goes through an asm
+ * statement so that the compiler does not recognise a count-trailing-zeros and wrap it into its guarded sequence for
+ * x = 0 (two more instructions in the innermost loop of every worker). */
+__device__ __forceinline__ int matched_bases(uint32_t x)
+{
+    uint32_t t;
+    asm("add.u32 %0, %1, -1;" : "=r"(t) : "r"(x));
+    return __popc(t & ~x) >> 1;
+}
+
 /* ------------------------------------------------------------------ next
  * One diagonal of wfa.go:572-699.  Inputs are raw source words (0 = absent):
  *   mo_l = M[s-o-e][k-1]  ie_l = I[s-e][k-1]

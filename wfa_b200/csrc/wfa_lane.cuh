@@ -345,12 +345,12 @@ __device__ __forceinline__ void lane_stage(const KParams &P, const int stg, cons
             auto cell_b = [&](Pend &q, const int k) {
                 /* bases matched by the first compare: index of the lowest differing bit pair, 16 when
                  * there is none (brev(0) = 0 has 32 leading zeros).  ext = 0 adds nothing. */
-                int l = __clz((int)__brev(q.xr)) >> 1;
+                int l = matched_bases(q.xr);
                 if (l == 16 && q.ext > 16) {
                     const int h = (int)q.c.M, v = h - k;
                     while (l < q.ext) {
                         const uint32_t xx = lane_chunk(sQ, v + l) ^ lane_chunk(sT, h + l);
-                        if (xx) { l += __clz((int)__brev(xx)) >> 1; break; }
+                        if (xx) { l += matched_bases(xx); break; }
                         l += 16;
                     }
                 }

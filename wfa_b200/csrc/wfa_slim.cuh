@@ -174,11 +174,11 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
              * addresses wrap inside the ring; an absent cell or one at the end of a sequence advances by 0),
              * so the common case is straight-line code for all lanes */
             const uint32_t xx = Q.chunk((uint32_t)v) ^ T.chunk((uint32_t)h);
-            int l = __clz((int)__brev(xx)) >> 1;                                /* 16 when all 16 bases agree */
+            int l = matched_bases(xx);                                /* 16 when all 16 bases agree */
             if (l >= 16 && ext > 16) {
                 do {
                     const uint32_t x2 = Q.chunk((uint32_t)(v + l)) ^ T.chunk((uint32_t)(h + l));
-                    if (x2) { l += __clz((int)__brev(x2)) >> 1; break; }
+                    if (x2) { l += matched_bases(x2); break; }
                     l += 16;
                 } while (l < ext);
             }
@@ -191,11 +191,11 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
         if ((uint32_t)v < Q.wbase * 16u || (uint32_t)h < T.wbase * 16u) { slow = true; return M; }
         const int lim = min(ext, min((int)(Q.wend * 16u) - v, (int)(T.wend * 16u) - h));       /* > 0 only if both chunks start inside */
         if (lim <= 0) { slow = true; return M; }
-        int l = __clz((int)__brev(xx)) >> 1;                                    /* 16 when all 16 bases agree */
+        int l = matched_bases(xx);                                    /* 16 when all 16 bases agree */
         if (l >= 16 && lim > 16) {
             do {
                 const uint32_t x2 = Q.chunk((uint32_t)(v + l)) ^ T.chunk((uint32_t)(h + l));
-                if (x2) { l += __clz((int)__brev(x2)) >> 1; break; }
+                if (x2) { l += matched_bases(x2); break; }
                 l += 16;
             } while (l < lim);
         }
@@ -210,7 +210,7 @@ __device__ __forceinline__ FwdOut forward_slim(const KParams &P, const uint32_t 
         int l = 0;
         do {
             const uint32_t xx = Q.chunk_global((uint32_t)(v + l)) ^ T.chunk_global((uint32_t)(h + l));
-            if (xx) { l += __clz((int)__brev(xx)) >> 1; break; }
+            if (xx) { l += matched_bases(xx); break; }
             l += 16;
         } while (l < ext);
         return M + (uint32_t)min(l, ext);

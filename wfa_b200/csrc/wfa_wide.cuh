@@ -236,11 +236,11 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
                 const int ext = (int)min(j + 1u, um) - (int)M;                  /* min(n + k, m) - M */
                 const uint32_t v = min((uint32_t)((int)M - k), (uint32_t)nm1);
                 const uint32_t xx = Q.chunk(v) ^ Tq.chunk(M);
-                int l = __clz((int)__brev(xx)) >> 1;                            /* 16 when all 16 bases agree */
+                int l = matched_bases(xx);                            /* 16 when all 16 bases agree */
                 if (l >= 16 && ext > 16) {
                     do {
                         const uint32_t x2 = Q.chunk(v + (uint32_t)l) ^ Tq.chunk(M + (uint32_t)l);
-                        if (x2) { l += __clz((int)__brev(x2)) >> 1; break; }
+                        if (x2) { l += matched_bases(x2); break; }
                         l += 16;
                     } while (l < ext);
                 }
