@@ -39,7 +39,7 @@
 namespace wfak {
 
 constexpr uint32_t WIDE_MAX_M = 65534;            /* offsets up to m + 1 must fit 16 bits */
-constexpr uint32_t WIDE_HEAD_BYTES = 1280;        /* mailboxes 512 + reduction scratch 640 + work item 16, padded */
+constexpr uint32_t WIDE_HEAD_BYTES = 1280;        /* mailboxes 512 + reduction scratch 640 + work item 16 + the record keeper's 56 bytes, padded */
 constexpr int WIDE_MAX_CLUSTER = 8;
 
 /* shared memory of one CTA: head, 9 ring rows of seg + 4 16-bit columns (two halo columns on either
@@ -139,11 +139,10 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
     keep(Q.sa); keep(Tq.sa);                                   /* (opaque: not to be re-derived from the kernel parameters inside the cell loop) */
     cluster_sync_all();                                        /* nobody pushes a halo cell into a ring that is still being cleared */
 
-    SlimHdr *hdrs = reinterpret_cast<SlimHdr *>(slot);         /* grows up, index s/g */
+    /* slot: headers (SlimHdr, index s/g) grow up from its start, rows grow down from its end */
     CellT   *cells = reinterpret_cast<CellT *>(slot);          /* rows grow down from the end */
     const uint32_t slot_cells = (uint32_t)min(slot_bytes / sizeof(CellT), (uint64_t)0xfffffff0u) & ~1u;
     uint32_t top = slot_cells;
-    long long room = (long long)slot_cells - (long long)(3 * HDR_CELLS + 8);
 
     const int nm1 = n - 1;
     uint32_t base_j = rank * SEG;                              /* first column of this CTA's segment */
@@ -151,12 +150,18 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
     const int ilo = SEMI ? -nm1 : 0, ihi = SEMI ? m - 1 : 0;   /* init cells, wfa.go:155-183 */
     const bool edgeL = rank > 0, edgeR = rank + 1u < C;        /* the segment has a neighbour on that side: its first / last column pair needs halo cells */
 
-    unsigned long long c_cells = 0, c_written = 0, c_steps = 0;
-    int status = ST_OK, si = -1, lastK = Ak, si_final = 0;
-    uint32_t minS = 0, top_final = slot_cells;
+    /* What only the record keeper (thread 0 of CTA 0) needs -- work counters, the last existing row, where the
+     * backtrace starts, the previous row's place in the slot -- lives in its shared memory, not in 2 048 threads'
+     * registers (the cell loop runs at the 64-register limit; what spills is re-read after every cluster barrier,
+     * which invalidates L1). */
+    struct Keep { unsigned long long c_cells, c_written, c_steps; uint32_t top_final, minS; int si_final, lastK; uint32_t p_off, p_ja, p_aw; };
+    Keep *K = reinterpret_cast<Keep *>(__cvta_shared_to_generic((size_t)(sbase + 1168u)));
+    const bool keeper = rank == 0 && tid == 0;
+    if (keeper) { K->c_cells = K->c_written = K->c_steps = 0; K->top_final = slot_cells; K->minS = 0; K->si_final = 0; K->lastK = Ak; K->p_off = K->p_ja = K->p_aw = 0; }
+    int status = ST_OK, si = -1;
     uint32_t slotM = 4;                                        /* ring slot of row si (si mod 5), advanced incrementally */
     /* the previous row, whose reductions are still on their way */
-    bool pending = false; uint32_t p_off = 0, p_ja = 0, p_aw = 0;
+    bool pending = false;
 
     for (;;) {
         si++;
@@ -165,8 +170,8 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
         const int lo = SEMI ? -nm1 : max(-si, -nm1), hi = SEMI ? m - 1 : min(si, m - 1);
         const uint32_t ja = (uint32_t)(lo + nm1) & ~1u, jb = (uint32_t)(hi + nm1) | 1u;       /* even / odd: whole column pairs */
         const uint32_t aw = jb - ja + 1u;
-        room -= (long long)(HDR_CELLS + aw);
-        if (room < 0) { if (pending) cluster_wait(); status = ST_ARENA; break; }
+        /* room between the headers (growing up: this row's, two spare, some slack) and the rows (growing down) */
+        if (top < aw + (uint32_t)(si + 4) * HDR_CELLS + 8u) { if (pending) cluster_wait(); status = ST_ARENA; break; }
         const uint32_t off = top - aw;
         /* this CTA's share: column pairs c (columns base_j + 2c, + 1), c in [cl, ch]; the pairs next to a
          * neighbouring segment wait for the halo cells (after the barrier of the previous row) */
@@ -203,6 +208,7 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
              * tests pass and the recurrence is I = max + 1, D = max, M = max(M[s-x] + 1, I, D) on present sources,
              * which sm_100a does on both halves at once (VIMNMX.U16x2, VIADD.16x2); otherwise cell by cell. */
             Cell3O c0, c1;
+            uint32_t Iw, Dw;                                                    /* I and D of both cells as they go to the ring */
             {
                 const uint32_t L2 = __byte_perm(a, b, 0x5432), I2 = __byte_perm(ia, ib, 0x5432);      /* M[s-o-e][k-1], I[s-e][k-1] */
                 const uint32_t R2 = __byte_perm(b, d, 0x5432), D2 = __byte_perm(db, dd, 0x5432);      /* M[s-o-e][k+1], D[s-e][k+1] */
@@ -212,10 +218,11 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
                     const uint32_t Iw2 = __vadd2(mi, __vminu2(mi, 0x00010001u));                        /* + 1 where present */
                     const uint32_t Ew2 = __vadd2(xm, __vminu2(xm, 0x00010001u));
                     const uint32_t Mw2 = __vmaxu2(__vmaxu2(Ew2, Iw2), md);
-                    c0.M = Mw2 & 0xffffu; c1.M = Mw2 >> 16; c0.I = Iw2 & 0xffffu; c1.I = Iw2 >> 16; c0.D = md & 0xffffu; c1.D = md >> 16;
+                    c0.M = Mw2 & 0xffffu; c1.M = Mw2 >> 16; Iw = Iw2; Dw = md;
                 } else {
                     c0 = next_off3(a >> 16, ia >> 16, b >> 16, db >> 16, xm & 0xffffu, um, j0 + 1u);
                     c1 = next_off3(b & 0xffffu, ib & 0xffffu, d & 0xffffu, dd & 0xffffu, xm >> 16, act1 ? um : 0u, act1 ? j0 + 2u : 0u);
+                    Iw = c0.I | c1.I << 16; Dw = c0.D | c1.D << 16;
                 }
             }
             const int k0 = (int)j0 - nm1;
@@ -260,7 +267,7 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
             };
             c0.M = extend(c0.M, j0, k0);
             c1.M = extend(c1.M, j0 + 1u, k0 + 1);
-            const uint32_t Mw = c0.M | c1.M << 16, Iw = c0.I | c1.I << 16, Dw = c0.D | c1.D << 16;
+            const uint32_t Mw = c0.M | c1.M << 16;
             sts_u32(bMc + wa, Mw);
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(bEc + 2u * wa), "r"(Iw), "r"(Dw) : "memory");
             /* arena: two 8-byte cells {M | I << 16, D}, one 128-bit store */
@@ -289,19 +296,19 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
                     if (g3 != INT_MIN && (g3 & 1)) { hit = true; hitK = (g3 >> 1) - n; }
                     if (g4 != INT_MAX && (g4 & 1)) { hit = true; hitK = (g4 >> 1) - n; }
                 }
-                if (rank == 0 && tid == 0) {
-                    /* the record keeper: header of the row, work counters, where the backtrace starts */
+                if (keeper) {
+                    /* header of the row, work counters, where the backtrace starts */
                     const int wlo = g0 - nm1, whi = g1 - nm1;
                     int4 hc = make_int4(0, 1, 0, 0);
-                    c_written += p_aw;
+                    K->c_written += K->p_aw;
                     if (exists) {
-                        c_steps++; c_cells += (unsigned long long)(whi - wlo + 1);
-                        hc = make_int4((int)p_ja - nm1, wlo, whi, (int)p_off);
-                        top_final = p_off;
+                        K->c_steps++; K->c_cells += (unsigned long long)(whi - wlo + 1);
+                        hc = make_int4((int)K->p_ja - nm1, wlo, whi, (int)K->p_off);
+                        K->top_final = K->p_off;
                     }
-                    *reinterpret_cast<int4 *>(hdrs + (si - 1)) = hc;
-                    si_final = si - 1;
-                    if (exists && (endhit || hit)) { minS = (uint32_t)(si - 1) * P.g; lastK = SEMI && hit ? hitK : Ak; }
+                    *reinterpret_cast<int4 *>(reinterpret_cast<SlimHdr *>(slot) + (si - 1)) = hc;
+                    K->si_final = si - 1;
+                    if (exists && (endhit || hit)) { K->minS = (uint32_t)(si - 1) * P.g; K->lastK = SEMI && hit ? hitK : Ak; }
                 }
                 if (exists && (endhit || (SEMI && hit))) return true;
             }
@@ -370,12 +377,16 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
         /* arrive now, wait in the middle of the next row: halos (their writers' fences) and mailboxes are
          * in place everywhere once the barrier completes */
         cluster_arrive_relaxed();
-        pending = true; p_off = off; p_ja = ja; p_aw = aw;
+        pending = true;
+        if (keeper) { K->p_off = off; K->p_ja = ja; K->p_aw = aw; }
         top = off;
     }
 
-    f.status = status; f.minS = minS; f.lastK = lastK; f.si = si_final; f.top = (uint64_t)top_final;
-    f.c_cells = c_cells; f.c_written = c_written; f.c_steps = c_steps;
+    f.status = status;
+    if (keeper) {
+        f.minS = K->minS; f.lastK = K->lastK; f.si = K->si_final; f.top = (uint64_t)K->top_final;
+        f.c_cells = K->c_cells; f.c_written = K->c_written; f.c_steps = K->c_steps;
+    }
     return f;
 }
 
