@@ -39,7 +39,7 @@
 namespace wfak {
 
 constexpr uint32_t WIDE_MAX_M = 65534;            /* offsets up to m + 1 must fit 16 bits */
-constexpr uint32_t WIDE_HEAD_BYTES = 1280;        /* mailboxes 512 + reduction scratch 640 + work item 16 + the record keeper's 56 bytes, padded */
+constexpr uint32_t WIDE_HEAD_BYTES = 1280;        /* mailboxes 512 + reduction scratch 640 + work item 16 + the record keeper's 56 bytes + row flags 24, padded */
 constexpr int WIDE_MAX_CLUSTER = 8;
 
 /* shared memory of one CTA: head, 9 ring rows of seg + 4 16-bit columns (two halo columns on either
@@ -136,6 +136,9 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(Tq.sa + j * 8u), "r"(a), "r"(b) : "memory");
         }
     }
+    /* per row parity: {scan (a) key, scan (b) key, end test} -- written by the few cells that reach the end of a sequence */
+    const uint32_t sFlags = sbase + 1224u;
+    if (tid == 0) for (uint32_t q = 0; q < 2; q++) { sts_u32(sFlags + q * 12u, (uint32_t)INT_MIN); sts_u32(sFlags + q * 12u + 4u, (uint32_t)INT_MAX); sts_u32(sFlags + q * 12u + 8u, 0u); }
     keep(Q.sa); keep(Tq.sa);                                   /* (opaque: not to be re-derived from the kernel parameters inside the cell loop) */
     cluster_sync_all();                                        /* nobody pushes a halo cell into a ring that is still being cleared */
 
@@ -188,7 +191,8 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
         keep(bM4); keep(bM2); keep(bMc); keep(bE1); keep(bEc);                 /* (not to be re-derived inside the cell loop) */
         uint4 *grow = reinterpret_cast<uint4 *>(cells + off - ja + base_j);     /* column pair c of this CTA at grow[c] */
         keep_ptr(grow);
-        int pmin = INT_MAX, pmax = INT_MIN, ka = INT_MIN, kb = INT_MAX;         /* pmin / pmax: first / last column PAIR with a present cell */
+        int pmin = INT_MAX, pmax = INT_MIN;                                     /* first / last column PAIR with a present cell */
+        const uint32_t sF = sFlags + (uint32_t)(si & 1) * 12u;
 
         /* one column pair: next (wfa.go:572-699) + extend (wfa.go:394-455) of its two cells, stores */
         auto cellpair = [&](const int c, auto initc) {
@@ -252,15 +256,21 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
                     } while (l < ext);
                 }
                 const uint32_t Mn = M ? M + (uint32_t)max(min(l, ext), 0) : 0u;
-                if (SEMI && M != 0u && l >= ext) {
-                    /* the cell has reached the end of a sequence: start-cell classification (wfa.go:306-323 / :341-358) */
-                    const int h = (int)Mn, vv = h - k;
-                    int cls = 0;
-                    if (vv <= 0 || vv > n || h > m) cls = 1;
-                    else if ((vv == n && h >= n) || (h == m && vv >= m)) cls = 2;
-                    if (cls) {
-                        const int key = (k + n) * 2 + (cls == 2);
-                        if (k <= Ak) ka = max(ka, key); else kb = min(kb, key);
+                if (M != 0u && l >= ext) {
+                    /* The cell has reached the end of a sequence -- the only cells that can pass the end test on
+                     * diagonal m - n (wfa.go:235-239: offset >= m) or count in the start-cell search (wfa.go:306-323 /
+                     * :341-358); they post to the row's flags in shared memory, nobody else pays for either test. */
+                    if (k == Ak && Mn >= um) sts_u32(sF + 8u, 1u);
+                    if (SEMI) {
+                        const int h = (int)Mn, vv = h - k;
+                        int cls = 0;
+                        if (vv <= 0 || vv > n || h > m) cls = 1;
+                        else if ((vv == n && h >= n) || (h == m && vv >= m)) cls = 2;
+                        if (cls) {
+                            const int key = (k + n) * 2 + (cls == 2);
+                            if (k <= Ak) asm volatile("red.shared.max.s32 [%0], %1;" :: "r"(sF), "r"(key) : "memory");
+                            else asm volatile("red.shared.min.s32 [%0], %1;" :: "r"(sF + 4u), "r"(key) : "memory");
+                        }
                     }
                 }
                 return Mn;
@@ -334,43 +344,27 @@ __device__ __forceinline__ FwdOut forward_wide(const KParams &P, const uint32_t 
         const bool done = has_init ? run(std::true_type{}) : run(std::false_type{});
         if (done) break;
 
-        /* ---- this row's reductions: exact first / last present column from the thread's own pair words,
-         * end test on diagonal m - n = column m - 1 (wfa.go:235-239) by the thread that wrote it */
+        /* ---- this row's reductions: exact first / last present column from the thread's own pair words; the end
+         * test and the start-cell keys are in the row's flags already */
         int cmin = INT_MAX, cmax = INT_MIN;
         if (pmin <= pmax) {
             const uint32_t w0 = lds_u32(bMc + 4u * (uint32_t)pmin + 4u), w1 = lds_u32(bMc + 4u * (uint32_t)pmax + 4u);
             cmin = (int)base_j + 2 * pmin + ((w0 & 0xffffu) ? 0 : 1);
             cmax = (int)base_j + 2 * pmax + ((w1 >> 16) ? 1 : 0);
         }
-        bool endhit = false;
-        {
-            /* the thread that computed column m - 1 reads its own store */
-            const int cA = (int)(((uint32_t)m - 1u) >> 1) - (int)(base_j >> 1);
-            bool mine;
-            if (doL && cA == 0) mine = wid == nw - 1u && lane == 0;
-            else if (doR && cA == (int)HALF - 1) mine = wid == nw - 1u && lane == 1;
-            else mine = cA >= c_first && cA <= c_last && tid == (uint32_t)(cA - c_first) % T;
-            if (mine) endhit = lds_u16(bMc + 4u + ((uint32_t)m - 1u - base_j) * 2u) >= (uint32_t)m;
-        }
         cmin = __reduce_min_sync(0xffffffffu, cmin); cmax = __reduce_max_sync(0xffffffffu, cmax);
-        const uint32_t eh = __any_sync(0xffffffffu, endhit) ? 1u : 0u;
-        if (SEMI) { ka = __reduce_max_sync(0xffffffffu, ka); kb = __reduce_min_sync(0xffffffffu, kb); }
-        if (lane == 0) {
-            sts_u32(sRed + wid * 4u, (uint32_t)cmin); sts_u32(sRed + 128u + wid * 4u, (uint32_t)cmax); sts_u32(sRed + 256u + wid * 4u, eh);
-            if (SEMI) { sts_u32(sRed + 384u + wid * 4u, (uint32_t)ka); sts_u32(sRed + 512u + wid * 4u, (uint32_t)kb); }
-        }
+        if (lane == 0) { sts_u32(sRed + wid * 4u, (uint32_t)cmin); sts_u32(sRed + 128u + wid * 4u, (uint32_t)cmax); }
         __syncthreads();
         if (wid == 0) {
             int a0 = lane < nw ? (int)lds_u32(sRed + lane * 4u) : INT_MAX, a1 = lane < nw ? (int)lds_u32(sRed + 128u + lane * 4u) : INT_MIN;
-            uint32_t a2 = lane < nw ? lds_u32(sRed + 256u + lane * 4u) : 0u;
-            int a3 = INT_MIN, a4 = INT_MAX;
-            if (SEMI) { a3 = lane < nw ? (int)lds_u32(sRed + 384u + lane * 4u) : INT_MIN; a4 = lane < nw ? (int)lds_u32(sRed + 512u + lane * 4u) : INT_MAX; }
-            a0 = __reduce_min_sync(0xffffffffu, a0); a1 = __reduce_max_sync(0xffffffffu, a1); a2 = __reduce_or_sync(0xffffffffu, a2);
-            if (SEMI) { a3 = __reduce_max_sync(0xffffffffu, a3); a4 = __reduce_min_sync(0xffffffffu, a4); }
+            a0 = __reduce_min_sync(0xffffffffu, a0); a1 = __reduce_max_sync(0xffffffffu, a1);
+            const uint32_t a3 = lds_u32(sF), a4 = lds_u32(sF + 4u), a2 = lds_u32(sF + 8u);
+            __syncwarp();
+            if (lane == 0) { sts_u32(sF, (uint32_t)INT_MIN); sts_u32(sF + 4u, (uint32_t)INT_MAX); sts_u32(sF + 8u, 0u); }      /* free for the row after the next */
             if (lane < C) {
                 const uint32_t dst = cluster_map(sMail + (uint32_t)(si & 1) * 256u + rank * 32u, lane);
                 st_cluster_u32(dst, (uint32_t)a0); st_cluster_u32(dst + 4u, (uint32_t)a1); st_cluster_u32(dst + 8u, a2);
-                st_cluster_u32(dst + 12u, (uint32_t)a3); st_cluster_u32(dst + 16u, (uint32_t)a4);
+                st_cluster_u32(dst + 12u, a3); st_cluster_u32(dst + 16u, a4);
                 cluster_fence();
             }
         }
