@@ -50,7 +50,7 @@ WORKLOAD_TEXT = {
 CPU_SAMPLE = {"cfg2_150bp_e5_global": 400_000, "cfg3_1kbp_e10_global_adaptive": 40_000,
               "cfg4_10kbp_in_12kbp_e5_semiglobal": 4, "cfg5_100kbp_e15_global_adaptive": 32}
 # pairs per GPU and step when a workload is a row of `configs` (None: the config's full size;
-# config 4 needs 0.4 GB of backtrace arena per pair, config 5 is one config cut into N shards)
+# config 4 writes 0.27 GB of backtrace arena per pair (8 B per cell; 12 B in round 1), config 5 is one config cut into N shards)
 SIDE_PAIRS = {"cfg3_1kbp_e10_global_adaptive": None, "cfg4_10kbp_in_12kbp_e5_semiglobal": 296,
               "cfg5_100kbp_e15_global_adaptive": "strong"}
 KERNEL_SOURCES = ("wfa_kernels.cuh", "wfa_lane.cuh", "wfa_slim.cuh", "wfa_wide.cuh")
@@ -468,7 +468,7 @@ def main():
             if SIDE_PAIRS.get(wl) == "strong":
                 r["scaling"] = "strong (the 10 000 pairs of the config cut into %d shards)" % world
             elif isinstance(SIDE_PAIRS.get(wl), int):
-                r["bounded"] = "%d of the config's %d pairs per step (0.4 GB of backtrace arena per pair)" % (SIDE_PAIRS[wl], datagen.CONFIGS[wl]["pairs"])
+                r["bounded"] = "%d of the config's %d pairs per step (0.27 GB of backtrace arena per pair)" % (SIDE_PAIRS[wl], datagen.CONFIGS[wl]["pairs"])
             configs[wl] = r
         # CPU port beside every GPU number, on this box's cores (bounded samples), at every N
         if not args.no_cpu_baseline:
