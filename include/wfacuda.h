@@ -237,6 +237,15 @@ int wfacuda_shard_plan(int n_shards, uint64_t n_pairs, const uint32_t *q_len, co
 int wfacuda_chunk_plan(uint64_t n_pairs, uint64_t chunk_pairs, int tail_levels,
                        uint64_t *cuts, uint32_t cuts_capacity, uint32_t *n_cuts);
 
+/* Geometry of a WIDE launch (one thread-block cluster per pair, the live wavefront rows as 16-bit offsets in
+ * the cluster's shared memory -- replaces the Component / WaveFront store of wfa_component.go:37-41 for the
+ * scores still needed): for pairs whose widest wavefront spans `max_diagonals` = n + m - 1 diagonals and whose
+ * sequences need `seq_entries` 8-byte window entries, with `smem_per_cta` bytes of shared memory per CTA:
+ * the cluster size (1, 2, 4, 8), diagonals per CTA, threads per CTA and shared-memory bytes per CTA.
+ * Returns WFACUDA_E_INVALID when eight CTAs cannot hold the rows (such pairs go to the CTA worker).  Pure host logic. */
+int wfacuda_wide_plan(uint64_t max_diagonals, uint32_t seq_entries, uint64_t smem_per_cta,
+                      int *cluster_ctas, uint32_t *diagonals_per_cta, int *threads, uint64_t *smem_bytes);
+
 /* Page-locked host memory for the caller's input / output arrays.  Every entry point accepts
  * any host pointer; arrays that live in memory from wfacuda_host_alloc (or registered with
  * wfacuda_host_register) are moved by the DMA engines directly, without the staging copy

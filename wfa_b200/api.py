@@ -102,7 +102,7 @@ EXPORTS = ["wfacuda_device_count", "wfacuda_create", "wfacuda_destroy", "wfacuda
            "wfacuda_batch_download", "wfacuda_batch_ops_total", "wfacuda_batch_free",
            "wfacuda_align_batch_multi", "wfacuda_shard_plan", "wfacuda_shard_assign", "wfacuda_get_stats", "wfacuda_last_error",
            "wfacuda_host_alloc", "wfacuda_host_free", "wfacuda_host_register", "wfacuda_host_unregister",
-           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components", "wfacuda_measure_issue_peak", "wfacuda_chunk_plan"]
+           "wfacuda_batch_render", "wfacuda_last_render_total", "wfacuda_align_components", "wfacuda_measure_issue_peak", "wfacuda_chunk_plan", "wfacuda_wide_plan"]
 
 _LIB = None
 
@@ -145,6 +145,8 @@ def load_library():
     L.wfacuda_align_components.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, vp, vp, u64, vp, C.c_uint32, vp, vp, u64, vp]
     L.wfacuda_align_batch_multi.restype = C.c_int
     L.wfacuda_align_batch_multi.argtypes = [C.POINTER(vp), C.c_int, u64, vp, vp, u32p, vp, u32p, vp, vp, u64, vp]
+    L.wfacuda_wide_plan.restype = C.c_int
+    L.wfacuda_wide_plan.argtypes = [u64, C.c_uint32, u64, vp, vp, vp, vp]
     L.wfacuda_chunk_plan.restype = C.c_int
     L.wfacuda_chunk_plan.argtypes = [u64, u64, C.c_int, vp, C.c_uint32, vp]
     L.wfacuda_shard_plan.restype = C.c_int
@@ -229,6 +231,13 @@ def chunk_plan(n_pairs, chunk_pairs, tail_levels=2):
     if rc != 0:
         raise WfaError("wfacuda_chunk_plan failed (%d)" % rc)
     return cuts[:n.value].copy()
+
+
+def wide_plan(max_diagonals, seq_entries, smem_per_cta=232448):
+    """Geometry of a WIDE launch (host logic only): (cluster CTAs, diagonals per CTA, threads per CTA, shared-memory bytes), or None."""
+    c, seg, th, sm = C.c_int(0), C.c_uint32(0), C.c_int(0), C.c_uint64(0)
+    rc = load_library().wfacuda_wide_plan(int(max_diagonals), int(seq_entries), int(smem_per_cta), C.byref(c), C.byref(seg), C.byref(th), C.byref(sm))
+    return None if rc != 0 else (c.value, seg.value, th.value, sm.value)
 
 
 def device_count():

@@ -747,17 +747,14 @@ int run_wide_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         if (to_cta) to_cta->insert(to_cta->end(), too_wide.begin(), too_wide.end());
         else if (!too_wide.empty()) return fail(ctx, WFACUDA_E_INVALID, "internal: WIDE class without a fallback");
         if (fit.empty()) break;
-        int C = 1; uint32_t seg = 0;
-        for (;; C *= 2) {
-            seg = (uint32_t)(((wmax + C - 1) / C + 63) & ~63ull);
-            if (wide_smem_bytes(seg, seq_ent) + head <= ctx->smem_optin || C == WIDE_MAX_CLUSTER) break;
-        }
+        int C = 1, threads = 0; uint32_t seg = 0; uint64_t smem64 = 0;
+        if (wfacuda_wide_plan(wmax, seq_ent, ctx->smem_optin, &C, &seg, &threads, &smem64) != 0) return fail(ctx, WFACUDA_E_INVALID, "internal: WIDE geometry");
         if (const char *e = getenv("WFACUDA_WIDE_CLUSTER")) {         /* testing: small pairs over several CTAs */
             C = std::max(1, std::min(WIDE_MAX_CLUSTER, atoi(e)));
             seg = (uint32_t)(((wmax + C - 1) / C + 63) & ~63ull);
+            threads = (int)std::min<uint32_t>(1024, std::max<uint32_t>(128, ((seg / 2 + 31) / 32) * 32));
         }
         const size_t smem = wide_smem_bytes(seg, seq_ent);
-        int threads = (int)std::min<uint32_t>(1024, std::max<uint32_t>(128, ((seg / 2 + 31) / 32) * 32));
         if (const char *e = getenv("WFACUDA_WIDE_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
         /* slots: 8-byte cells instead of the estimate's 12, one slot per pair of a sub-batch */
         uint64_t slot = (uint64_t)((double)need_max * (8.0 / 12.0) * ctx->arena_scale_wide / std::max(ctx->arena_scale, 1e-9) * boost);
@@ -1902,6 +1899,24 @@ static std::vector<uint64_t> plan_chunks(uint64_t n_pairs, uint64_t C, int tail_
     for (size_t j = 1; j < cuts.size(); j++) if (cuts[j] > out.back()) out.push_back(cuts[j]);
     if (out.back() != n_pairs) out.push_back(n_pairs);
     return out;
+}
+
+int wfacuda_wide_plan(uint64_t max_diagonals, uint32_t seq_entries, uint64_t smem_per_cta,
+                      int *cluster_ctas, uint32_t *diagonals_per_cta, int *threads, uint64_t *smem_bytes)
+{
+    if (!cluster_ctas || !diagonals_per_cta || !threads || !smem_bytes || max_diagonals == 0) return WFACUDA_E_INVALID;
+    const uint64_t head = (uint64_t)WIDE_HEAD_BYTES + 64;
+    for (int C = 1; C <= WIDE_MAX_CLUSTER; C *= 2) {
+        const uint64_t seg = ((max_diagonals + C - 1) / C + 63) & ~63ull;              /* whole warps of column pairs */
+        if (seg > 0xffffffc0ull) continue;
+        const uint64_t smem = wide_smem_bytes((uint32_t)seg, seq_entries);
+        if (smem + head <= smem_per_cta) {
+            *cluster_ctas = C; *diagonals_per_cta = (uint32_t)seg; *smem_bytes = smem;
+            *threads = (int)std::min<uint64_t>(1024, std::max<uint64_t>(128, ((seg / 2 + 31) / 32) * 32));
+            return 0;
+        }
+    }
+    return WFACUDA_E_INVALID;
 }
 
 int wfacuda_chunk_plan(uint64_t n_pairs, uint64_t chunk_pairs, int tail_levels, uint64_t *cuts, uint32_t cuts_capacity, uint32_t *n_cuts)
