@@ -34,8 +34,18 @@ while time.time() - t0 < budget:
                 t = bytes(rng.choice(alpha) for _ in range(rng.randint(0, 40))) + t + bytes(rng.choice(alpha) for _ in range(rng.randint(0, 40)))
         pairs.append((q, t))
     batch = datagen.Batch.from_pairs(pairs)
-    gpu, ref, st = parity.check(batch, what="fuzz %r" % (kw,), **kw)
+    # a third of the rounds on the wide-wavefront workers (WIDE clusters of a random size where they apply, else the CTA worker)
+    gpu_kw = {}
+    os.environ.pop("WFACUDA_WIDE_CLUSTER", None)
+    if rng.random() < 0.34:
+        from wfa_b200 import api
+        gpu_kw = dict(flags=api.FLAG_FORCE_CTA)
+        c = rng.choice([None, "1", "2", "4", "8"])
+        if c:
+            os.environ["WFACUDA_WIDE_CLUSTER"] = c
+    gpu, ref, st = parity.check(batch, what="fuzz %r %r cluster %s" % (kw, gpu_kw, os.environ.get("WFACUDA_WIDE_CLUSTER")), gpu_kw=gpu_kw, **kw)
+    wide_rounds = globals().get("wide_rounds", 0) + (1 if st.get("pairs_wide", 0) else 0)
     if kw["global_alignment"]:      # semi-global stops at the first score with a start-cell hit: fewer cells than the literal scan
         assert st["cells"] == ref[3]["cells"], (kw, st["cells"], ref[3]["cells"])
     rounds += 1; pairs_done += len(pairs)
-print("fuzz ok: %d rounds, %d pairs in %.0f s" % (rounds, pairs_done, time.time() - t0))
+print("fuzz ok: %d rounds (%d of them with pairs on the WIDE worker), %d pairs in %.0f s" % (rounds, globals().get("wide_rounds", 0), pairs_done, time.time() - t0))

@@ -55,7 +55,7 @@ for wl in ("cfg5_100kbp_e15_global_adaptive", "cfg2_150bp_e5_global"):
         m = m["multi_entry"]
         w("| %s | %s | %d | %.2f / %.2f | %.4g | %s |" % (wl, m["entry"].split(", ")[-1], m["pairs"], m["ms_per_call_mean"], m["ms_per_call_min"], m["value"], m["pairs_per_device"]))
 if tr:
-    w("\nOne process per GPU under torchrun (`scripts/r2_multi.sh`; config 2, 1 M pairs per GPU and step; kernels of config 2 unchanged since), with the box's measured PCIe ceiling (`scripts/pcie_ceiling.py`: N concurrent streams moving the e2e path's bytes per million pairs, page-locked):\n")
+    w("\nOne process per GPU under torchrun (`scripts/r2_multi.sh`; config 2, 1 M pairs per GPU and step; N > 1 measured earlier in the round: the config-2 kernels changed by less than 1 % since), with the box's measured PCIe ceiling (`scripts/pcie_ceiling.py`: N concurrent streams moving the e2e path's bytes per million pairs, page-locked):\n")
     w("| N | device-resident alignments/s | e2e alignments/s | e2e ms per step (mean) | PCIe ceiling of the box (pairs/s) | e2e / ceiling |")
     w("|---|---|---|---|---|---|")
     ceil = {}
