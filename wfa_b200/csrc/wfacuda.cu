@@ -779,8 +779,11 @@ int run_wide_class(wfacuda_ctx *ctx, wfacuda_batch *b, const std::vector<uint32_
         lc.gridDim = dim3((unsigned)C);
         int max_clusters = 0;
         if (cudaOccupancyMaxActiveClusters(&max_clusters, kfn, &lc) != cudaSuccess || max_clusters < 1) {
+            /* no such cluster can be resident on this device (partitioned GPU, other tenants' shared memory ...): the CTA worker takes the pairs */
             cudaGetLastError();
-            return fail(ctx, WFACUDA_E_CUDA, "WIDE kernel: a cluster of %d CTAs x %d threads with %zu bytes of shared memory cannot be resident", C, threads, smem);
+            if (!to_cta) return fail(ctx, WFACUDA_E_CUDA, "WIDE kernel: a cluster of %d CTAs x %d threads with %zu bytes of shared memory cannot be resident", C, threads, smem);
+            to_cta->insert(to_cta->end(), fit.begin(), fit.end());
+            break;
         }
         std::vector<uint32_t> again;
         bool ops_full = false, arena_full = false;
