@@ -5,7 +5,7 @@ bench.py quotes them in `roofline.traffic` / `roofline_int32.executed_*` -- stam
 so that bench.py stops quoting them the moment a kernel changes.
 A launch list holds every launch of one short bench run (3 warm-up steps, 1 timed step, the e2e and api legs): runs of
 the batch are told apart by their pack launch, and the full-size steady-state ones averaged.
-   make_roofline_r2.py <tag>"""
+   make_roofline_r2.py <tag> [note]"""
 import collections, csv, hashlib, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1]
@@ -20,7 +20,8 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us":
 h = hashlib.sha256()
 for f in SOURCES:
     h.update(open(os.path.join(ROOT, "wfa_b200", "csrc", f), "rb").read())
-out = {"source": "ncu per-launch counters, gpurun_out/%s (scripts/r2_capture.sh; profiles/r2_launches.md)" % tag,
+note = sys.argv[2] if len(sys.argv) > 2 else None          # e.g. what changed in the sources since the capture without changing the machine code
+out = {"source": "ncu per-launch counters, gpurun_out/%s (scripts/r2_capture.sh; profiles/r2_launches.md)%s" % (tag, "; " + note if note else ""),
        "kernel_source_sha": h.hexdigest()[:16], "workloads": {}}
 for short, (wl, pairs, names) in CLASS.items():
     path = os.path.join(src, "launches_%s.csv" % short)

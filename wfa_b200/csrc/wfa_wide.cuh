@@ -17,18 +17,21 @@
  *     (st.shared::cluster), and one cluster barrier per score makes them visible;
  *   - the same barrier carries the row's reductions (first / last present diagonal, end test,
  *     start-cell search): every CTA posts its partial results into every CTA's mailbox before
- *     arriving, so all CTAs take the same decision without a second round;
+ *     arriving, so all CTAs take the same decision without a second round -- and, rows being computed
+ *     over ranges that depend on the score alone, that decision is only needed one row later: the
+ *     barrier of a row overlaps the first cells of the next;
  *   - a thread handles two neighbouring diagonals per step (one 32-bit shared-memory word per row),
- *     only offsets are computed (codes re-derived by the backtrace, as in the LANE / SLIM classes),
- *     both sequences are read through shared-memory windows (one LDS.64 + one funnel shift per
- *     16-base compare), and the arena gets ONE 64-bit word per cell (M | I << 21 | D << 42, the
- *     SLIM worker's wide cell): 8 instead of 12 bytes per cell, written once with 128-bit stores,
- *     never read by the forward pass;
- *   - Lo/Hi, the end test (wfa.go:235-239) and the semi-global start-cell test (wfa.go:270-375,
- *     early-stop form) are taken on the way; there is no second pass over a row.
+ *     only offsets are computed (codes re-derived by the backtrace, as in the LANE / SLIM classes) --
+ *     for both cells at once on 16-bit halves (VIMNMX.U16x2 / VIADD.16x2) wherever no source reaches
+ *     a bound; both sequences are read through shared-memory windows (one LDS.64 + one funnel shift
+ *     per 16-base compare), and the arena gets ONE 64-bit word per cell (M | I << 16 | D << 32):
+ *     8 instead of 12 bytes per cell, written once with 128-bit stores, never read by the forward pass;
+ *   - Lo/Hi are taken on the way; the end test (wfa.go:235-239) and the semi-global start-cell test
+ *     (wfa.go:270-375, early-stop form) are paid by the few cells that can pass them
+ *     -- those that have reached the end of a sequence -- through per-row flags in shared memory.
  * The backtraces run afterwards in their own kernel (wide_finish_kernel: lane-parallel over the
- * pairs of the launch, SlimView on the slots the forward pass left), so no cluster idles while one
- * thread chases pointers.
+ * pairs of the launch; semi-global slots are addressed arithmetically, WideSemiView), so no cluster
+ * idles while one thread chases pointers.  Step-by-step measurements: profiles/r2_wide_cfg4.md.
  *
  * Semantics follow the reference at /root/reference (cited as wfa.go:LINE); the recurrences are
  * next_off3 / next_off of wfa_lane.cuh.
@@ -85,8 +88,8 @@ struct SeqAll {
 };
 
 /* Forward pass of one pair by the whole cluster: wfa.go:228-251 with next + extend fused per cell.
- * Every thread of every CTA keeps the same row bookkeeping in registers (the reductions are combined
- * identically everywhere).  Returns what the finish kernel needs (complete in thread 0 of CTA 0, the record keeper).
+ * Every thread of every CTA takes the same decisions (the reductions are combined identically everywhere);
+ * what only the result needs is kept by thread 0 of CTA 0, the record keeper, whose return value is complete.
  *
  * Rows and ranges.  Row si (score si * g) is computed over a range that depends on si alone: all
  * n + m - 1 diagonals for semi-global alignment (the init cells span them, wfa.go:160-183), [-si, si]
