@@ -1,11 +1,10 @@
 #!/bin/bash
-# LANE class pass: parity (lane tests, fixtures, edge cases), config-2 bench with and without the staged finish
+# LANE class pass: parity (lane tests, fixtures, edge cases), staged-run check, config-2 bench
 cd "$(dirname "$0")/.."
 TAG=${1:-l1}; OUT=gpurun_out/$TAG; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -q -x -k "lane or random_small or fixture or edge or cfg2 or readme or errors or context or multi" > $OUT/pytest.log 2>&1; echo "exit $?" >> $OUT/pytest.log; tail -3 $OUT/pytest.log
 timeout 300 python scripts/staged_check.py 200000 > $OUT/staged_check.log 2>&1; tail -2 $OUT/staged_check.log
-for v in staged serial; do
-if [ $v == serial ]; then export WFACUDA_LANE_SERIAL_FINISH=1; else unset WFACUDA_LANE_SERIAL_FINISH; fi
+for v in run; do
 timeout 600 python bench.py --steps 5 --warmup 3 --only-headline --no-cpu-baseline > $OUT/bench_cfg2_$v.json 2> $OUT/bench_cfg2_$v.err
 python - <<PY
 import json
