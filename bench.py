@@ -487,6 +487,11 @@ def main():
         barrier()
     # ---- the library's own multi-GPU entry from ONE process (rank 0 drives all devices, the other ranks wait)
     if world > 1 and not args.only_headline and not args.pairs:
+        # the waiting ranks wait on the CPU (a gloo group): an NCCL barrier would keep a spinning kernel on every other
+        # rank's GPU -- the devices rank 0 is about to drive (measured at N = 2: 530 ms per config-5 call with the NCCL
+        # barrier, 250-290 ms for the same call from a process of its own)
+        cpu_group = dist.new_group(backend="gloo")
+        torch.cuda.empty_cache()
         if rank == 0:
             try:
                 c5 = "cfg5_100kbp_e15_global_adaptive"
@@ -495,7 +500,7 @@ def main():
                     "cfg2": multi_entry(api, "cfg2_150bp_e5_global", 1_000_000 * world, world, 5)}
             except Exception as e:
                 line["multi_entry"] = {"error": str(e)[:300]}
-        barrier()
+        dist.barrier(group=cpu_group)
     if rank == 0:
         emit(line)
     if world > 1:
