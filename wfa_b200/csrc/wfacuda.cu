@@ -1353,7 +1353,7 @@ wfacuda_batch *wfacuda_batch_upload(wfacuda_ctx *ctx, uint64_t n_pairs, const ui
          * queries then all targets cut into chunks, windows into one shared reference, the runs of a
          * multi-GPU shard) that range would be most of the pool for every chunk: gather them into a
          * page-locked pool of the ctx instead and address that. */
-        const bool gather = hi - base > 2 * sum_len + (1u << 20);
+        const bool gather = hi - base > sum_len + sum_len / 2 + (1u << 18);          /* (an interleaved pool with padded pairs stays below 1.5x) */
         const uint8_t *src = seq_bytes;
         if (gather) {
             if (ctx->pin_pool_cap < sum_len + 64) {
@@ -1981,10 +1981,18 @@ int wfacuda_align_batch(wfacuda_ctx *ctx, uint64_t n_pairs, const uint8_t *seq_b
         return rc;
     }
     /* chunk size: about 20 MB of sequence (0.45 ms of PCIe; ~one full wave of the LANE kernel for 150 bp reads), at least kMinChunk pairs */
-    /* pageable caller memory is staged by the workers themselves (host memcpy, memory-bound):
-     * fewer, larger chunks there */
+    /* Pageable (or scattered: per-pair heap strings) caller memory is staged by the workers themselves -- a host copy
+     * into their page-locked pools before the chunk can be uploaded.  All workers stage at once and share the host's
+     * memory bandwidth, so with one chunk per worker every chunk is ready at about the same time and the uploads, which
+     * go out in chunk order, only start when the staging is over (the reference's call shape: first full chunk uploaded
+     * at 9.5 ms of 16.9).  Smaller chunks, several per worker, finish their staging in chunk order and the uploads
+     * overlap the staging of the later ones: a dense pageable pool 48 -> 72-82 M alignments/s on config 2, per-pair
+     * heap strings 18.5 -> 17.2 ms per million pairs (those are bound by the per-string copies themselves).  Letting
+     * only a few workers stage at a time, in chunk order, was tried on top and changed nothing measurable. */
     const bool src_pinned = is_pinned(seq_bytes);
-    uint64_t chunk_pairs = std::max<uint64_t>(kMinChunk, std::min<uint64_t>(262144, (uint64_t)((src_pinned ? 20e6 : 24e6) / mean_bytes)));
+    double chunk_bytes = src_pinned ? 20e6 : 8e6;
+    if (const char *e = getenv("WFACUDA_CHUNK_MB")) chunk_bytes = std::max(1.0, atof(e)) * 1e6;
+    uint64_t chunk_pairs = std::max<uint64_t>(src_pinned ? kMinChunk : kMinChunk / 2, std::min<uint64_t>(262144, (uint64_t)(chunk_bytes / mean_bytes)));
     if (long_pairs) chunk_pairs = std::max<uint64_t>(32, (((n_pairs + 3) / 4 + 31) / 32) * 32);
     if (const char *e = getenv("WFACUDA_CHUNK_PAIRS")) chunk_pairs = std::max<uint64_t>(long_pairs ? 32 : 1024, strtoull(e, nullptr, 10));
     int tail_levels = 2;
